@@ -1,0 +1,176 @@
+/*
+ * smf_hmm.h -- C-ABI of libsmfhmm.so: the B200 (sm_100a) implementation of the smftools
+ * HMM footprinting hot path.
+ *
+ * The reference hot path sits behind a *Python registry* (no FFI):
+ *   /root/reference/src/smftools/hmm/HMM.py:27-54   register_hmm / create_hmm
+ *   /root/reference/src/smftools/hmm/HMM.py:398     class BaseHMM (fit / decode / annotate_adata)
+ * so there is no pre-existing foreign-function table to copy.  Each entry point below
+ * states which reference method body it replaces; the Python host mirror
+ * (smftools_b200/hmm.py) is the only caller and binds these through ctypes
+ * (INTEGRATION.md shows the binding a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types.
+ *   - data buffers (obs, gamma, states, ...) are DEVICE pointers unless a name ends in
+ *     `_host`; the small model tables are HOST pointers (they are copied into the kernel
+ *     parameter space, no hidden device allocation).
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), allocates
+ *     nothing, keeps no global state, and returns SMF_OK or a negative error code.
+ *   - caller-owned workspaces: ask smf_hmm_workspace_bytes() first.
+ */
+#ifndef SMF_HMM_H
+#define SMF_HMM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMF_HMM_ABI_VERSION 1
+
+#define SMF_MAX_STATES 4
+#define SMF_MAX_CHANNELS 4
+#define SMF_MAX_BINS 16
+
+/* error codes (mapped to ValueError / RuntimeError by the Python shim) */
+#define SMF_OK 0
+#define SMF_ERR_BAD_ARG (-1)      /* NULL / negative size / unsupported K, C, dtype   -> ValueError   */
+#define SMF_ERR_TOO_LONG (-2)     /* one read does not fit the on-chip staging        -> ValueError   */
+#define SMF_ERR_WORKSPACE (-3)    /* workspace too small                              -> ValueError   */
+#define SMF_ERR_CUDA (-4)         /* a CUDA runtime call / launch failed              -> RuntimeError */
+#define SMF_ERR_ALIGN (-5)        /* pointer not aligned as required                  -> ValueError   */
+
+/* observation element types (obs_dtype) */
+#define SMF_OBS_F32 0 /* float,  NaN = missing  (HMM.py:707-708 nan_to_num + ~isnan)       */
+#define SMF_OBS_F64 1 /* double, NaN = missing  (the reference's own host dtype)           */
+#define SMF_OBS_U8 2  /* uint8 binary code: 0, 1, anything else = missing                  */
+
+/* operations for smf_hmm_workspace_bytes() */
+#define SMF_OP_POSTERIOR 0
+#define SMF_OP_VITERBI 1
+#define SMF_OP_ESTEP 2
+#define SMF_OP_FEATURES 3
+
+/*
+ * Model tables in the log domain, exactly the quantities the reference forms at the top
+ * of every pass (HMM.py:593-595, 1494-1496, 1773-1775, 2149-2150):
+ *   log_start[k]        = log(start[k] + eps)
+ *   log_trans[b][i][j]  = log(trans_by_bin[b][i][j] + eps)      (n_bins == 1: trans)
+ *   log_emit1[k][c]     = log(emission[k][c] + eps)
+ *   log_emit0[k][c]     = log1p(-emission[k][c] + eps)
+ * The host mirror computes them with the same torch ops as the reference so the Viterbi
+ * kernel (which works on these doubles directly) reproduces its decisions bit for bit.
+ */
+typedef struct smf_hmm_tables {
+  int32_t n_states;   /* K in [2, SMF_MAX_STATES]   */
+  int32_t n_channels; /* C in [1, SMF_MAX_CHANNELS] */
+  int32_t n_bins;     /* 1 (homogeneous) .. SMF_MAX_BINS (distance-binned, HMM.py:2115-2125) */
+  int32_t reserved;
+  const double* log_start; /* host [K]          */
+  const double* log_trans; /* host [n_bins,K,K] */
+  const double* log_emit1; /* host [K,C]        */
+  const double* log_emit0; /* host [K,C]        */
+} smf_hmm_tables;
+
+int smf_hmm_abi_version(void);
+const char* smf_hmm_strerror(int code);
+
+/* Bytes of caller-owned device workspace an operation needs (0 = none). */
+size_t smf_hmm_workspace_bytes(int op, const smf_hmm_tables* tab, int64_t n_reads, int64_t n_pos);
+
+/* Longest read (positions) the fused on-chip posterior / E-step kernel accepts for this model. */
+int64_t smf_hmm_max_positions(const smf_hmm_tables* tab, int want_all_states);
+
+/*
+ * Posterior decode.  Replaces BaseHMM._alpha_beta + _forward_backward + argmax
+ * (HMM.py:572-629, 718; distance-binned variant 2127-2188).
+ *   obs         device [N, L, C] of obs_dtype
+ *   bins        device int8 [L-1] distance-bin index per step, or NULL when n_bins == 1
+ *   gamma       device float [N, L, K] (gamma_state < 0) or [N, L] holding state `gamma_state`; may be NULL
+ *   states      device int8 [N, L] = argmax_k gamma (first maximum), may be NULL
+ *   loglik      device double [N] = log P(read), may be NULL
+ */
+int smf_hmm_posterior(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int64_t n_reads,
+                      int64_t n_pos, const int8_t* bins, float* gamma, int gamma_state,
+                      int8_t* states, double* loglik, void* stream);
+
+/*
+ * Viterbi decode.  Replaces BaseHMM._viterbi (HMM.py:631-671; binned 2190-2236).
+ *   states      device int8 [N, L]
+ *   workspace   device scratch of smf_hmm_workspace_bytes(SMF_OP_VITERBI, ...) bytes
+ *               (packed back-pointers, one byte per read-position)
+ */
+int smf_hmm_viterbi(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int64_t n_reads,
+                    int64_t n_pos, const int8_t* bins, int8_t* states, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/*
+ * Baum-Welch E-step.  Replaces the body of fit_em between the forward-backward pass and the
+ * M-step (HMM.py:1566-1596; multi 1849-1882; binned 2289-2320).
+ *   stats       device double [smf_hmm_stats_len(tab)] =
+ *               [ start_acc K | trans_acc n_bins*K*K | emit_num K*C | emit_den K*C | loglik 1 ]
+ *               (overwritten; reduced in a fixed order => run-to-run deterministic)
+ *   workspace   device scratch of smf_hmm_workspace_bytes(SMF_OP_ESTEP, ...) bytes
+ */
+int64_t smf_hmm_stats_len(const smf_hmm_tables* tab);
+int smf_hmm_estep(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int64_t n_reads,
+                  int64_t n_pos, const int8_t* bins, double* stats, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
+/*
+ * Footprint / feature calling on decoded reads.  Replaces the per-read Python loops of
+ * BaseHMM.annotate_adata (HMM.py:1318-1370) for one feature group:
+ *   membership[n,t] = states[n,t] == target            (post == NULL, Viterbi mode)
+ *                   = post[n,t] >= threshold           (post != NULL, marginal mode)
+ *   every run [s,e) of membership gets genomic length coords[e-1]-coords[s]+1, the first
+ *   size class with lo <= len < hi, and is span-filled into the full grid columns
+ *   [left[s], right[e-1]) (searchsorted left/right of the site coordinate in the full grid,
+ *   precomputed on the host: HMM.py:1344-1345).
+ * The kernel requires the site coordinates to be strictly increasing and present in the
+ * (sorted) full grid, which makes the span-filled runs pairwise disjoint and non-abutting, so
+ * the run length of a cell is the same in the all_{group}_features layer and in its class
+ * layer (HMM.py:1361-1370); the host mirror checks this and otherwise uses its own slow path.
+ * Outputs (all device, row-major [N, V]):
+ *   class_out   uint8: 0 = no feature, c+1 = size class c       (dense "which layer is 1")
+ *   run_len     int32: run length in grid columns of the run covering the cell, else 0; may be NULL
+ *   intervals   int32 [max_intervals,4] = (read, grid_start, grid_end, class) compacted runs; may be NULL
+ *   n_intervals device uint64 counter (zeroed by the caller); total runs found, may exceed max_intervals
+ */
+int smf_hmm_call_features(const int8_t* states, const float* post, int target_state,
+                          float threshold, int64_t n_reads, int64_t n_pos,
+                          const int64_t* coords, const int32_t* grid_left,
+                          const int32_t* grid_right, int64_t n_grid, const double* class_lo_host,
+                          const double* class_hi_host, int n_classes, uint8_t* class_out,
+                          int32_t* run_len, int32_t* intervals, int64_t max_intervals,
+                          unsigned long long* n_intervals, void* stream);
+
+/*
+ * Merge adjacent runs of a binary layer when the coordinate gap is <= distance_threshold and
+ * (optionally) re-bin the merged runs into size classes.  Replaces
+ * BaseHMM.merge_intervals_to_new_layer + write_size_class_layers_from_binary
+ * (HMM.py:1006-1123).  layer is uint8 [N, V] (non-zero = member); coords int64 [V].
+ *   merged      uint8 [N, V]; merged_len int32 [N, V]
+ *   class_out / len_cls as in smf_hmm_call_features (may be NULL when n_classes == 0)
+ */
+int smf_hmm_merge_runs(const uint8_t* layer, int64_t n_reads, int64_t n_grid,
+                       const int64_t* coords, int coords_are_ints, int64_t distance_threshold,
+                       uint8_t* merged, int32_t* merged_len, const double* class_lo_host,
+                       const double* class_hi_host, int n_classes, uint8_t* class_out,
+                       int32_t* len_cls, void* stream);
+
+/*
+ * Read-span masking.  Replaces mask_layers_outside_read_span (HMM.py:148-231):
+ *   valid_out[n,v] = covered[n,v] != 0                          (covered != NULL)
+ *                  = !(coords[v] < start[n] || coords[v] > end[n])  (non-finite start/end => all valid)
+ */
+int smf_hmm_span_mask(const uint8_t* covered, const int64_t* coords, const double* read_start,
+                      const double* read_end, int64_t n_reads, int64_t n_grid, uint8_t* valid_out,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMF_HMM_H */

@@ -1,0 +1,62 @@
+"""Load the UNMODIFIED reference HMM module from /root/reference (container only).
+
+TEST INFRASTRUCTURE -- never imported by the product package.
+
+``import smftools`` fails in this image (``smftools/__init__.py`` pulls in anndata), but
+``smftools/hmm/HMM.py`` itself only needs numpy / scipy.sparse / torch and three light
+helper modules (``HMM.py:8-13``).  Registering empty parent packages whose ``__path__``
+points at the reference tree lets ``import smftools.hmm.HMM`` run the reference class
+unmodified.
+
+``/root/reference`` does not exist on the GPU box: only ``oracle/make_golden.py`` and
+the container-only cross-check tests call :func:`load_reference_hmm`.
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+import types
+
+REFERENCE_SRC = os.environ.get("SMF_REFERENCE_SRC", "/root/reference/src")
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_SRC, "smftools", "hmm", "HMM.py"))
+
+
+def load_reference_hmm():
+    """Return the reference ``smftools.hmm.HMM`` module (imported once, cached)."""
+    if "smftools.hmm.HMM" in sys.modules and getattr(
+        sys.modules["smftools.hmm.HMM"], "__smf_reference__", False
+    ):
+        return sys.modules["smftools.hmm.HMM"]
+    if not reference_available():
+        raise FileNotFoundError(f"reference tree not found under {REFERENCE_SRC}")
+    root = os.path.join(REFERENCE_SRC, "smftools")
+    pkg = types.ModuleType("smftools")
+    pkg.__path__ = [root]
+    sub = types.ModuleType("smftools.hmm")
+    sub.__path__ = [os.path.join(root, "hmm")]
+    sys.modules["smftools"] = pkg
+    sys.modules["smftools.hmm"] = sub
+    mod = importlib.import_module("smftools.hmm.HMM")
+    mod.__smf_reference__ = True
+    return mod
+
+
+class DuckAnnData:
+    """Minimal stand-in for AnnData (the reference only touches these attributes)."""
+
+    def __init__(self, n_obs, var_names, obs=None, var=None):
+        import pandas as pd
+
+        self.var_names = pd.Index([str(v) for v in var_names])
+        self.n_obs = int(n_obs)
+        self.n_vars = len(self.var_names)
+        self.shape = (self.n_obs, self.n_vars)
+        self.layers = {}
+        self.uns = {}
+        self.obs = obs if obs is not None else pd.DataFrame(index=[f"r{i}" for i in range(n_obs)])
+        self.var = var if var is not None else pd.DataFrame(index=self.var_names)
+        self.obs_names = self.obs.index

@@ -1,0 +1,18 @@
+"""smftools_b200 -- B200-native (sm_100a) implementation of the smftools HMM footprinting hot path.
+
+Public surface mirrors ``smftools.hmm.HMM`` of the reference (see ``smftools_b200/hmm.py``).
+"""
+from .hmm import (  # noqa: F401
+    HMM,
+    BaseHMM,
+    DistanceBinnedSingleBernoulliHMM,
+    MultiBernoulliHMM,
+    SingleBernoulliHMM,
+    create_hmm,
+    install_into_reference,
+    mask_layers_outside_read_span,
+    normalize_hmm_feature_sets,
+    register_hmm,
+)
+
+__version__ = "0.1.0"

@@ -1,0 +1,151 @@
+"""ctypes binding of ``libsmfhmm.so`` (the C-ABI declared in ``include/smf_hmm.h``).
+
+The product path has no CPU fallback: if the shared library is missing, or a compute entry
+point is called without a CUDA device, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsmfhmm.so")
+
+SMF_OK = 0
+SMF_ERR_BAD_ARG = -1
+SMF_ERR_TOO_LONG = -2
+SMF_ERR_WORKSPACE = -3
+SMF_ERR_CUDA = -4
+SMF_ERR_ALIGN = -5
+
+OBS_F32, OBS_F64, OBS_U8 = 0, 1, 2
+OP_POSTERIOR, OP_VITERBI, OP_ESTEP, OP_FEATURES = 0, 1, 2, 3
+MAX_STATES, MAX_CHANNELS, MAX_BINS = 4, 4, 16
+
+EXPORTS = (
+    "smf_hmm_abi_version",
+    "smf_hmm_strerror",
+    "smf_hmm_workspace_bytes",
+    "smf_hmm_max_positions",
+    "smf_hmm_posterior",
+    "smf_hmm_viterbi",
+    "smf_hmm_stats_len",
+    "smf_hmm_estep",
+    "smf_hmm_call_features",
+    "smf_hmm_merge_runs",
+    "smf_hmm_span_mask",
+)
+
+
+class Tables(ctypes.Structure):
+    """Mirror of ``smf_hmm_tables``."""
+
+    _fields_ = [
+        ("n_states", c_int32),
+        ("n_channels", c_int32),
+        ("n_bins", c_int32),
+        ("reserved", c_int32),
+        ("log_start", POINTER(c_double)),
+        ("log_trans", POINTER(c_double)),
+        ("log_emit1", POINTER(c_double)),
+        ("log_emit0", POINTER(c_double)),
+    ]
+
+
+class HostTables:
+    """Owns the fp64 host arrays a ``Tables`` struct points at."""
+
+    def __init__(self, log_start, log_trans, log_emit1, log_emit0):
+        self.log_start = np.ascontiguousarray(log_start, dtype=np.float64).reshape(-1)
+        K = self.log_start.shape[0]
+        self.log_trans = np.ascontiguousarray(log_trans, dtype=np.float64).reshape(-1, K, K)
+        self.log_emit1 = np.ascontiguousarray(log_emit1, dtype=np.float64).reshape(K, -1)
+        self.log_emit0 = np.ascontiguousarray(log_emit0, dtype=np.float64).reshape(K, -1)
+        self.K = K
+        self.C = self.log_emit1.shape[1]
+        self.n_bins = self.log_trans.shape[0]
+        dp = POINTER(c_double)
+        self.struct = Tables(
+            self.K,
+            self.C,
+            self.n_bins,
+            0,
+            self.log_start.ctypes.data_as(dp),
+            self.log_trans.ctypes.data_as(dp),
+            self.log_emit1.ctypes.data_as(dp),
+            self.log_emit0.ctypes.data_as(dp),
+        )
+
+    @property
+    def ref(self):
+        return ctypes.byref(self.struct)
+
+
+_lib = None
+
+
+def library_built() -> bool:
+    return os.path.isfile(LIB_PATH)
+
+
+def load():
+    """Load libsmfhmm.so (once).  Raises if it has not been built -- there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not library_built():
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `python -m smftools_b200.build`). smftools_b200 has no CPU fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    T = POINTER(Tables)
+    lib.smf_hmm_abi_version.restype = c_int
+    lib.smf_hmm_abi_version.argtypes = []
+    lib.smf_hmm_strerror.restype = c_char_p
+    lib.smf_hmm_strerror.argtypes = [c_int]
+    lib.smf_hmm_workspace_bytes.restype = c_size_t
+    lib.smf_hmm_workspace_bytes.argtypes = [c_int, T, c_int64, c_int64]
+    lib.smf_hmm_max_positions.restype = c_int64
+    lib.smf_hmm_max_positions.argtypes = [T, c_int]
+    lib.smf_hmm_stats_len.restype = c_int64
+    lib.smf_hmm_stats_len.argtypes = [T]
+    lib.smf_hmm_posterior.restype = c_int
+    lib.smf_hmm_posterior.argtypes = [T, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int,
+                                      c_void_p, c_void_p, c_void_p]
+    lib.smf_hmm_viterbi.restype = c_int
+    lib.smf_hmm_viterbi.argtypes = [T, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                    c_size_t, c_void_p]
+    lib.smf_hmm_estep.restype = c_int
+    lib.smf_hmm_estep.argtypes = [T, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                  c_size_t, c_void_p]
+    lib.smf_hmm_call_features.restype = c_int
+    lib.smf_hmm_call_features.argtypes = [c_void_p, c_void_p, c_int, c_float, c_int64, c_int64, c_void_p,
+                                          c_void_p, c_void_p, c_int64, POINTER(c_double), POINTER(c_double),
+                                          c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
+    lib.smf_hmm_merge_runs.restype = c_int
+    lib.smf_hmm_merge_runs.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_int, c_int64, c_void_p,
+                                       c_void_p, POINTER(c_double), POINTER(c_double), c_int, c_void_p,
+                                       c_void_p, c_void_p]
+    lib.smf_hmm_span_mask.restype = c_int
+    lib.smf_hmm_span_mask.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p,
+                                      c_void_p]
+    if lib.smf_hmm_abi_version() != 1:
+        raise RuntimeError("libsmfhmm.so ABI version mismatch; rebuild the extension")
+    _lib = lib
+    return lib
+
+
+def check(code: int, what: str = "") -> None:
+    """Map a C-ABI status to the reference's exception conventions."""
+    if code == SMF_OK:
+        return
+    msg = load().smf_hmm_strerror(code).decode()
+    if what:
+        msg = f"{what}: {msg}"
+    if code in (SMF_ERR_BAD_ARG, SMF_ERR_TOO_LONG, SMF_ERR_WORKSPACE, SMF_ERR_ALIGN):
+        raise ValueError(msg)
+    raise RuntimeError(msg)

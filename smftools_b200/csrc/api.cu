@@ -1,0 +1,555 @@
+// C-ABI of libsmfhmm.so (see include/smf_hmm.h): argument checks, table conversion,
+// launch-shape selection and kernel launches.  No torch, no allocation, no global state
+// other than cached device attributes.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <type_traits>
+
+#include "fb_kernel.cuh"
+#include "features_kernel.cuh"
+#include "smf_hmm.h"
+#include "viterbi_kernel.cuh"
+
+namespace smf {
+
+struct DeviceInfo {
+  int device = -1;
+  int num_sms = 0;
+  int max_smem_optin = 0;
+};
+
+static int get_device_info(DeviceInfo* out) {
+  static DeviceInfo cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return SMF_ERR_CUDA;
+  if (cache[dev].device != dev) {
+    DeviceInfo d;
+    d.device = dev;
+    if (cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      return SMF_ERR_CUDA;
+    if (cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) !=
+        cudaSuccess)
+      return SMF_ERR_CUDA;
+    cache[dev] = d;
+  }
+  *out = cache[dev];
+  return SMF_OK;
+}
+
+static int check_tables(const smf_hmm_tables* t) {
+  if (t == nullptr) return SMF_ERR_BAD_ARG;
+  if (t->n_states < 2 || t->n_states > kMaxK) return SMF_ERR_BAD_ARG;
+  if (t->n_channels < 1 || t->n_channels > kMaxC) return SMF_ERR_BAD_ARG;
+  if (t->n_bins < 1 || t->n_bins > kMaxB) return SMF_ERR_BAD_ARG;
+  if (!t->log_start || !t->log_trans || !t->log_emit1 || !t->log_emit0) return SMF_ERR_BAD_ARG;
+  return SMF_OK;
+}
+
+template <int K>
+static void build_fb_tables(const smf_hmm_tables* t, FbTables<K>* out) {
+  memset(out, 0, sizeof(*out));
+  const int C = t->n_channels;
+  const double log2e = 1.4426950408889634074;
+  double pisum = 0.0;
+  for (int k = 0; k < K; ++k) {
+    const double p = exp(t->log_start[k]);
+    out->pi[k] = (float)p;
+    pisum += (double)out->pi[k];
+  }
+  out->log_pi_sum = log(pisum);
+  for (int b = 0; b < t->n_bins; ++b)
+    for (int i = 0; i < K; ++i)
+      for (int j = 0; j < K; ++j) out->A[b][i][j] = (float)exp(t->log_trans[(b * K + i) * K + j]);
+  for (int c = 0; c < C; ++c) {
+    const double l0_0 = t->log_emit0[0 * C + c];
+    const double d_0 = t->log_emit1[0 * C + c] - l0_0;
+    out->l00[c] = l0_0;
+    out->dl0[c] = d_0;
+    for (int k = 0; k < K; ++k) {
+      const double l0 = t->log_emit0[k * C + c];
+      const double d = t->log_emit1[k * C + c] - l0;
+      out->rl0[k][c] = (float)((l0 - l0_0) * log2e);
+      out->rdl[k][c] = (float)((d - d_0) * log2e);
+    }
+  }
+  out->nb = t->n_bins;
+  out->C = C;
+}
+
+template <int K>
+static void build_vit_tables(const smf_hmm_tables* t, VitTables<K>* out) {
+  memset(out, 0, sizeof(*out));
+  const int C = t->n_channels;
+  for (int k = 0; k < K; ++k) out->log_pi[k] = t->log_start[k];
+  for (int b = 0; b < t->n_bins; ++b)
+    for (int i = 0; i < K; ++i)
+      for (int j = 0; j < K; ++j) out->logA[b][i][j] = t->log_trans[(b * K + i) * K + j];
+  for (int k = 0; k < K; ++k)
+    for (int c = 0; c < C; ++c) {
+      out->l1[k][c] = t->log_emit1[k * C + c];
+      out->l0[k][c] = t->log_emit0[k * C + c];
+    }
+  out->nb = t->n_bins;
+  out->C = C;
+}
+
+static inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
+
+// Threads a group may use for a given model / mode (register budget; matches launch bounds).
+static int fb_max_threads(int K, bool stats) {
+  if (stats) return K == 2 ? 640 : (K == 3 ? 512 : 384);
+  return K == 4 ? 512 : 640;
+}
+
+struct FbPlan {
+  int T, chunk, groups, smem, block;
+};
+
+// Launch-shape selection for the fused forward-backward kernel.
+static int plan_fb(int K, int C, int nb, int64_t L64, bool stats, int S, int max_smem, FbArgs* a,
+                   FbPlan* plan) {
+  if (L64 < 1 || L64 > (1 << 24)) return SMF_ERR_TOO_LONG;
+  const int L = (int)L64;
+  const int maxT = fb_max_threads(K, stats);
+  int T = align_up((L + 16) / 17, 32);
+  if (T > maxT) T = maxT;
+  if (T < 32) T = 32;
+  int chunk = (L + T - 1) / T;
+  if ((chunk & 1) == 0) ++chunk;
+  T = align_up((L + chunk - 1) / chunk, 32);
+  const int KK = K * K;
+  const int in_b = align_up(L * C * 4, 16);
+  const int stage_b = align_up(L * K * 4, 16);
+  const int st_b = align_up(L + 16, 16);
+  const int scan_b = align_up(32 * (KK + 2 * K) * 4 + 32 * 8, 16);
+  const int group_bytes = in_b + stage_b + st_b + scan_b;
+  int groups = 256 / T;
+  if (groups < 1) groups = 1;
+  if (groups > 8) groups = 8;
+  const bool binned = nb > 1;
+  for (;; --groups) {
+    const int warps = groups * T / 32;
+    const int bins_b = binned ? align_up(L, 16) : 0;
+    const int sA_b = binned ? align_up(nb * KK * 4, 16) : 0;
+    const int wacc_b = stats ? align_up(warps * S * 8, 16) : 0;
+    const int total = bins_b + sA_b + wacc_b + groups * group_bytes;
+    if (total <= max_smem) {
+      a->off_bins = 0;
+      a->off_sA = bins_b;
+      a->off_wacc = bins_b + sA_b;
+      a->off_group0 = bins_b + sA_b + wacc_b;
+      a->group_bytes = group_bytes;
+      a->goff_in = 0;
+      a->goff_stage = in_b;
+      a->goff_st = in_b + stage_b;
+      a->goff_scan = in_b + stage_b + st_b;
+      a->chunk = chunk;
+      a->T = T;
+      a->groups = groups;
+      plan->T = T;
+      plan->chunk = chunk;
+      plan->groups = groups;
+      plan->smem = total;
+      plan->block = T * groups;
+      return SMF_OK;
+    }
+    if (groups == 1) return SMF_ERR_TOO_LONG;
+  }
+}
+
+template <int K, bool MULTI, bool BINNED, bool STATS>
+static int launch_fb_t(const smf_hmm_tables* t, FbArgs& a, const FbPlan& plan, const DeviceInfo& di,
+                       int* nblocks_out, cudaStream_t stream) {
+  constexpr int MAXT = STATS ? (K == 2 ? 640 : (K == 3 ? 512 : 384)) : (K == 4 ? 512 : 640);
+  FbTables<K> tab;
+  build_fb_tables<K>(t, &tab);
+  auto kern = fb_kernel<K, MULTI, BINNED, STATS, MAXT>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem) != cudaSuccess)
+    return SMF_ERR_CUDA;
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, plan.block, plan.smem) != cudaSuccess)
+    return SMF_ERR_CUDA;
+  if (occ < 1) return SMF_ERR_CUDA;
+  long long want = (a.N + plan.groups - 1) / plan.groups;
+  long long cap = (long long)di.num_sms * occ;
+  int nblocks = (int)(want < cap ? want : cap);
+  if (nblocks < 1) nblocks = 1;
+  if (nblocks_out) {
+    if (*nblocks_out > 0 && nblocks > *nblocks_out) nblocks = *nblocks_out;  // workspace cap
+    *nblocks_out = nblocks;
+  }
+  kern<<<nblocks, plan.block, plan.smem, stream>>>(tab, a);
+  return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
+}
+
+template <int K, bool STATS>
+static int launch_fb_k(const smf_hmm_tables* t, FbArgs& a, const FbPlan& plan, const DeviceInfo& di,
+                       int* nblocks, cudaStream_t stream) {
+  const bool multi = t->n_channels > 1;
+  const bool binned = t->n_bins > 1;
+  if (multi && binned) return launch_fb_t<K, true, true, STATS>(t, a, plan, di, nblocks, stream);
+  if (multi) return launch_fb_t<K, true, false, STATS>(t, a, plan, di, nblocks, stream);
+  if (binned) return launch_fb_t<K, false, true, STATS>(t, a, plan, di, nblocks, stream);
+  return launch_fb_t<K, false, false, STATS>(t, a, plan, di, nblocks, stream);
+}
+
+template <bool STATS>
+static int launch_fb(const smf_hmm_tables* t, FbArgs& a, const FbPlan& plan, const DeviceInfo& di,
+                     int* nblocks, cudaStream_t stream) {
+  switch (t->n_states) {
+    case 2: return launch_fb_k<2, STATS>(t, a, plan, di, nblocks, stream);
+    case 3: return launch_fb_k<3, STATS>(t, a, plan, di, nblocks, stream);
+    case 4: return launch_fb_k<4, STATS>(t, a, plan, di, nblocks, stream);
+  }
+  return SMF_ERR_BAD_ARG;
+}
+
+static int stats_len(const smf_hmm_tables* t) {
+  const int K = t->n_states, C = t->n_channels;
+  return K + t->n_bins * K * K + 2 * K * C + 1;
+}
+
+// E-step workspace: per-CTA partial statistics, for at most this many CTAs.
+static const int kMaxEstepBlocks = 148 * 8;
+
+template <int K, bool MULTI, bool BINNED>
+static int launch_vit_t(const smf_hmm_tables* t, const VitArgs& a, bool wide, const DeviceInfo& di,
+                        cudaStream_t stream) {
+  VitTables<K> tab;
+  build_vit_tables<K>(t, &tab);
+  const int C = a.C;
+  const int row_stride = (kVitTile * C) | 1;
+  const size_t elem = wide ? 8 : 4;
+  const size_t smem = (size_t)kVitReads * row_stride * elem + (size_t)kVitReads * (kVitTile + 4) +
+                      (BINNED ? (size_t)align_up(a.L, 16) : 0);
+  if ((long long)smem > di.max_smem_optin) return SMF_ERR_TOO_LONG;
+  const long long nblk = (a.N + kVitReads - 1) / kVitReads;
+  if (nblk > 0x7fffffffLL) return SMF_ERR_BAD_ARG;
+  cudaError_t e;
+  if (wide) {
+    auto kern = viterbi_kernel<K, MULTI, BINNED, true>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return SMF_ERR_CUDA;
+    kern<<<(int)nblk, kVitReads, smem, stream>>>(tab, a);
+  } else {
+    auto kern = viterbi_kernel<K, MULTI, BINNED, false>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return SMF_ERR_CUDA;
+    kern<<<(int)nblk, kVitReads, smem, stream>>>(tab, a);
+  }
+  return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
+}
+
+template <int K>
+static int launch_vit_k(const smf_hmm_tables* t, const VitArgs& a, bool wide, const DeviceInfo& di,
+                        cudaStream_t stream) {
+  const bool multi = t->n_channels > 1;
+  const bool binned = t->n_bins > 1;
+  if (multi && binned) return launch_vit_t<K, true, true>(t, a, wide, di, stream);
+  if (multi) return launch_vit_t<K, true, false>(t, a, wide, di, stream);
+  if (binned) return launch_vit_t<K, false, true>(t, a, wide, di, stream);
+  return launch_vit_t<K, false, false>(t, a, wide, di, stream);
+}
+
+static int fill_class_table(const double* lo, const double* hi, int n, ClassTable* ct) {
+  if (n < 0 || n > kMaxClasses) return SMF_ERR_BAD_ARG;
+  if (n > 0 && (!lo || !hi)) return SMF_ERR_BAD_ARG;
+  memset(ct, 0, sizeof(*ct));
+  for (int i = 0; i < n; ++i) {
+    ct->lo[i] = lo[i];
+    ct->hi[i] = hi[i];
+  }
+  ct->n = n;
+  return SMF_OK;
+}
+
+}  // namespace smf
+
+using namespace smf;
+
+extern "C" {
+
+int smf_hmm_abi_version(void) { return SMF_HMM_ABI_VERSION; }
+
+const char* smf_hmm_strerror(int code) {
+  switch (code) {
+    case SMF_OK: return "ok";
+    case SMF_ERR_BAD_ARG: return "bad argument (null pointer, negative size, or unsupported K/C/bins/dtype)";
+    case SMF_ERR_TOO_LONG: return "read too long for the on-chip staging of this kernel";
+    case SMF_ERR_WORKSPACE: return "workspace too small";
+    case SMF_ERR_CUDA: return "CUDA runtime error";
+    case SMF_ERR_ALIGN: return "pointer alignment";
+  }
+  return "unknown error";
+}
+
+int64_t smf_hmm_stats_len(const smf_hmm_tables* tab) {
+  if (check_tables(tab) != SMF_OK) return -1;
+  return stats_len(tab);
+}
+
+size_t smf_hmm_workspace_bytes(int op, const smf_hmm_tables* tab, int64_t n_reads, int64_t n_pos) {
+  if (n_reads < 0 || n_pos < 0) return 0;
+  switch (op) {
+    case SMF_OP_VITERBI: return (size_t)n_reads * (size_t)n_pos;
+    case SMF_OP_ESTEP:
+      if (check_tables(tab) != SMF_OK) return 0;
+      return (size_t)kMaxEstepBlocks * (size_t)stats_len(tab) * sizeof(double);
+    default: return 0;
+  }
+}
+
+int64_t smf_hmm_max_positions(const smf_hmm_tables* tab, int want_all_states) {
+  (void)want_all_states;
+  if (check_tables(tab) != SMF_OK) return -1;
+  DeviceInfo di;
+  int max_smem = 232448;
+  if (get_device_info(&di) == SMF_OK) max_smem = di.max_smem_optin;
+  int64_t lo = 1, hi = 1 << 20;
+  FbArgs a;
+  FbPlan p;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi + 1) / 2;
+    if (plan_fb(tab->n_states, tab->n_channels, tab->n_bins, mid, false, stats_len(tab), max_smem, &a, &p) ==
+        SMF_OK)
+      lo = mid;
+    else
+      hi = mid - 1;
+  }
+  return lo;
+}
+
+int smf_hmm_posterior(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int64_t n_reads,
+                      int64_t n_pos, const int8_t* bins, float* gamma, int gamma_state,
+                      int8_t* states, double* loglik, void* stream) {
+  int rc = check_tables(tab);
+  if (rc != SMF_OK) return rc;
+  if (n_reads < 0 || n_pos < 0) return SMF_ERR_BAD_ARG;
+  if (n_reads == 0 || n_pos == 0) return SMF_OK;
+  if (obs == nullptr) return SMF_ERR_BAD_ARG;
+  if (obs_dtype < SMF_OBS_F32 || obs_dtype > SMF_OBS_U8) return SMF_ERR_BAD_ARG;
+  if (tab->n_bins > 1 && n_pos > 1 && bins == nullptr) return SMF_ERR_BAD_ARG;
+  if (gamma_state >= tab->n_states) return SMF_ERR_BAD_ARG;
+  DeviceInfo di;
+  rc = get_device_info(&di);
+  if (rc != SMF_OK) return rc;
+  FbArgs a;
+  memset(&a, 0, sizeof(a));
+  FbPlan plan;
+  rc = plan_fb(tab->n_states, tab->n_channels, tab->n_bins, n_pos, false, stats_len(tab),
+               di.max_smem_optin, &a, &plan);
+  if (rc != SMF_OK) return rc;
+  a.obs = obs;
+  a.obs_dtype = obs_dtype;
+  a.N = n_reads;
+  a.L = (int)n_pos;
+  a.C = tab->n_channels;
+  a.bins = bins;
+  a.gamma = gamma;
+  a.gamma_state = gamma_state;
+  a.states = states;
+  a.loglik = loglik;
+  a.partials = nullptr;
+  a.S = stats_len(tab);
+  a.flush_every = 1;
+  return launch_fb<false>(tab, a, plan, di, nullptr, (cudaStream_t)stream);
+}
+
+int smf_hmm_estep(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int64_t n_reads,
+                  int64_t n_pos, const int8_t* bins, double* stats, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+  int rc = check_tables(tab);
+  if (rc != SMF_OK) return rc;
+  if (n_reads < 0 || n_pos < 0 || stats == nullptr) return SMF_ERR_BAD_ARG;
+  const int S = stats_len(tab);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_reads == 0 || n_pos == 0) {
+    return cudaMemsetAsync(stats, 0, S * sizeof(double), st) == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
+  }
+  if (obs == nullptr || workspace == nullptr) return SMF_ERR_BAD_ARG;
+  if (obs_dtype < SMF_OBS_F32 || obs_dtype > SMF_OBS_U8) return SMF_ERR_BAD_ARG;
+  if (tab->n_bins > 1 && n_pos > 1 && bins == nullptr) return SMF_ERR_BAD_ARG;
+  if (workspace_bytes < smf_hmm_workspace_bytes(SMF_OP_ESTEP, tab, n_reads, n_pos))
+    return SMF_ERR_WORKSPACE;
+  DeviceInfo di;
+  rc = get_device_info(&di);
+  if (rc != SMF_OK) return rc;
+  FbArgs a;
+  memset(&a, 0, sizeof(a));
+  FbPlan plan;
+  rc = plan_fb(tab->n_states, tab->n_channels, tab->n_bins, n_pos, true, S, di.max_smem_optin, &a, &plan);
+  if (rc != SMF_OK) return rc;
+  a.obs = obs;
+  a.obs_dtype = obs_dtype;
+  a.N = n_reads;
+  a.L = (int)n_pos;
+  a.C = tab->n_channels;
+  a.bins = bins;
+  a.gamma = nullptr;
+  a.gamma_state = -1;
+  a.states = nullptr;
+  a.loglik = nullptr;
+  a.partials = reinterpret_cast<double*>(workspace);
+  a.S = S;
+  a.flush_every = 8;
+  int nblocks = kMaxEstepBlocks;
+  rc = launch_fb<true>(tab, a, plan, di, &nblocks, st);
+  if (rc != SMF_OK) return rc;
+  reduce_partials_kernel<<<(S + 127) / 128, 128, 0, st>>>(a.partials, nblocks, S, stats);
+  return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
+}
+
+int smf_hmm_viterbi(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int64_t n_reads,
+                    int64_t n_pos, const int8_t* bins, int8_t* states, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  int rc = check_tables(tab);
+  if (rc != SMF_OK) return rc;
+  if (n_reads < 0 || n_pos < 0) return SMF_ERR_BAD_ARG;
+  if (n_reads == 0 || n_pos == 0) return SMF_OK;
+  if (obs == nullptr || states == nullptr || workspace == nullptr) return SMF_ERR_BAD_ARG;
+  if (obs_dtype < SMF_OBS_F32 || obs_dtype > SMF_OBS_U8) return SMF_ERR_BAD_ARG;
+  if (n_pos > 0x7fffffff) return SMF_ERR_TOO_LONG;
+  if (tab->n_bins > 1 && n_pos > 1 && bins == nullptr) return SMF_ERR_BAD_ARG;
+  if (workspace_bytes < (size_t)n_reads * (size_t)n_pos) return SMF_ERR_WORKSPACE;
+  DeviceInfo di;
+  rc = get_device_info(&di);
+  if (rc != SMF_OK) return rc;
+  VitArgs a;
+  a.obs = obs;
+  a.obs_dtype = obs_dtype;
+  a.N = n_reads;
+  a.L = (int)n_pos;
+  a.C = tab->n_channels;
+  a.bins = bins;
+  a.states = states;
+  a.bp = reinterpret_cast<uint8_t*>(workspace);
+  const bool wide = obs_dtype == SMF_OBS_F64;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (tab->n_states) {
+    case 2: return launch_vit_k<2>(tab, a, wide, di, st);
+    case 3: return launch_vit_k<3>(tab, a, wide, di, st);
+    case 4: return launch_vit_k<4>(tab, a, wide, di, st);
+  }
+  return SMF_ERR_BAD_ARG;
+}
+
+int smf_hmm_call_features(const int8_t* states, const float* post, int target_state,
+                          float threshold, int64_t n_reads, int64_t n_pos,
+                          const int64_t* coords, const int32_t* grid_left,
+                          const int32_t* grid_right, int64_t n_grid, const double* class_lo_host,
+                          const double* class_hi_host, int n_classes, uint8_t* class_out,
+                          int32_t* run_len, int32_t* intervals, int64_t max_intervals,
+                          unsigned long long* n_intervals, void* stream) {
+  if (n_reads < 0 || n_pos < 0 || n_grid < 0) return SMF_ERR_BAD_ARG;
+  if (n_reads == 0 || n_grid == 0) return SMF_OK;
+  if ((states == nullptr) == (post == nullptr)) return SMF_ERR_BAD_ARG;  // exactly one of them
+  if (!coords || !grid_left || !grid_right || !class_out) return SMF_ERR_BAD_ARG;
+  if (intervals != nullptr && n_intervals == nullptr) return SMF_ERR_BAD_ARG;
+  if (n_pos > 0x3fffffff || n_grid > 0x3fffffff) return SMF_ERR_TOO_LONG;
+  ClassTable ct;
+  int rc = fill_class_table(class_lo_host, class_hi_host, n_classes, &ct);
+  if (rc != SMF_OK) return rc;
+  DeviceInfo di;
+  rc = get_device_info(&di);
+  if (rc != SMF_OK) return rc;
+  const int maxruns = ((int)n_pos + 1) / 2 + 1;
+  const size_t smem = (size_t)maxruns * 8 + (2 * kFeatWarps + 2) * 4 + (size_t)align_up(maxruns, 16);
+  if ((long long)smem > di.max_smem_optin) return SMF_ERR_TOO_LONG;
+  if (cudaFuncSetAttribute(call_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+      cudaSuccess)
+    return SMF_ERR_CUDA;
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, call_features_kernel, kFeatThreads, smem) !=
+          cudaSuccess || occ < 1)
+    return SMF_ERR_CUDA;
+  FeatArgs a;
+  a.states = states;
+  a.post = post;
+  a.target = target_state;
+  a.thr = threshold;
+  a.N = n_reads;
+  a.L = (int)n_pos;
+  a.coords = reinterpret_cast<const long long*>(coords);
+  a.grid_left = grid_left;
+  a.grid_right = grid_right;
+  a.V = (int)n_grid;
+  a.class_out = class_out;
+  a.run_len = run_len;
+  a.intervals = intervals;
+  a.max_intervals = max_intervals;
+  a.n_intervals = n_intervals;
+  long long cap = (long long)di.num_sms * occ;
+  const int nblocks = (int)(n_reads < cap ? n_reads : cap);
+  call_features_kernel<<<nblocks, kFeatThreads, smem, (cudaStream_t)stream>>>(ct, a);
+  return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
+}
+
+int smf_hmm_merge_runs(const uint8_t* layer, int64_t n_reads, int64_t n_grid,
+                       const int64_t* coords, int coords_are_ints, int64_t distance_threshold,
+                       uint8_t* merged, int32_t* merged_len, const double* class_lo_host,
+                       const double* class_hi_host, int n_classes, uint8_t* class_out,
+                       int32_t* len_cls, void* stream) {
+  if (n_reads < 0 || n_grid < 0) return SMF_ERR_BAD_ARG;
+  if (n_reads == 0 || n_grid == 0) return SMF_OK;
+  if (!layer || !merged || !merged_len) return SMF_ERR_BAD_ARG;
+  if (coords_are_ints && !coords) return SMF_ERR_BAD_ARG;
+  if (n_grid > 0x3fffffff) return SMF_ERR_TOO_LONG;
+  ClassTable ct;
+  int rc = fill_class_table(class_lo_host, class_hi_host, n_classes, &ct);
+  if (rc != SMF_OK) return rc;
+  DeviceInfo di;
+  rc = get_device_info(&di);
+  if (rc != SMF_OK) return rc;
+  const int maxruns = ((int)n_grid + 1) / 2 + 1;
+  const size_t smem = (size_t)maxruns * 16 + (2 * kFeatWarps + 2) * 4 + (size_t)align_up(maxruns, 16);
+  if ((long long)smem > di.max_smem_optin) return SMF_ERR_TOO_LONG;
+  if (cudaFuncSetAttribute(merge_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+      cudaSuccess)
+    return SMF_ERR_CUDA;
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, merge_runs_kernel, kFeatThreads, smem) !=
+          cudaSuccess || occ < 1)
+    return SMF_ERR_CUDA;
+  MergeArgs a;
+  a.layer = layer;
+  a.N = n_reads;
+  a.V = (int)n_grid;
+  a.coords = reinterpret_cast<const long long*>(coords);
+  a.coords_are_ints = coords_are_ints;
+  a.dt = distance_threshold;
+  a.merged = merged;
+  a.merged_len = merged_len;
+  a.class_out = (n_classes > 0) ? class_out : nullptr;
+  a.len_cls = (n_classes > 0) ? len_cls : nullptr;
+  long long cap = (long long)di.num_sms * occ;
+  const int nblocks = (int)(n_reads < cap ? n_reads : cap);
+  merge_runs_kernel<<<nblocks, kFeatThreads, smem, (cudaStream_t)stream>>>(ct, a);
+  return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
+}
+
+int smf_hmm_span_mask(const uint8_t* covered, const int64_t* coords, const double* read_start,
+                      const double* read_end, int64_t n_reads, int64_t n_grid, uint8_t* valid_out,
+                      void* stream) {
+  if (n_reads < 0 || n_grid < 0) return SMF_ERR_BAD_ARG;
+  if (n_reads == 0 || n_grid == 0) return SMF_OK;
+  if (!valid_out) return SMF_ERR_BAD_ARG;
+  if (!covered && (!coords || !read_start || !read_end)) return SMF_ERR_BAD_ARG;
+  if (n_grid > 0x3fffffff) return SMF_ERR_TOO_LONG;
+  SpanArgs a;
+  a.covered = covered;
+  a.coords = reinterpret_cast<const long long*>(coords);
+  a.start = read_start;
+  a.end = read_end;
+  a.N = n_reads;
+  a.V = (int)n_grid;
+  a.valid = valid_out;
+  dim3 grid((unsigned)((n_grid + 255) / 256 > 64 ? 64 : (n_grid + 255) / 256),
+            (unsigned)(n_reads > 32768 ? 32768 : n_reads));
+  span_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
+}
+
+}  // extern "C"

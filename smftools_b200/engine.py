@@ -1,0 +1,252 @@
+"""Device-side entry points: torch CUDA tensors in, torch CUDA tensors out, through the C-ABI.
+
+PyTorch is plumbing here (device memory, streams, ``torch.distributed``); every arithmetic
+step runs in ``libsmfhmm.so``.  All functions raise if no CUDA device / library is present.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_OBS_DTYPES = {torch.float32: _lib.OBS_F32, torch.float64: _lib.OBS_F64, torch.uint8: _lib.OBS_U8}
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{name} must be a CUDA tensor: smftools_b200 runs only on a CUDA device (no CPU fallback)"
+        )
+
+
+def _stream_ptr(device) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else int(t.data_ptr())
+
+
+def _obs_args(obs: torch.Tensor, tables: _lib.HostTables) -> Tuple[int, int, int]:
+    _require_cuda(obs, "obs")
+    if obs.dtype not in _OBS_DTYPES:
+        raise ValueError(f"unsupported observation dtype {obs.dtype}; use float32, float64 or uint8")
+    if obs.dim() == 2:
+        N, L = obs.shape
+        C = 1
+    elif obs.dim() == 3:
+        N, L, C = obs.shape
+    else:
+        raise ValueError(f"X must be 2D or 3D; got shape {tuple(obs.shape)}")
+    if C != tables.C:
+        raise ValueError(f"observations have {C} channels but the model has {tables.C}")
+    if not obs.is_contiguous():
+        raise ValueError("obs must be contiguous")
+    return int(N), int(L), _OBS_DTYPES[obs.dtype]
+
+
+def _bins_arg(bins: Optional[torch.Tensor], tables: _lib.HostTables, L: int) -> Optional[int]:
+    if tables.n_bins <= 1:
+        return None
+    if L <= 1:
+        return None
+    if bins is None:
+        raise ValueError("Distance-binned HMM requires coords.")
+    _require_cuda(bins, "bins")
+    if bins.dtype != torch.int8 or bins.numel() != L - 1 or not bins.is_contiguous():
+        raise ValueError("bins must be a contiguous int8 tensor of length L-1")
+    return int(bins.data_ptr())
+
+
+def max_positions(tables: _lib.HostTables) -> int:
+    return int(_lib.load().smf_hmm_max_positions(tables.ref, 1))
+
+
+def posterior(
+    tables: _lib.HostTables,
+    obs: torch.Tensor,
+    bins: Optional[torch.Tensor] = None,
+    *,
+    want_gamma: bool = True,
+    gamma_state: int = -1,
+    want_states: bool = True,
+    want_loglik: bool = False,
+    out_gamma: Optional[torch.Tensor] = None,
+    out_states: Optional[torch.Tensor] = None,
+):
+    """Posterior decode (``smf_hmm_posterior``): returns (gamma, states, loglik), any may be None."""
+    lib = _lib.load()
+    N, L, dt = _obs_args(obs, tables)
+    dev = obs.device
+    K = tables.K
+    gamma = states = ll = None
+    if want_gamma:
+        shape = (N, L, K) if gamma_state < 0 else (N, L)
+        gamma = out_gamma if out_gamma is not None else torch.empty(shape, dtype=torch.float32, device=dev)
+        if tuple(gamma.shape) != shape or gamma.dtype != torch.float32 or not gamma.is_contiguous():
+            raise ValueError("out_gamma has the wrong shape / dtype")
+    if want_states:
+        states = out_states if out_states is not None else torch.empty((N, L), dtype=torch.int8, device=dev)
+        if tuple(states.shape) != (N, L) or states.dtype != torch.int8 or not states.is_contiguous():
+            raise ValueError("out_states has the wrong shape / dtype")
+    if want_loglik:
+        ll = torch.empty((N,), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.smf_hmm_posterior(tables.ref, _ptr(obs), dt, N, L, _bins_arg(bins, tables, L), _ptr(gamma),
+                                   int(gamma_state), _ptr(states), _ptr(ll), _stream_ptr(dev))
+    _lib.check(rc, "smf_hmm_posterior")
+    return gamma, states, ll
+
+
+def viterbi(tables: _lib.HostTables, obs: torch.Tensor, bins: Optional[torch.Tensor] = None,
+            *, out_states: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Viterbi decode (``smf_hmm_viterbi``): int8 states [N, L]."""
+    lib = _lib.load()
+    N, L, dt = _obs_args(obs, tables)
+    dev = obs.device
+    states = out_states if out_states is not None else torch.empty((N, L), dtype=torch.int8, device=dev)
+    need = int(lib.smf_hmm_workspace_bytes(_lib.OP_VITERBI, tables.ref, N, L))
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty((max(need, 1),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.smf_hmm_viterbi(tables.ref, _ptr(obs), dt, N, L, _bins_arg(bins, tables, L), _ptr(states),
+                                 _ptr(workspace), workspace.numel() * workspace.element_size(), _stream_ptr(dev))
+    _lib.check(rc, "smf_hmm_viterbi")
+    return states
+
+
+def stats_len(tables: _lib.HostTables) -> int:
+    return int(_lib.load().smf_hmm_stats_len(tables.ref))
+
+
+def estep(tables: _lib.HostTables, obs: torch.Tensor, bins: Optional[torch.Tensor] = None,
+          *, out_stats: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Baum-Welch E-step (``smf_hmm_estep``): fp64 statistics vector on the device."""
+    lib = _lib.load()
+    N, L, dt = _obs_args(obs, tables)
+    dev = obs.device
+    S = stats_len(tables)
+    stats = out_stats if out_stats is not None else torch.empty((S,), dtype=torch.float64, device=dev)
+    need = int(lib.smf_hmm_workspace_bytes(_lib.OP_ESTEP, tables.ref, N, L))
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty((max(need // 8, 1),), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.smf_hmm_estep(tables.ref, _ptr(obs), dt, N, L, _bins_arg(bins, tables, L), _ptr(stats),
+                               _ptr(workspace), workspace.numel() * workspace.element_size(), _stream_ptr(dev))
+    _lib.check(rc, "smf_hmm_estep")
+    return stats
+
+
+def estep_workspace(tables: _lib.HostTables, device) -> torch.Tensor:
+    need = int(_lib.load().smf_hmm_workspace_bytes(_lib.OP_ESTEP, tables.ref, 1, 1))
+    return torch.empty((max(need // 8, 1),), dtype=torch.float64, device=device)
+
+
+def _class_arrays(ranges: Sequence[Tuple[float, float]]):
+    lo = np.ascontiguousarray([float(r[0]) for r in ranges], dtype=np.float64)
+    hi = np.ascontiguousarray([float(r[1]) for r in ranges], dtype=np.float64)
+    dp = ctypes.POINTER(ctypes.c_double)
+    return lo, hi, lo.ctypes.data_as(dp), hi.ctypes.data_as(dp)
+
+
+def call_features(
+    *,
+    states: Optional[torch.Tensor],
+    post: Optional[torch.Tensor],
+    target: int,
+    threshold: float,
+    coords: torch.Tensor,
+    grid_left: torch.Tensor,
+    grid_right: torch.Tensor,
+    n_grid: int,
+    ranges: Sequence[Tuple[float, float]],
+    want_len: bool = True,
+    max_intervals: int = 0,
+):
+    """Feature calling (``smf_hmm_call_features``).
+
+    Returns (class_out uint8 [N,V], run_len int32 [N,V] | None, intervals int32 [n,4] | None).
+    """
+    lib = _lib.load()
+    src = states if states is not None else post
+    _require_cuda(src, "states/post")
+    N, L = src.shape
+    dev = src.device
+    if states is not None and (states.dtype != torch.int8 or not states.is_contiguous()):
+        raise ValueError("states must be contiguous int8")
+    if post is not None and (post.dtype != torch.float32 or not post.is_contiguous()):
+        raise ValueError("post must be contiguous float32")
+    for t, dt_, nm in ((coords, torch.int64, "coords"), (grid_left, torch.int32, "grid_left"),
+                       (grid_right, torch.int32, "grid_right")):
+        _require_cuda(t, nm)
+        if t.dtype != dt_ or t.numel() != L or not t.is_contiguous():
+            raise ValueError(f"{nm} must be contiguous {dt_} of length L")
+    V = int(n_grid)
+    cls = torch.empty((N, V), dtype=torch.uint8, device=dev)
+    rlen = torch.empty((N, V), dtype=torch.int32, device=dev) if want_len else None
+    ivals = cnt = None
+    if max_intervals > 0:
+        ivals = torch.empty((max_intervals, 4), dtype=torch.int32, device=dev)
+        cnt = torch.zeros((1,), dtype=torch.int64, device=dev)
+    lo, hi, plo, phi = _class_arrays(ranges)
+    with torch.cuda.device(dev):
+        rc = lib.smf_hmm_call_features(_ptr(states), _ptr(post), int(target), float(threshold), N, L,
+                                       _ptr(coords), _ptr(grid_left), _ptr(grid_right), V, plo, phi, len(lo),
+                                       _ptr(cls), _ptr(rlen), _ptr(ivals), int(max_intervals), _ptr(cnt),
+                                       _stream_ptr(dev))
+    _lib.check(rc, "smf_hmm_call_features")
+    if ivals is not None:
+        n = min(int(cnt.item()), max_intervals)
+        ivals = ivals[:n]
+    return cls, rlen, ivals
+
+
+def merge_runs(layer: torch.Tensor, coords: Optional[torch.Tensor], coords_are_ints: bool,
+               distance_threshold: int, ranges: Sequence[Tuple[float, float]] = ()):
+    """Run merging + size classes (``smf_hmm_merge_runs``).
+
+    Returns (merged uint8, merged_len int32, class_out uint8 | None, len_cls int32 | None), all [N, V].
+    """
+    lib = _lib.load()
+    _require_cuda(layer, "layer")
+    if layer.dtype != torch.uint8 or not layer.is_contiguous() or layer.dim() != 2:
+        raise ValueError("layer must be a contiguous uint8 [N, V] tensor")
+    N, V = layer.shape
+    dev = layer.device
+    if coords is not None:
+        _require_cuda(coords, "coords")
+        if coords.dtype != torch.int64 or coords.numel() != V or not coords.is_contiguous():
+            raise ValueError("coords must be contiguous int64 of length V")
+    merged = torch.empty((N, V), dtype=torch.uint8, device=dev)
+    mlen = torch.empty((N, V), dtype=torch.int32, device=dev)
+    cls = clen = None
+    lo, hi, plo, phi = _class_arrays(ranges)
+    if len(lo) > 0:
+        cls = torch.empty((N, V), dtype=torch.uint8, device=dev)
+        clen = torch.empty((N, V), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.smf_hmm_merge_runs(_ptr(layer), N, V, _ptr(coords), int(bool(coords_are_ints)),
+                                    int(distance_threshold), _ptr(merged), _ptr(mlen), plo, phi, len(lo),
+                                    _ptr(cls), _ptr(clen), _stream_ptr(dev))
+    _lib.check(rc, "smf_hmm_merge_runs")
+    return merged, mlen, cls, clen
+
+
+def span_mask(n_reads: int, n_grid: int, device, *, covered: Optional[torch.Tensor] = None,
+              coords: Optional[torch.Tensor] = None, start: Optional[torch.Tensor] = None,
+              end: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Read-span validity bitmap (``smf_hmm_span_mask``): uint8 [N, V], 1 = keep, 0 = NaN."""
+    lib = _lib.load()
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("span_mask needs a CUDA device (no CPU fallback)")
+    valid = torch.empty((n_reads, n_grid), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.smf_hmm_span_mask(_ptr(covered), _ptr(coords), _ptr(start), _ptr(end), int(n_reads),
+                                   int(n_grid), _ptr(valid), _stream_ptr(dev))
+    _lib.check(rc, "smf_hmm_span_mask")
+    return valid
