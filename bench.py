@@ -1,0 +1,465 @@
+#!/usr/bin/env python
+"""bench.py -- HMM footprinting hot path throughput on B200 (read-positions / s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3p|...]
+
+One "step" = one pass of the hot path over one batch of synthetic reads.  At N=1 the default
+workload is BASELINE.json configs[1]: 100k reads x 5 kb binary GpC calls (30 % NaN), 2-state
+posterior decode.  With N>1 (torchrun) every rank decodes its own batch of the same shape (weak
+scaling, no data-path collective) and additionally times Baum-Welch iterations whose sufficient
+statistics are NCCL-all-reduced; rank 0 prints ONE JSON line.
+
+`--impl reference` times the CPU port of the reference algorithm (oracle/hmm_oracle.py: the
+reference is pure Python and /root/reference does not travel to the GPU box) on the host cores,
+one single-threaded worker process per core like the reference's own process pool.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES = {  # algorithmic bytes per read-position: obs f32 in + gamma f32*K + state i8
+    "posterior": lambda K, C: 4 * C + 4 * K + 1,
+    "viterbi": lambda K, C: 4 * C + 1,
+    "estep": lambda K, C: 4 * C,
+}
+
+WORKLOADS = {
+    # name: (N, L, K, prob, op)
+    "c2": dict(N=100_000, L=5_000, K=2, prob=False, op="posterior",
+               desc="BASELINE configs[1]: 100k reads x 5 kb binary GpC (30% NaN), 2-state posterior decode"),
+    "c3p": dict(N=65_536, L=10_000, K=2, prob=False, op="posterior",
+                desc="headline shape: 1M x 10 kb posterior decode, one 65,536-read device-resident chunk"),
+    "c3p_k3": dict(N=65_536, L=10_000, K=3, prob=True, op="posterior",
+                   desc="1M x 10 kb m6A probabilistic, 3-state posterior decode, one 65,536-read chunk"),
+    "c3v": dict(N=65_536, L=10_000, K=3, prob=True, op="viterbi",
+                desc="BASELINE configs[2]: 1M x 10 kb 3-state Viterbi, one 65,536-read chunk"),
+    "c4": dict(N=262_144, L=8_000, K=4, prob=False, op="estep",
+               desc="BASELINE configs[3]: 4-state Baum-Welch iteration, 262,144 reads x 8 kb per GPU"),
+}
+
+
+# --------------------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------------------
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(workload):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh).get(workload)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def device_reads(N, L, K, prob, seed, device):
+    """Synthetic SMF-like reads generated ON the device (fp32, NaN = missing): K-state block
+    structure with the survey's per-state emission means, Bernoulli calls or k/255-quantised
+    probabilities, 30 % iid NaN plus read-span truncation."""
+    import torch
+
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    em = torch.tensor([0.85, 0.08, 0.35, 0.60][:K], device=device)
+    blk = 40
+    nb = (L + blk - 1) // blk
+    out = torch.empty((N, L), dtype=torch.float32, device=device)
+    step = max(1, min(N, (1 << 28) // max(L, 1)))
+    for lo in range(0, N, step):
+        hi = min(N, lo + step)
+        n = hi - lo
+        st = torch.randint(0, K, (n, nb), device=device, generator=gen)
+        keep = torch.rand((n, nb), device=device, generator=gen) < 0.6  # sticky: often keep previous block's state
+        for b in range(1, nb):
+            st[:, b] = torch.where(keep[:, b], st[:, b - 1], st[:, b])
+        p = em[st].repeat_interleave(blk, dim=1)[:, :L]
+        u = torch.rand((n, L), device=device, generator=gen)
+        if prob:
+            noise = torch.rand((n, L), device=device, generator=gen)
+            x = (p + (noise - 0.5) * 0.5).clamp_(0.0, 1.0)
+            x = torch.where(u < 0.15, 1.0 - x, x)
+            x = torch.round(x * 255.0) / 255.0
+        else:
+            x = (u < p).float()
+        x[torch.rand((n, L), device=device, generator=gen) < 0.3] = float("nan")
+        lo_t = torch.randint(0, max(1, L // 10), (n, 1), device=device, generator=gen)
+        hi_t = L - torch.randint(0, max(1, L // 10), (n, 1), device=device, generator=gen)
+        pos = torch.arange(L, device=device)[None, :]
+        x[(pos < lo_t) | (pos >= hi_t)] = float("nan")
+        out[lo:hi] = x
+        del st, keep, p, u, x
+    return out
+
+
+def bench_params(K):
+    """'Fitted-looking' parameters: dwell 60/150/25/80 positions, emission
+    .85/.08/.35/.60 -- the same table the CPU port uses (oracle.synth_params)."""
+    dwell = [60.0, 150.0, 25.0, 80.0][:K]
+    trans = np.zeros((K, K))
+    for i in range(K):
+        leave = 1.0 / dwell[i]
+        trans[i] = leave / (K - 1)
+        trans[i, i] = 1.0 - leave
+    start = np.linspace(1.0, 2.0, K)
+    start /= start.sum()
+    eps = 1e-8
+    start = (start + eps) / (start + eps).sum()
+    trans = (trans + eps) / (trans + eps).sum(axis=1, keepdims=True)
+    em = np.clip(np.array([0.85, 0.08, 0.35, 0.60][:K]), eps, 1 - eps)
+    return start, trans, em
+
+
+def make_model(K, device):
+    import torch
+
+    import smftools_b200 as S
+
+    start, trans, em = bench_params(K)
+    m = S.create_hmm({"hmm_n_states": K}, arch="single", device=None)
+    with torch.no_grad():
+        m.start.data = torch.tensor(start, dtype=torch.float64)
+        m.trans.data = torch.tensor(trans, dtype=torch.float64)
+        m.emission.data = torch.tensor(em, dtype=torch.float64)
+    return m
+
+
+# --------------------------------------------------------------------------------------
+# CPU baseline (oracle port on the host cores)
+# --------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    os.environ["MKL_NUM_THREADS"] = "1"
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    n, L, K, prob, op, seed = args
+    from oracle import hmm_oracle as O
+
+    X = O.synth_reads(n, L, K, seed, prob=prob, nan_rate=0.3, truncate=False).astype(np.float64)
+    p = O.synth_params(K)
+    t0 = time.perf_counter()
+    if op == "posterior":
+        O.decode(X, p, None, "marginal")
+    elif op == "viterbi":
+        O.decode(X, p, None, "viterbi")
+    else:
+        O.estep(X, p, None)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(wl, cores=None, reads_per_worker=None):
+    """Time the CPU port on a bounded sample: P single-threaded worker processes (the reference's
+    own way of using all cores, parallel_utils.py:25-96), wall = slowest worker."""
+    import multiprocessing as mp
+
+    if cores is None:
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    workers = max(1, min(cores, 64))
+    L, K = wl["L"], wl["K"]
+    if reads_per_worker is None:
+        reads_per_worker = max(64, int(8e6 // L))  # ~8e6 read-positions per worker (~10-20 s)
+    ctx = mp.get_context("spawn")
+    args = [(reads_per_worker, L, K, wl["prob"], wl["op"], 9000 + i) for i in range(workers)]
+    t0 = time.perf_counter()
+    with ctx.Pool(workers) as pool:
+        times = pool.map(_cpu_worker, args)
+    wall_all = time.perf_counter() - t0
+    rp = workers * reads_per_worker * L
+    return {
+        "value": rp / max(times), "unit": "read-positions/s", "cores": workers, "kind": "port",
+        "sample": f"{workers} workers x {reads_per_worker} reads x {L} positions, K={K}, op={wl['op']}, "
+                  f"numpy fp64 oracle port, compute time of slowest worker {max(times):.1f}s (pool wall {wall_all:.1f}s)",
+    }
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    last = None
+    total = args.steps + args.warmup
+    # bounded: the whole run must end within a few minutes
+    per = max(32, int(2.5e6 // wl["L"]))
+    for i in range(total):
+        last = cpu_baseline(wl, reads_per_worker=per)
+        if i >= args.warmup:
+            vals.append(last["value"])
+    v = statistics.median(vals)
+    last["value"] = v
+    rp_step = last["cores"] * per * wl["L"]
+    line = {
+        "impl": "reference", "metric": "HMM read-positions/sec", "value": v, "unit": "read-positions/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * rp_step / v,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "op": wl["op"], "K": wl["K"], "L": wl["L"],
+                   "note": "reference algorithm (CPU port, oracle/hmm_oracle.py) on a bounded sample per step"},
+        "cpu_baseline": last,
+        "e2e": {"value": v, "unit": "read-positions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    from smftools_b200 import engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    N, L, K, op = wl["N"], wl["L"], wl["K"], wl["op"]
+    C = 1
+    model = make_model(K, device)
+    tables = model._host_tables()
+    obs = device_reads(N, L, K, wl["prob"], 1234 + 1000 * rank, device)
+    torch.cuda.synchronize()
+
+    gamma = torch.empty((N, L, K), dtype=torch.float32, device=device) if op == "posterior" else None
+    states = torch.empty((N, L), dtype=torch.int8, device=device) if op in ("posterior", "viterbi") else None
+    ws = None
+    if op == "viterbi":
+        ws = torch.empty((N * L,), dtype=torch.uint8, device=device)
+    if op == "estep":
+        ws = engine.estep_workspace(tables, device)
+        stats = torch.empty((engine.stats_len(tables),), dtype=torch.float64, device=device)
+
+    launches = {"n": 0}
+
+    def step():
+        if op == "posterior":
+            engine.posterior(tables, obs, None, out_gamma=gamma, out_states=states)
+            launches["n"] += 1
+        elif op == "viterbi":
+            engine.viterbi(tables, obs, None, out_states=states, workspace=ws)
+            launches["n"] += 1
+        else:
+            engine.estep(tables, obs, None, out_stats=stats, workspace=ws)
+            launches["n"] += 2
+            if world > 1:
+                dist.all_reduce(stats)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches["n"] = 0
+    stream = torch.cuda.current_stream(device)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start.record(stream)
+    for i in range(args.steps):
+        ev[i][0].record(stream)
+        step()
+        ev[i][1].record(stream)
+    t_end.record(stream)
+    barrier()
+    total_ms = t_start.elapsed_time(t_end)
+    kernel_ms = [a.elapsed_time(b) for a, b in ev]
+    clocks = sampler.stop() if rank == 0 else None
+    n_launch = launches["n"]
+
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms = float(tmax.item())
+    ms_per_step = total_ms / args.steps
+    value = world * N * L / (ms_per_step * 1e-3)
+
+    # ---- end-to-end through the public API with HOST buffers (pinned), copies inside the timed region ----
+    e2e = None
+    if op == "posterior":
+        e2e_steps = max(1, min(args.steps, 3))
+        n_e2e = min(N, 32_768)
+        host_in = torch.empty((n_e2e, L), dtype=torch.float32, pin_memory=True)
+        host_in.copy_(obs[:n_e2e])
+        out_states = torch.empty((n_e2e, L), dtype=torch.int8, pin_memory=True)
+        out_gamma = torch.empty((n_e2e, L, K), dtype=torch.float32, pin_memory=True)
+        X_host = host_in.numpy()
+        outs = (out_states.numpy(), out_gamma.numpy())
+        model.decode(X_host, decode="marginal", compact=True, out=outs)  # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            model.decode(X_host, decode="marginal", compact=True, out=outs)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        e2e = {
+            "value": world * n_e2e * L * e2e_steps / dt, "unit": "read-positions/s",
+            "h2d_bytes_per_step": int(n_e2e * L * 4), "d2h_bytes_per_step": int(n_e2e * L * (4 * K + 1)),
+            "steps": e2e_steps, "reads_per_step": n_e2e,
+            "api": "SingleBernoulliHMM.decode(X_host_f32, decode='marginal', compact=True, out=pinned buffers)",
+        }
+        del host_in, out_states, out_gamma
+
+    # ---- Baum-Welch iteration (E-step kernel + NCCL all-reduce of the statistics + host M-step) ----
+    bw = None
+    if op == "posterior" and not args.no_bw:
+        n_bw = N
+        wsb = engine.estep_workspace(tables, device)
+        stats = torch.empty((engine.stats_len(tables),), dtype=torch.float64, device=device)
+
+        def bw_iter():
+            engine.estep(tables, obs[:n_bw], None, out_stats=stats, workspace=wsb)
+            if world > 1:
+                dist.all_reduce(stats)
+            return stats.cpu()  # the M-step / convergence test needs the statistics on the host every iteration
+
+        for _ in range(3):
+            bw_iter()
+        barrier()
+        iters = max(3, min(args.steps, 10))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(iters):
+            bw_iter()
+        b.record(stream)
+        barrier()
+        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item()) / iters
+        bw = {"value": world * n_bw * L / (ms * 1e-3), "unit": "read-positions/s per EM iteration", "ms_per_iter": ms,
+              "reads_per_gpu": n_bw, "K": K, "collective": "nccl all_reduce fp64 x %d" % stats.numel() if world > 1 else "none"}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        algo = ALGO_BYTES[op](K, C)
+        k_ms = statistics.mean(kernel_ms)
+        achieved = algo * N * L / (k_ms * 1e-3) / 1e9
+        line = {
+            "metric": "HMM read-positions/sec", "value": value, "unit": "read-positions/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "op": op, "reads_per_gpu": N, "positions": L, "K": K, "obs": "f32 NaN-coded",
+                       "l2": f"inputs {N * L * 4 / 1e9:.2f} GB + outputs per step, far larger than the 126 MB L2 (no flush needed)"},
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": n_launch,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
+                         "algorithmic_bytes_per_read_position": algo, "kernel_ms": k_ms,
+                         "kernel": {"posterior": "fb_kernel<K,...,STATS=false>", "viterbi": "viterbi_kernel",
+                                    "estep": "fb_kernel<K,...,STATS=true>"}[op]},
+            "baum_welch": bw,
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(wl)
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-bw", action="store_true", help="skip the Baum-Welch leg")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -465,12 +465,16 @@ class BaseHMM(nn.Module):
         decode: str = "marginal",
         device: Optional[Union[str, torch.device]] = None,
         compact: bool = False,
+        out: Optional[Tuple[np.ndarray, np.ndarray]] = None,
     ) -> Tuple[np.ndarray, np.ndarray]:
         """States (N,L) and posteriors (N,L,K).
 
         Like the reference, the posterior is always computed; ``decode="viterbi"`` replaces the
-        arg-max states with the Viterbi path.  Returns ``(int64, model dtype)`` arrays, or the
-        kernels' native ``(int8, float32)`` when ``compact=True``.
+        arg-max states with the Viterbi path.  Returns ``(int64, model dtype)`` host arrays, or the
+        kernels' native ``(int8, float32)`` when ``compact=True``.  ``out=(states, gamma)`` lets the
+        caller supply (ideally pinned) result buffers.  Host inputs are streamed through the device
+        in read chunks: H2D copy, kernels and D2H copy of consecutive chunks overlap on three
+        streams.
         """
         device = self._ensure_device_dtype(device)
         src = self._as_obs_source(X)
@@ -486,18 +490,89 @@ class BaseHMM(nn.Module):
         K = self.n_states
         use_viterbi = str(decode).lower() == "viterbi"
 
-        np_gamma_dtype = np.float32 if compact else _TORCH_TO_NP[self.dtype]
-        states_out = np.empty((N, L), dtype=np.int8 if compact else np.int64)
-        gamma_out = np.empty((N, L, K), dtype=np_gamma_dtype)
-        item = src.element_size() if isinstance(src, torch.Tensor) else src.dtype.itemsize
-        for lo, hi in self._chunks(N, L, C, item, 4 * K + 2):
-            obs = self._to_device(src[lo:hi], device)
-            gamma, st, _ = engine.posterior(tables, obs, bins, want_gamma=True, want_states=not use_viterbi)
-            if use_viterbi:
-                st = engine.viterbi(tables, obs, bins)
-            states_out[lo:hi] = st.cpu().numpy()
-            gamma_out[lo:hi] = gamma.cpu().numpy()
+        st_dtype = np.int8 if compact else np.int64
+        g_dtype = np.float32 if compact else _TORCH_TO_NP[self.dtype]
+        if out is not None:
+            states_out, gamma_out = out
+            if states_out.shape != (N, L) or gamma_out.shape != (N, L, K):
+                raise ValueError("out buffers have the wrong shape")
+            if states_out.dtype != st_dtype or gamma_out.dtype != g_dtype:
+                raise ValueError(f"out buffers must be ({np.dtype(st_dtype)}, {np.dtype(g_dtype)})")
+        else:
+            states_out = np.empty((N, L), dtype=st_dtype)
+            gamma_out = np.empty((N, L, K), dtype=g_dtype)
+        if N == 0 or L == 0:
+            return states_out, gamma_out
+        self._decode_stream(src, tables, bins, use_viterbi, states_out, gamma_out, device, C)
         return states_out, gamma_out
+
+    def _decode_stream(self, src, tables, bins, use_viterbi, states_out, gamma_out, device, C):
+        """Chunked, triple-stream decode: chunk i+1 uploads while chunk i computes and chunk i-1
+        downloads.  Device buffers are double-buffered; events order reuse."""
+        N, L = int(src.shape[0]), int(src.shape[1])
+        K = self.n_states
+        src_t = src if isinstance(src, torch.Tensor) else torch.from_numpy(src)
+        on_device = src_t.is_cuda
+        st_t = torch.from_numpy(states_out)
+        g_t = torch.from_numpy(gamma_out)
+        widen_g = g_t.dtype != torch.float32
+        widen_s = st_t.dtype != torch.int8
+        in_item = src_t.element_size()
+        per_read = L * (C * in_item + K * (4 + (g_t.element_size() if widen_g else 0)) + 2 + st_t.element_size())
+        rows = max(1, int(self.device_chunk_bytes // (2 * per_read)))
+        rows = min(rows, max(1, -(-N // 4)) if N >= 4096 else N)  # >= 4 chunks on big inputs so copies overlap
+        cur = torch.cuda.current_stream(device)
+        s_in = torch.cuda.Stream(device)
+        s_out = torch.cuda.Stream(device)
+        nbuf = 2
+        obs_shape = (rows, L) if src_t.dim() == 2 else (rows, L, C)
+        d_obs = [None] * nbuf if on_device else [torch.empty(obs_shape, dtype=src_t.dtype, device=device) for _ in range(nbuf)]
+        d_g = [torch.empty((rows, L, K), dtype=torch.float32, device=device) for _ in range(nbuf)]
+        d_s = [torch.empty((rows, L), dtype=torch.int8, device=device) for _ in range(nbuf)]
+        d_gw = [torch.empty((rows, L, K), dtype=g_t.dtype, device=device) for _ in range(nbuf)] if widen_g else None
+        d_sw = [torch.empty((rows, L), dtype=st_t.dtype, device=device) for _ in range(nbuf)] if widen_s else None
+        ws = torch.empty((rows * L,), dtype=torch.uint8, device=device) if use_viterbi else None
+        ev_in = [None] * nbuf
+        ev_cmp = [None] * nbuf
+        ev_out = [None] * nbuf
+        for i, lo in enumerate(range(0, N, rows)):
+            hi = min(N, lo + rows)
+            n = hi - lo
+            b = i % nbuf
+            if on_device:
+                obs = src_t[lo:hi].contiguous()
+            else:
+                if ev_cmp[b] is not None:
+                    s_in.wait_event(ev_cmp[b])
+                with torch.cuda.stream(s_in):
+                    d_obs[b][:n].copy_(src_t[lo:hi], non_blocking=True)
+                    ev_in[b] = torch.cuda.Event()
+                    ev_in[b].record(s_in)
+                cur.wait_event(ev_in[b])
+                obs = d_obs[b][:n]
+            if ev_out[b] is not None:
+                cur.wait_event(ev_out[b])
+            engine.posterior(tables, obs, bins, want_gamma=True, want_states=not use_viterbi,
+                             out_gamma=d_g[b][:n], out_states=None if use_viterbi else d_s[b][:n])
+            if use_viterbi:
+                engine.viterbi(tables, obs, bins, out_states=d_s[b][:n], workspace=ws)
+            g_src, s_src = d_g[b][:n], d_s[b][:n]
+            if widen_g:
+                d_gw[b][:n].copy_(g_src)
+                g_src = d_gw[b][:n]
+            if widen_s:
+                d_sw[b][:n].copy_(s_src)
+                s_src = d_sw[b][:n]
+            ev_cmp[b] = torch.cuda.Event()
+            ev_cmp[b].record(cur)
+            s_out.wait_event(ev_cmp[b])
+            with torch.cuda.stream(s_out):
+                g_t[lo:hi].copy_(g_src, non_blocking=True)
+                st_t[lo:hi].copy_(s_src, non_blocking=True)
+                ev_out[b] = torch.cuda.Event()
+                ev_out[b].record(s_out)
+        s_out.synchronize()
+        cur.synchronize()
 
     # ---- EM fit (HMM.py:724-821, 1518-1630) ----------------------------------------------------
     def fit(
