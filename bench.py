@@ -356,7 +356,7 @@ def run_ours(args, wl):
 
     # ---- end-to-end through the public API with HOST buffers (pinned), copies inside the timed region ----
     e2e = None
-    if op == "posterior":
+    if op == "posterior" and not args.no_e2e:
         e2e_steps = max(1, min(args.steps, 3))
         n_e2e = min(N, 32_768)
         host_in = torch.empty((n_e2e, L), dtype=torch.float32, pin_memory=True)
@@ -453,6 +453,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-bw", action="store_true", help="skip the Baum-Welch leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

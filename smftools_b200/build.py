@@ -11,7 +11,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libsmfhmm.so")
 SOURCES = ["api.cu"]
-HEADERS = ["hmm_common.cuh", "fb_kernel.cuh", "viterbi_kernel.cuh", "features_kernel.cuh"]
+HEADERS = ["hmm_common.cuh", "fb_kernel.cuh", "fb2_kernel.cuh", "viterbi_kernel.cuh", "features_kernel.cuh"]
 
 
 def _nvcc() -> str:

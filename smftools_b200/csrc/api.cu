@@ -4,16 +4,21 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <type_traits>
 
+#include "fb2_kernel.cuh"
 #include "fb_kernel.cuh"
 #include "features_kernel.cuh"
 #include "smf_hmm.h"
 #include "viterbi_kernel.cuh"
 
 namespace smf {
+
+// E-step workspace: per-CTA partial statistics, for at most this many CTAs.
+static const int kMaxEstepBlocks = 148 * 8;
 
 struct DeviceInfo {
   int device = -1;
@@ -38,6 +43,12 @@ static int get_device_info(DeviceInfo* out) {
   *out = cache[dev];
   return SMF_OK;
 }
+
+// SMF_HMM_FORCE_GENERIC=1 routes everything through the generic kernel (testing / A-B timing).
+static const bool g_force_generic = [] {
+  const char* e = getenv("SMF_HMM_FORCE_GENERIC");
+  return e != nullptr && e[0] == '1';
+}();
 
 static int check_tables(const smf_hmm_tables* t) {
   if (t == nullptr) return SMF_ERR_BAD_ARG;
@@ -169,6 +180,7 @@ static int launch_fb_t(const smf_hmm_tables* t, FbArgs& a, const FbPlan& plan, c
   auto kern = fb_kernel<K, MULTI, BINNED, STATS, MAXT>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem) != cudaSuccess)
     return SMF_ERR_CUDA;
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   int occ = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, plan.block, plan.smem) != cudaSuccess)
     return SMF_ERR_CUDA;
@@ -207,13 +219,127 @@ static int launch_fb(const smf_hmm_tables* t, FbArgs& a, const FbPlan& plan, con
   return SMF_ERR_BAD_ARG;
 }
 
+// ---------------------------------------------------------------------------------------
+// fast path (fb2_kernel): single channel, homogeneous transitions, compile-time chunk
+// ---------------------------------------------------------------------------------------
+constexpr int kFb2Chunk = 17;
+
+static int fb2_max_threads(int K, bool stats) {
+  if (stats) return K == 2 ? 640 : (K == 3 ? 512 : 384);
+  return K == 4 ? 512 : 640;
+}
+
+struct Fb2Plan {
+  int block, smem;
+};
+
+static int plan_fb2(int K, int64_t L64, bool stats, int S, int es, bool want_gamma_one, bool want_states,
+                    int max_smem, Fb2Args* a, Fb2Plan* plan) {
+  if (L64 < 1) return SMF_ERR_TOO_LONG;
+  const int CH = kFb2Chunk;
+  if (L64 > (int64_t)CH * 1024) return SMF_ERR_TOO_LONG;
+  const int L = (int)L64;
+  const int Tact = (L + CH - 1) / CH;
+  const int T = align_up(Tact, 32);
+  if (T > fb2_max_threads(K, stats)) return SMF_ERR_TOO_LONG;
+  const int Lpad = Tact * CH;
+  const int KK = K * K;
+  const int bar_b = 16;
+  const int in_b = align_up((Lpad + 16) * es + 16, 16);
+  const int stage_b = align_up((Lpad * K + 4) * 4, 16);
+  const int out1_b = want_gamma_one ? align_up((Lpad + 4) * 4, 16) : 0;
+  const int st_b = want_states ? align_up(Lpad + 32, 16) : 0;
+  const int scan_b = align_up(32 * (KK + 2 * K) * 4 + 32 * 8, 16);
+  const int group_bytes = bar_b + in_b + stage_b + out1_b + st_b + scan_b;
+  int groups = 256 / T;
+  if (groups < 1) groups = 1;
+  if (groups > 8) groups = 8;
+  for (;; --groups) {
+    const int warps = groups * T / 32;
+    const int wacc_b = stats ? align_up(warps * S * 8, 16) : 0;
+    const int total = wacc_b + groups * group_bytes;
+    if (total <= max_smem) {
+      a->off_wacc = 0;
+      a->off_group0 = wacc_b;
+      a->group_bytes = group_bytes;
+      a->goff_bar = 0;
+      a->goff_in = bar_b;
+      a->goff_stage = bar_b + in_b;
+      a->goff_out1 = bar_b + in_b + stage_b;
+      a->goff_st = bar_b + in_b + stage_b + out1_b;
+      a->goff_scan = bar_b + in_b + stage_b + out1_b + st_b;
+      a->T = T;
+      a->groups = groups;
+      plan->block = T * groups;
+      plan->smem = total;
+      return SMF_OK;
+    }
+    if (groups == 1) return SMF_ERR_TOO_LONG;
+  }
+}
+
+template <int K, bool STATS, typename ObsT>
+static int launch_fb2_t(const smf_hmm_tables* t, Fb2Args& a, const Fb2Plan& plan, const DeviceInfo& di,
+                        int* nblocks_out, cudaStream_t stream) {
+  constexpr int MAXT = STATS ? (K == 2 ? 640 : (K == 3 ? 512 : 384)) : (K == 4 ? 512 : 640);
+  FbTables<K> tab;
+  build_fb_tables<K>(t, &tab);
+  auto kern = fb2_kernel<K, kFb2Chunk, STATS, ObsT, MAXT>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem) != cudaSuccess)
+    return SMF_ERR_CUDA;
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, plan.block, plan.smem) != cudaSuccess)
+    return SMF_ERR_CUDA;
+  if (occ < 1) return SMF_ERR_CUDA;
+  long long want = (a.N + a.groups - 1) / a.groups;
+  long long cap = (long long)di.num_sms * occ;
+  int nblocks = (int)(want < cap ? want : cap);
+  if (nblocks < 1) nblocks = 1;
+  if (nblocks_out) {
+    if (*nblocks_out > 0 && nblocks > *nblocks_out) nblocks = *nblocks_out;
+    *nblocks_out = nblocks;
+  }
+  kern<<<nblocks, plan.block, plan.smem, stream>>>(tab, a);
+  return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
+}
+
+template <bool STATS>
+static int launch_fb2(const smf_hmm_tables* t, int obs_dtype, Fb2Args& a, const Fb2Plan& plan,
+                      const DeviceInfo& di, int* nblocks, cudaStream_t stream) {
+#define SMF_FB2_CASE(KV)                                                                                    \
+  case KV:                                                                                                  \
+    if (obs_dtype == SMF_OBS_F32) return launch_fb2_t<KV, STATS, float>(t, a, plan, di, nblocks, stream);   \
+    if (obs_dtype == SMF_OBS_F64) return launch_fb2_t<KV, STATS, double>(t, a, plan, di, nblocks, stream);  \
+    return launch_fb2_t<KV, STATS, unsigned char>(t, a, plan, di, nblocks, stream);
+  switch (t->n_states) {
+    SMF_FB2_CASE(2)
+    SMF_FB2_CASE(3)
+    SMF_FB2_CASE(4)
+  }
+#undef SMF_FB2_CASE
+  return SMF_ERR_BAD_ARG;
+}
+
+static inline int obs_elem_size(int dt) { return dt == SMF_OBS_F32 ? 4 : (dt == SMF_OBS_F64 ? 8 : 1); }
+
+// The fast path needs natural alignment of the row pointers it vectorises.
+static bool fb2_aligned(const void* obs, int obs_dtype, const float* gamma, int K, int gamma_state) {
+  if (reinterpret_cast<uintptr_t>(obs) % obs_elem_size(obs_dtype)) return false;
+  if (gamma != nullptr) {
+    const uintptr_t g = reinterpret_cast<uintptr_t>(gamma);
+    if (gamma_state < 0 && K == 2 && (g & 7u)) return false;
+    if (gamma_state < 0 && K == 4 && (g & 15u)) return false;
+    if (g & 3u) return false;
+  }
+  return true;
+}
+
 static int stats_len(const smf_hmm_tables* t) {
   const int K = t->n_states, C = t->n_channels;
   return K + t->n_bins * K * K + 2 * K * C + 1;
 }
 
-// E-step workspace: per-CTA partial statistics, for at most this many CTAs.
-static const int kMaxEstepBlocks = 148 * 8;
 
 template <int K, bool MULTI, bool BINNED>
 static int launch_vit_t(const smf_hmm_tables* t, const VitArgs& a, bool wide, const DeviceInfo& di,
@@ -336,6 +462,26 @@ int smf_hmm_posterior(const smf_hmm_tables* tab, const void* obs, int obs_dtype,
   DeviceInfo di;
   rc = get_device_info(&di);
   if (rc != SMF_OK) return rc;
+  if (tab->n_channels == 1 && tab->n_bins == 1 && !g_force_generic &&
+      fb2_aligned(obs, obs_dtype, gamma, tab->n_states, gamma_state)) {
+    Fb2Args b;
+    memset(&b, 0, sizeof(b));
+    Fb2Plan p2;
+    if (plan_fb2(tab->n_states, n_pos, false, stats_len(tab), obs_elem_size(obs_dtype),
+                 gamma != nullptr && gamma_state >= 0, states != nullptr, di.max_smem_optin, &b, &p2) == SMF_OK) {
+      b.obs = obs;
+      b.N = n_reads;
+      b.L = (int)n_pos;
+      b.gamma = gamma;
+      b.gamma_state = gamma_state;
+      b.states = states;
+      b.loglik = loglik;
+      b.partials = nullptr;
+      b.S = stats_len(tab);
+      b.flush_every = 1;
+      return launch_fb2<false>(tab, obs_dtype, b, p2, di, nullptr, (cudaStream_t)stream);
+    }
+  }
   FbArgs a;
   memset(&a, 0, sizeof(a));
   FbPlan plan;
@@ -377,6 +523,30 @@ int smf_hmm_estep(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int
   DeviceInfo di;
   rc = get_device_info(&di);
   if (rc != SMF_OK) return rc;
+  if (tab->n_channels == 1 && tab->n_bins == 1 && !g_force_generic &&
+      fb2_aligned(obs, obs_dtype, nullptr, tab->n_states, -1)) {
+    Fb2Args b;
+    memset(&b, 0, sizeof(b));
+    Fb2Plan p2;
+    if (plan_fb2(tab->n_states, n_pos, true, S, obs_elem_size(obs_dtype), false, false, di.max_smem_optin, &b,
+                 &p2) == SMF_OK) {
+      b.obs = obs;
+      b.N = n_reads;
+      b.L = (int)n_pos;
+      b.gamma = nullptr;
+      b.gamma_state = -1;
+      b.states = nullptr;
+      b.loglik = nullptr;
+      b.partials = reinterpret_cast<double*>(workspace);
+      b.S = S;
+      b.flush_every = 8;
+      int nb2 = kMaxEstepBlocks;
+      rc = launch_fb2<true>(tab, obs_dtype, b, p2, di, &nb2, st);
+      if (rc != SMF_OK) return rc;
+      reduce_partials_kernel<<<(S + 127) / 128, 128, 0, st>>>(b.partials, nb2, S, stats);
+      return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
+    }
+  }
   FbArgs a;
   memset(&a, 0, sizeof(a));
   FbPlan plan;
