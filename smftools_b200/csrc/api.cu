@@ -250,32 +250,39 @@ static int plan_fb2(int K, int64_t L64, bool stats, int S, int es, bool want_gam
   const int out1_b = want_gamma_one ? align_up((Lpad + 4) * 4, 16) : 0;
   const int st_b = want_states ? align_up(Lpad + 32, 16) : 0;
   const int scan_b = align_up(32 * (KK + 2 * K) * 4 + 32 * 8, 16);
-  const int group_bytes = bar_b + in_b + stage_b + out1_b + st_b + scan_b;
+  const int obuf_b = stage_b + out1_b + st_b;  // one output staging set
   int groups = 256 / T;
   if (groups < 1) groups = 1;
   if (groups > 8) groups = 8;
-  for (;; --groups) {
-    const int warps = groups * T / 32;
-    const int wacc_b = stats ? align_up(warps * S * 8, 16) : 0;
-    const int total = wacc_b + groups * group_bytes;
-    if (total <= max_smem) {
-      a->off_wacc = 0;
-      a->off_group0 = wacc_b;
-      a->group_bytes = group_bytes;
-      a->goff_bar = 0;
-      a->goff_in = bar_b;
-      a->goff_stage = bar_b + in_b;
-      a->goff_out1 = bar_b + in_b + stage_b;
-      a->goff_st = bar_b + in_b + stage_b + out1_b;
-      a->goff_scan = bar_b + in_b + stage_b + out1_b + st_b;
-      a->T = T;
-      a->groups = groups;
-      plan->block = T * groups;
-      plan->smem = total;
-      return SMF_OK;
+  // prefer double-buffered output staging (bulk stores of read i drain while read i+1 computes)
+  for (int nbuf = stats ? 1 : 2; nbuf >= 1; --nbuf) {
+    const int group_bytes = bar_b + in_b + nbuf * obuf_b + scan_b;
+    for (int gr = groups; gr >= 1; --gr) {
+      if (nbuf == 2 && gr < groups && gr > 1) continue;  // only trade groups for buffers at the extremes
+      const int warps = gr * T / 32;
+      const int wacc_b = stats ? align_up(warps * S * 8, 16) : 0;
+      const int total = wacc_b + gr * group_bytes;
+      if (total <= max_smem) {
+        a->off_wacc = 0;
+        a->off_group0 = wacc_b;
+        a->group_bytes = group_bytes;
+        a->goff_bar = 0;
+        a->goff_in = bar_b;
+        a->goff_stage = bar_b + in_b;
+        a->goff_out1 = bar_b + in_b + stage_b;
+        a->goff_st = bar_b + in_b + stage_b + out1_b;
+        a->goff_scan = bar_b + in_b + nbuf * obuf_b;
+        a->nbuf = nbuf;
+        a->obuf_bytes = obuf_b;
+        a->T = T;
+        a->groups = gr;
+        plan->block = T * gr;
+        plan->smem = total;
+        return SMF_OK;
+      }
     }
-    if (groups == 1) return SMF_ERR_TOO_LONG;
   }
+  return SMF_ERR_TOO_LONG;
 }
 
 template <int K, bool STATS, typename ObsT>

@@ -31,6 +31,8 @@ struct Fb2Args {
   int T;            // threads per group (multiple of 32)
   int groups;       // reads in flight per CTA
   int flush_every;
+  int nbuf;         // output staging buffers per group (2 = a read's bulk stores drain while the next read computes)
+  int obuf_bytes;   // bytes between the two staging sets (stage | out1 | st)
   int off_wacc;     // CTA-wide double [warps][S]
   int off_group0;
   int group_bytes;
@@ -76,6 +78,7 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uin
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -229,9 +232,10 @@ __global__ void __launch_bounds__(MAXT) fb2_kernel(const __grid_constant__ FbTab
     const uint32_t in_mis =
         (uint32_t)(reinterpret_cast<uintptr_t>(obs_base + (size_t)n * row_bytes) & 15u) / (uint32_t)sizeof(ObsT);
     ObsT* s_in = reinterpret_cast<ObsT*>(s_in_raw) + in_mis;
-    float* s_stage = s_stage_base;
-    float* s_out1 = s_out1_base;
-    int8_t* s_st = s_st_base;
+    const size_t obuf = (a.nbuf > 1 && (iter & 1)) ? (size_t)a.obuf_bytes : 0;
+    float* s_stage = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_stage_base) + obuf);
+    float* s_out1 = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_out1_base) + obuf);
+    int8_t* s_st = s_st_base + obuf;
     if (w_gamma_all) s_stage += (reinterpret_cast<uintptr_t>(a.gamma + (size_t)n * L * K) & 15u) >> 2;
     if (w_gamma_one) s_out1 += (reinterpret_cast<uintptr_t>(a.gamma + (size_t)n * L) & 15u) >> 2;
     if (w_states) s_st += reinterpret_cast<uintptr_t>(a.states + (size_t)n * L) & 15u;
@@ -352,75 +356,74 @@ __global__ void __launch_bounds__(MAXT) fb2_kernel(const __grid_constant__ FbTab
       // the observation buffer is free: prefetch the next read of this group
       const long long nn = n + read_stride;
       if (nn < a.N) issue_load(nn);
-      // the previous read's bulk stores must have finished READING the staging buffers
-      bulk_wait_read_all();
+      // the bulk stores that last used this iteration's staging set must have finished READING it
+      if (a.nbuf > 1) bulk_wait_read_1(); else bulk_wait_read_all();
     }
     if (G > 1) {
-      if (gw == 0) {
-        float wp[K][K], ws[K][K];
+      if (gw < 2) {
+        // warp 0: exclusive prefix vectors u_w = pi T_0..T_{w-1};  warp 1: exclusive suffix vectors
+        // z_w = T_{w+1}..T_{G-1} 1   (T_w = product of warp w's chunk matrices)
+        float wm[K][K];
         if (lane < G) {
 #pragma unroll
           for (int i = 0; i < K; ++i)
 #pragma unroll
-            for (int j = 0; j < K; ++j) wp[i][j] = s_wtot[lane * KK + i * K + j];
+            for (int j = 0; j < K; ++j) wm[i][j] = s_wtot[lane * KK + i * K + j];
         } else {
-          mat_set_identity<K>(wp);
+          mat_set_identity<K>(wm);
         }
+        if (gw == 0) {
 #pragma unroll
-        for (int i = 0; i < K; ++i)
-#pragma unroll
-          for (int j = 0; j < K; ++j) ws[i][j] = wp[i][j];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          float q[K][K], r[K][K];
-#pragma unroll
-          for (int i = 0; i < K; ++i)
-#pragma unroll
-            for (int j = 0; j < K; ++j) q[i][j] = __shfl_up_sync(kFull, wp[i][j], d);
-          if (lane >= d) {
-            mat_mul<K>(q, wp, r);
+          for (int d = 1; d < 32; d <<= 1) {
+            float q[K][K], r[K][K];
 #pragma unroll
             for (int i = 0; i < K; ++i)
 #pragma unroll
-              for (int j = 0; j < K; ++j) wp[i][j] = r[i][j];
-            mat_rescale_if_small<K>(wp);
+              for (int j = 0; j < K; ++j) q[i][j] = __shfl_up_sync(kFull, wm[i][j], d);
+            if (lane >= d) {
+              mat_mul<K>(q, wm, r);
+#pragma unroll
+              for (int i = 0; i < K; ++i)
+#pragma unroll
+                for (int j = 0; j < K; ++j) wm[i][j] = r[i][j];
+              mat_rescale_if_small<K>(wm);
+            }
           }
 #pragma unroll
-          for (int i = 0; i < K; ++i)
+          for (int j = 0; j < K; ++j) {
+            float sacc = tab.pi[0] * wm[0][j];
 #pragma unroll
-            for (int j = 0; j < K; ++j) q[i][j] = __shfl_down_sync(kFull, ws[i][j], d);
-          if (lane + d < 32) {
-            mat_mul<K>(ws, q, r);
+            for (int i = 1; i < K; ++i) sacc = fmaf(tab.pi[i], wm[i][j], sacc);
+            float up = __shfl_up_sync(kFull, sacc, 1);
+            if (lane == 0) up = tab.pi[j];
+            s_u[lane * K + j] = up;
+          }
+        } else {
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            float q[K][K], r[K][K];
 #pragma unroll
             for (int i = 0; i < K; ++i)
 #pragma unroll
-              for (int j = 0; j < K; ++j) ws[i][j] = r[i][j];
-            mat_rescale_if_small<K>(ws);
+              for (int j = 0; j < K; ++j) q[i][j] = __shfl_down_sync(kFull, wm[i][j], d);
+            if (lane + d < 32) {
+              mat_mul<K>(wm, q, r);
+#pragma unroll
+              for (int i = 0; i < K; ++i)
+#pragma unroll
+                for (int j = 0; j < K; ++j) wm[i][j] = r[i][j];
+              mat_rescale_if_small<K>(wm);
+            }
           }
-        }
-        float uo[K], zo[K];
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
-          float s = tab.pi[0] * wp[0][j];
+          for (int i = 0; i < K; ++i) {
+            float sacc = wm[i][0];
 #pragma unroll
-          for (int i = 1; i < K; ++i) s = fmaf(tab.pi[i], wp[i][j], s);
-          uo[j] = s;
-        }
-#pragma unroll
-        for (int i = 0; i < K; ++i) {
-          float s = ws[i][0];
-#pragma unroll
-          for (int j = 1; j < K; ++j) s += ws[i][j];
-          zo[i] = s;
-        }
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          float up = __shfl_up_sync(kFull, uo[k], 1);
-          float zn = __shfl_down_sync(kFull, zo[k], 1);
-          if (lane == 0) up = tab.pi[k];
-          if (lane == 31) zn = 1.0f;
-          s_u[lane * K + k] = up;
-          s_z[lane * K + k] = zn;
+            for (int j = 1; j < K; ++j) sacc += wm[i][j];
+            float zn = __shfl_down_sync(kFull, sacc, 1);
+            if (lane == 31) zn = 1.0f;
+            s_z[lane * K + i] = zn;
+          }
         }
       }
       group_sync(bar_id, T);  // B2: boundary vectors visible; staging buffers reusable
