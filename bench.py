@@ -43,8 +43,8 @@ WORKLOADS = {
                 desc="headline shape: 1M x 10 kb posterior decode, one 65,536-read device-resident chunk"),
     "c3p_k3": dict(N=65_536, L=10_000, K=3, prob=True, op="posterior",
                    desc="1M x 10 kb m6A probabilistic, 3-state posterior decode, one 65,536-read chunk"),
-    "c3v": dict(N=65_536, L=10_000, K=3, prob=True, op="viterbi",
-                desc="BASELINE configs[2]: 1M x 10 kb 3-state Viterbi, one 65,536-read chunk"),
+    "c3v": dict(N=262_144, L=10_000, K=3, prob=True, op="viterbi",
+                desc="BASELINE configs[2]: 1M x 10 kb m6A probabilistic 3-state Viterbi, one 262,144-read chunk"),
     "c4": dict(N=262_144, L=8_000, K=4, prob=False, op="estep",
                desc="BASELINE configs[3]: 4-state Baum-Welch iteration, 262,144 reads x 8 kb per GPU"),
 }

@@ -86,6 +86,27 @@ static void build_fb_tables(const smf_hmm_tables* t, FbTables<K>* out) {
       out->rdl[k][c] = (float)((d - d_0) * log2e);
     }
   }
+  // fast-path tables (bin 0, channel 0)
+  {
+    double sdiag[K];
+    for (int j = 0; j < K; ++j) sdiag[j] = exp(t->log_trans[j * K + j]);
+    for (int i = 0; i < K; ++i)
+      for (int j = 0; j < K; ++j) out->Ap[i][j] = (i == j) ? 1.0f : (float)(exp(t->log_trans[i * K + j]) / sdiag[j]);
+    double p2sum = 0.0;
+    const double l0_0 = t->log_emit0[0];
+    const double d_0 = t->log_emit1[0] - l0_0;
+    (void)d_0;
+    for (int k = 0; k < K; ++k) {
+      const double ratio = sdiag[k] / sdiag[0];
+      out->pi2[k] = (float)(exp(t->log_start[k]) / ratio);
+      p2sum += (double)out->pi2[k];
+      const double l0 = t->log_emit0[k * C];
+      out->rl0p[k] = (float)((l0 - l0_0) * log2e + log2(ratio));
+      out->rmiss[k] = (float)log2(ratio);
+    }
+    out->log_s0 = t->log_trans[0];
+    out->log_pi2_sum = log(p2sum);
+  }
   out->nb = t->n_bins;
   out->C = C;
 }
@@ -356,8 +377,8 @@ static int launch_vit_t(const smf_hmm_tables* t, const VitArgs& a, bool wide, co
   const int C = a.C;
   const int row_stride = (kVitTile * C) | 1;
   const size_t elem = wide ? 8 : 4;
-  const size_t smem = (size_t)kVitReads * row_stride * elem + (size_t)kVitReads * (kVitTile + 4) +
-                      (BINNED ? (size_t)align_up(a.L, 16) : 0);
+  const size_t smem = (((size_t)kVitReads * row_stride * elem + 15) & ~(size_t)15) +
+                      (size_t)kVitReads * (kVitTile + 4) + (BINNED ? (size_t)align_up(a.L, 16) : 0);
   if ((long long)smem > di.max_smem_optin) return SMF_ERR_TOO_LONG;
   const long long nblk = (a.N + kVitReads - 1) / kVitReads;
   if (nblk > 0x7fffffffLL) return SMF_ERR_BAD_ARG;

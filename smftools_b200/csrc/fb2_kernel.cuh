@@ -207,6 +207,10 @@ __global__ void __launch_bounds__(MAXT) fb2_kernel(const __grid_constant__ FbTab
   const bool w_states = !STATS && a.states != nullptr;
   const uint32_t row_bytes = (uint32_t)L * (uint32_t)sizeof(ObsT);
   const char* obs_base = static_cast<const char*>(a.obs);
+  // this warp's slice of the read: positions [w0, w1)
+  const int w0 = gw * 32 * CH;
+  const int w1 = min(w0 + 32 * CH, L);
+  const int Lpad = ((L + CH - 1) / CH) * CH;
 
   auto issue_load = [&](long long n) {
     const char* src = obs_base + (size_t)n * row_bytes;
@@ -220,11 +224,34 @@ __global__ void __launch_bounds__(MAXT) fb2_kernel(const __grid_constant__ FbTab
   long long n = (long long)blockIdx.x * a.groups + g;
   if (gt == 0 && n < a.N) issue_load(n);
 
+  // column-normalised transitions: Ap[j][j] == 1 (see FbTables)
   float A[K][K];
 #pragma unroll
   for (int i = 0; i < K; ++i)
 #pragma unroll
-    for (int j = 0; j < K; ++j) A[i][j] = tab.A[0][i][j];
+    for (int j = 0; j < K; ++j) A[i][j] = tab.Ap[i][j];
+
+  // row-vector x Ap  and  Ap x column-vector with the unit diagonal folded into the addend
+  auto vecA = [&](const float (&x)[K], float (&y)[K]) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      float s = x[j];
+#pragma unroll
+      for (int i = 0; i < K; ++i)
+        if (i != j) s = fmaf(x[i], A[i][j], s);
+      y[j] = s;
+    }
+  };
+  auto Avec = [&](const float (&x)[K], float (&y)[K]) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      float s = x[i];
+#pragma unroll
+      for (int j = 0; j < K; ++j)
+        if (j != i) s = fmaf(A[i][j], x[j], s);
+      y[i] = s;
+    }
+  };
 
   int iter = 0;
   for (; n < a.N; n += read_stride, ++iter) {
@@ -243,12 +270,13 @@ __global__ void __launch_bounds__(MAXT) fb2_kernel(const __grid_constant__ FbTab
     mbar_wait(mbar, (uint32_t)(iter & 1));
 
     // ---------------- phase 1: chunk -> registers, transfer-matrix product ----------------
-    float rt[CH][KR];        // emission ratios b_k / b_0, k = 1..K-1
+    float rt[CH][KR];          // c_k(t) = s_k b_k / (s_0 b_0), k = 1..K-1
     float ov[STATS ? CH : 1];  // observation values (E-step emission statistics)
-    unsigned obsmask = 0;    // bit j: position t0+j observed
+    unsigned obsmask = 0;      // bit j: position t0+j observed (E-step only)
     float P[K][K];
     mat_set_identity<K>(P);
     float ll_sumo = 0.0f;
+    int ll_cnt = 0;
     bool prev_obs0 = false;  // observation just before this chunk present? (E-step xi validity)
     if (active) {
       if (STATS && !first) {
@@ -259,50 +287,56 @@ __global__ void __launch_bounds__(MAXT) fb2_kernel(const __grid_constant__ FbTab
         // pad the ragged end with missing observations (this thread is the only reader)
         for (int t = L; t < t0 + CH; ++t) s_in[t] = obs_missing<ObsT>();
       }
+      if (want_ll) {
+        // state-0 emission mass of the chunk as (count, sum o): combined in fp64 below
+        for (int j = 0; j < CH; ++j) {
+          const float o = obs_to_float<ObsT>(s_in[t0 + j]);
+          if (o == o) {
+            ll_sumo += o;
+            ++ll_cnt;
+          }
+        }
+      }
 #pragma unroll
       for (int j = 0; j < CH; ++j) {
         const float o = obs_to_float<ObsT>(s_in[t0 + j]);
         const bool m = (o == o);
-        obsmask |= m ? (1u << j) : 0u;
-        if (STATS) ov[j] = m ? o : 0.0f;
-        if (want_ll) ll_sumo += m ? o : 0.0f;
-        float b[K];
-        b[0] = 1.0f;
+        if (STATS) {
+          obsmask |= m ? (1u << j) : 0u;
+          ov[j] = m ? o : 0.0f;
+        }
+        float c[K];
+        c[0] = 1.0f;
 #pragma unroll
         for (int k = 1; k < K; ++k) {
-          b[k] = ex2_approx(m ? fmaf(o, tab.rdl[k][0], tab.rl0[k][0]) : 0.0f);
-          rt[j][k - 1] = b[k];
+          c[k] = ex2_approx(m ? fmaf(o, tab.rdl[k][0], tab.rl0p[k]) : tab.rmiss[k]);
+          rt[j][k - 1] = c[k];
         }
         if (j == 0) {
-          // P = I so far: P <- A diag(b), or diag(b) for the first position of the read
+          // P = I so far: P <- Ap diag(c), or diag(c) for the first position of the read
 #pragma unroll
           for (int i = 0; i < K; ++i)
 #pragma unroll
             for (int jj = 0; jj < K; ++jj) {
-              const float aij = first ? (i == jj ? 1.0f : 0.0f) : A[i][jj];
-              P[i][jj] = (jj == 0) ? aij : aij * b[jj];
+              const float aij = (i == jj) ? 1.0f : (first ? 0.0f : A[i][jj]);
+              P[i][jj] = (jj == 0) ? aij : aij * c[jj];
             }
         } else {
-          float Q[K][K];
 #pragma unroll
-          for (int i = 0; i < K; ++i)
+          for (int i = 0; i < K; ++i) {
+            float q[K];
+            vecA(P[i], q);
 #pragma unroll
-            for (int jj = 0; jj < K; ++jj) {
-              float s = P[i][0] * A[0][jj];
-#pragma unroll
-              for (int l = 1; l < K; ++l) s = fmaf(P[i][l], A[l][jj], s);
-              Q[i][jj] = (jj == 0) ? s : s * b[jj];
-            }
-#pragma unroll
-          for (int i = 0; i < K; ++i)
-#pragma unroll
-            for (int jj = 0; jj < K; ++jj) P[i][jj] = Q[i][jj];
+            for (int jj = 0; jj < K; ++jj) P[i][jj] = (jj == 0) ? q[jj] : q[jj] * c[jj];
+          }
         }
         if ((j & 3) == 3 || j == CH - 1) mat_scale<K>(P, pow2_rescale_noexp(mat_max<K>(P)));
       }
     }
 
     // ---------------- phase 2: warp-shuffle scans of the chunk matrices ----------------
+    // Kogge-Stone over the 32 lanes, inclusive prefix (pre) and suffix (suf); branch-free, with a
+    // power-of-two rescale every second level (entries stay far inside the fp32 range).
     float pre[K][K], suf[K][K];
 #pragma unroll
     for (int i = 0; i < K; ++i)
@@ -318,35 +352,37 @@ __global__ void __launch_bounds__(MAXT) fb2_kernel(const __grid_constant__ FbTab
       for (int i = 0; i < K; ++i)
 #pragma unroll
         for (int j = 0; j < K; ++j) q[i][j] = __shfl_up_sync(kFull, pre[i][j], d);
-      if (lane >= d) {
-        mat_mul<K>(q, pre, r);
+      mat_mul<K>(q, pre, r);
+      const bool up_ok = lane >= d;
 #pragma unroll
-        for (int i = 0; i < K; ++i)
+      for (int i = 0; i < K; ++i)
 #pragma unroll
-          for (int j = 0; j < K; ++j) pre[i][j] = r[i][j];
-        mat_rescale_if_small<K>(pre);
-      }
+        for (int j = 0; j < K; ++j) pre[i][j] = up_ok ? r[i][j] : pre[i][j];
 #pragma unroll
       for (int i = 0; i < K; ++i)
 #pragma unroll
         for (int j = 0; j < K; ++j) q[i][j] = __shfl_down_sync(kFull, suf[i][j], d);
-      if (lane + d < 32) {
-        mat_mul<K>(suf, q, r);
+      mat_mul<K>(suf, q, r);
+      const bool dn_ok = lane + d < 32;
 #pragma unroll
-        for (int i = 0; i < K; ++i)
+      for (int i = 0; i < K; ++i)
 #pragma unroll
-          for (int j = 0; j < K; ++j) suf[i][j] = r[i][j];
-        mat_rescale_if_small<K>(suf);
+        for (int j = 0; j < K; ++j) suf[i][j] = dn_ok ? r[i][j] : suf[i][j];
+      if (d == 2 || d == 8) {
+        mat_scale<K>(pre, pow2_rescale_noexp(mat_max<K>(pre)));
+        mat_scale<K>(suf, pow2_rescale_noexp(mat_max<K>(suf)));
       }
     }
 
     float u[K], z[K];
     if (G > 1) {
       if (lane == 31) {
+        // warp total (normalised)
+        const float sc = pow2_rescale_noexp(mat_max<K>(pre));
 #pragma unroll
         for (int i = 0; i < K; ++i)
 #pragma unroll
-          for (int j = 0; j < K; ++j) s_wtot[gw * KK + i * K + j] = pre[i][j];
+          for (int j = 0; j < K; ++j) s_wtot[gw * KK + i * K + j] = pre[i][j] * sc;
       }
       group_sync(bar_id, T);  // B1: chunk registers loaded by everyone, warp totals visible
     } else {
@@ -356,77 +392,50 @@ __global__ void __launch_bounds__(MAXT) fb2_kernel(const __grid_constant__ FbTab
       // the observation buffer is free: prefetch the next read of this group
       const long long nn = n + read_stride;
       if (nn < a.N) issue_load(nn);
-      // the bulk stores that last used this iteration's staging set must have finished READING it
-      if (a.nbuf > 1) bulk_wait_read_1(); else bulk_wait_read_all();
     }
     if (G > 1) {
-      if (gw < 2) {
-        // warp 0: exclusive prefix vectors u_w = pi T_0..T_{w-1};  warp 1: exclusive suffix vectors
-        // z_w = T_{w+1}..T_{G-1} 1   (T_w = product of warp w's chunk matrices)
-        float wm[K][K];
-        if (lane < G) {
+      // cross-warp boundary vectors by two threads: u_w = pi2 T_0..T_{w-1} (thread 0) and
+      // z_w = T_{w+1}..T_{G-1} 1 (thread 32); G <= 32 short dependent steps each
+      if (gt == 0) {
+        float x[K];
 #pragma unroll
-          for (int i = 0; i < K; ++i)
+        for (int k = 0; k < K; ++k) x[k] = tab.pi2[k];
+        for (int wv = 0; wv < G; ++wv) {
 #pragma unroll
-            for (int j = 0; j < K; ++j) wm[i][j] = s_wtot[lane * KK + i * K + j];
-        } else {
-          mat_set_identity<K>(wm);
-        }
-        if (gw == 0) {
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1) {
-            float q[K][K], r[K][K];
-#pragma unroll
-            for (int i = 0; i < K; ++i)
-#pragma unroll
-              for (int j = 0; j < K; ++j) q[i][j] = __shfl_up_sync(kFull, wm[i][j], d);
-            if (lane >= d) {
-              mat_mul<K>(q, wm, r);
-#pragma unroll
-              for (int i = 0; i < K; ++i)
-#pragma unroll
-                for (int j = 0; j < K; ++j) wm[i][j] = r[i][j];
-              mat_rescale_if_small<K>(wm);
-            }
-          }
+          for (int k = 0; k < K; ++k) s_u[wv * K + k] = x[k];
+          float y[K];
 #pragma unroll
           for (int j = 0; j < K; ++j) {
-            float sacc = tab.pi[0] * wm[0][j];
+            float sacc = x[0] * s_wtot[wv * KK + j];
 #pragma unroll
-            for (int i = 1; i < K; ++i) sacc = fmaf(tab.pi[i], wm[i][j], sacc);
-            float up = __shfl_up_sync(kFull, sacc, 1);
-            if (lane == 0) up = tab.pi[j];
-            s_u[lane * K + j] = up;
+            for (int i = 1; i < K; ++i) sacc = fmaf(x[i], s_wtot[wv * KK + i * K + j], sacc);
+            y[j] = sacc;
           }
-        } else {
+          const float sc = pow2_rescale_noexp(vec_max<K>(y));
 #pragma unroll
-          for (int d = 1; d < 32; d <<= 1) {
-            float q[K][K], r[K][K];
+          for (int k = 0; k < K; ++k) x[k] = y[k] * sc;
+        }
+      } else if (gt == 32) {
+        float x[K];
 #pragma unroll
-            for (int i = 0; i < K; ++i)
+        for (int k = 0; k < K; ++k) x[k] = 1.0f;
+        for (int wv = G - 1; wv >= 0; --wv) {
 #pragma unroll
-              for (int j = 0; j < K; ++j) q[i][j] = __shfl_down_sync(kFull, wm[i][j], d);
-            if (lane + d < 32) {
-              mat_mul<K>(wm, q, r);
-#pragma unroll
-              for (int i = 0; i < K; ++i)
-#pragma unroll
-                for (int j = 0; j < K; ++j) wm[i][j] = r[i][j];
-              mat_rescale_if_small<K>(wm);
-            }
-          }
+          for (int k = 0; k < K; ++k) s_z[wv * K + k] = x[k];
+          float y[K];
 #pragma unroll
           for (int i = 0; i < K; ++i) {
-            float sacc = wm[i][0];
+            float sacc = s_wtot[wv * KK + i * K] * x[0];
 #pragma unroll
-            for (int j = 1; j < K; ++j) sacc += wm[i][j];
-            float zn = __shfl_down_sync(kFull, sacc, 1);
-            if (lane == 31) zn = 1.0f;
-            s_z[lane * K + i] = zn;
+            for (int j = 1; j < K; ++j) sacc = fmaf(s_wtot[wv * KK + i * K + j], x[j], sacc);
+            y[i] = sacc;
           }
+          const float sc = pow2_rescale_noexp(vec_max<K>(y));
+#pragma unroll
+          for (int k = 0; k < K; ++k) x[k] = y[k] * sc;
         }
       }
-      group_sync(bar_id, T);  // B2: boundary vectors visible; staging buffers reusable
+      group_sync(bar_id, T);  // B2: boundary vectors visible
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         u[k] = s_u[gw * K + k];
@@ -436,7 +445,7 @@ __global__ void __launch_bounds__(MAXT) fb2_kernel(const __grid_constant__ FbTab
       __syncwarp();
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        u[k] = tab.pi[k];
+        u[k] = tab.pi2[k];
         z[k] = 1.0f;
       }
     }
@@ -471,12 +480,21 @@ __global__ void __launch_bounds__(MAXT) fb2_kernel(const __grid_constant__ FbTab
         sv += v[k];
         sw += w[k];
       }
-      const float rv = 1.0f / sv, rw = 1.0f / sw;
+      const float rv = want_ll ? (1.0f / sv) : rcp_approx(sv);
+      const float rw = rcp_approx(sw);
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         v[k] *= rv;
         w[k] *= rw;
       }
+    }
+
+    // this warp's previous bulk stores out of the staging set it is about to overwrite are done
+    if (!STATS) {
+      if (lane == 0) {
+        if (a.nbuf > 1) bulk_wait_read_1(); else bulk_wait_read_all();
+      }
+      __syncwarp();
     }
 
     // ---------------- phase 3: local forward / backward sweeps (fully unrolled) ----------------
@@ -491,23 +509,18 @@ __global__ void __launch_bounds__(MAXT) fb2_kernel(const __grid_constant__ FbTab
       for (int j = 0; j < CH; ++j) {
         float nx[K];
         if (j == 0) {
-          // first position of the read: alpha_0 = pi * b_0 (no transition)
+          float y[K];
+          vecA(al, y);
 #pragma unroll
           for (int jj = 0; jj < K; ++jj) {
-            float s = al[0] * A[0][jj];
-#pragma unroll
-            for (int i = 1; i < K; ++i) s = fmaf(al[i], A[i][jj], s);
-            s = first ? al[jj] : s;
+            const float s = first ? al[jj] : y[jj];  // alpha_0 = pi * b_0: no transition
             nx[jj] = (jj == 0) ? s : s * rt[0][jj - 1];
           }
         } else {
+          float y[K];
+          vecA(al, y);
 #pragma unroll
-          for (int jj = 0; jj < K; ++jj) {
-            float s = al[0] * A[0][jj];
-#pragma unroll
-            for (int i = 1; i < K; ++i) s = fmaf(al[i], A[i][jj], s);
-            nx[jj] = (jj == 0) ? s : s * rt[j][jj - 1];
-          }
+          for (int jj = 0; jj < K; ++jj) nx[jj] = (jj == 0) ? y[jj] : y[jj] * rt[j][jj - 1];
         }
         if ((j & 3) == 3) {
           const float sc = want_ll ? pow2_rescale(vec_max<K>(nx), e) : pow2_rescale_noexp(vec_max<K>(nx));
@@ -517,9 +530,9 @@ __global__ void __launch_bounds__(MAXT) fb2_kernel(const __grid_constant__ FbTab
 #pragma unroll
         for (int k = 0; k < K; ++k) al[k] = nx[k];
         if (K == 2) {
-          *reinterpret_cast<float2*>(stg + j * 2) = make_float2(nx[0], nx[1]);
+          *reinterpret_cast<float2*>(stg + j * 2) = make_float2(nx[0], nx[1 % K]);
         } else if (K == 4) {
-          *reinterpret_cast<float4*>(stg + j * 4) = make_float4(nx[0], nx[1], nx[2 % K], nx[3 % K]);
+          *reinterpret_cast<float4*>(stg + j * 4) = make_float4(nx[0], nx[1 % K], nx[2 % K], nx[3 % K]);
         } else {
 #pragma unroll
           for (int k = 0; k < K; ++k) stg[j * K + k] = nx[k];
@@ -529,9 +542,10 @@ __global__ void __launch_bounds__(MAXT) fb2_kernel(const __grid_constant__ FbTab
         float s = al[0];
 #pragma unroll
         for (int k = 1; k < K; ++k) s += al[k];
-        ll_thread = (double)logf(s) + (double)e * 0.6931471805599453094 +
-                    (double)__popc(obsmask) * tab.l00[0] + (double)ll_sumo * tab.dl0[0];
-        if (first) ll_thread += tab.log_pi_sum;
+        // log P(chunk | past) with the dropped scalars (s_0 per transition, b_0 per observed site) restored
+        ll_thread = (double)logf(s) + (double)e * 0.6931471805599453094 + (double)ll_cnt * tab.l00[0] +
+                    (double)ll_sumo * tab.dl0[0] + (double)(first ? CH - 1 : CH) * tab.log_s0;
+        if (first) ll_thread += tab.log_pi2_sum;
       }
 
       float bv[K];
@@ -552,14 +566,6 @@ __global__ void __launch_bounds__(MAXT) fb2_kernel(const __grid_constant__ FbTab
         const float r = rcp_approx(s);
 #pragma unroll
         for (int k = 0; k < K; ++k) gk[k] *= r;
-        int best = 0;
-        float gbest = gk[0];
-#pragma unroll
-        for (int k = 1; k < K; ++k)
-          if (gk[k] > gbest) {
-            gbest = gk[k];
-            best = k;
-          }
         // alpha of the previous position (this thread's chunk, or the incoming prefix vector)
         float alp[K];
         if (j > 0) {
@@ -598,7 +604,17 @@ __global__ void __launch_bounds__(MAXT) fb2_kernel(const __grid_constant__ FbTab
               if (gs == k) gsel = gk[k];
             s_out1[t0 + j] = gsel;
           }
-          if (w_states) s_st[t0 + j] = (int8_t)best;
+          if (w_states) {
+            int best = 0;
+            float gbest = gk[0];
+#pragma unroll
+            for (int k = 1; k < K; ++k)
+              if (gk[k] > gbest) {
+                gbest = gk[k];
+                best = k;
+              }
+            s_st[t0 + j] = (int8_t)best;
+          }
         }
 
         if (STATS) {
@@ -621,19 +637,10 @@ __global__ void __launch_bounds__(MAXT) fb2_kernel(const __grid_constant__ FbTab
           cb[0] = bv[0];
 #pragma unroll
           for (int k = 1; k < K; ++k) cb[k] = rt[j][k - 1] * bv[k];
+          Avec(cb, nb);
           if (STATS) {
-            float prod[K][K];
-#pragma unroll
-            for (int i = 0; i < K; ++i) {
-              float sN = 0.0f;
-#pragma unroll
-              for (int jj = 0; jj < K; ++jj) {
-                prod[i][jj] = A[i][jj] * cb[jj];
-                sN += prod[i][jj];
-              }
-              nb[i] = sN;
-            }
-            // xi_{t-1}(i,jj), t = t0+j > 0, both endpoints observed (HMM.py:1583-1591)
+            // xi_{t-1}(i,jj) ~ alpha_{t-1}(i) Ap[i][jj] cb[jj], t = t0+j > 0, counted when both
+            // endpoints are observed (HMM.py:1583-1591)
             const bool prev_obs = (j > 0) ? (((obsmask >> (j > 0 ? j - 1 : 0)) & 1u) != 0u) : prev_obs0;
             const bool valid = ((obsmask >> j) & 1u) && prev_obs;
             float s2 = 0.0f;
@@ -644,15 +651,10 @@ __global__ void __launch_bounds__(MAXT) fb2_kernel(const __grid_constant__ FbTab
             for (int i = 0; i < K; ++i) {
               const float ai = alp[i] * r2;
 #pragma unroll
-              for (int jj = 0; jj < K; ++jj) acc_xi[i * K + jj] = fmaf(ai, prod[i][jj], acc_xi[i * K + jj]);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < K; ++i) {
-              float sN = A[i][0] * cb[0];
-#pragma unroll
-              for (int jj = 1; jj < K; ++jj) sN = fmaf(A[i][jj], cb[jj], sN);
-              nb[i] = sN;
+              for (int jj = 0; jj < K; ++jj) {
+                const float pij = (i == jj) ? cb[jj] : A[i][jj] * cb[jj];
+                acc_xi[i * K + jj] = fmaf(ai, pij, acc_xi[i * K + jj]);
+              }
             }
           }
           if ((((CH - 1) - j) & 3) == 3) {
@@ -669,31 +671,34 @@ __global__ void __launch_bounds__(MAXT) fb2_kernel(const __grid_constant__ FbTab
     }
 
     if (STATS) acc_ll += ll_thread;
+
+    // ---------------- store: every warp bulk-stores its own slice (no CTA barrier) ----------------
+    if (!STATS) {
+      fence_proxy_async();  // make this lane's staging writes visible to the bulk-copy engine
+      __syncwarp();
+      if (lane == 0 && w0 < L) {
+        const uint32_t npos = (uint32_t)(w1 - w0);
+        if (w_gamma_all)
+          store_row_bulk<float>(a.gamma + ((size_t)n * L + w0) * K, s_stage + (size_t)w0 * K, npos * K * 4u);
+        if (w_gamma_one) store_row_bulk<float>(a.gamma + (size_t)n * L + w0, s_out1 + w0, npos * 4u);
+        if (w_states) store_row_bulk<int8_t>(a.states + (size_t)n * L + w0, s_st + w0, npos);
+      }
+      if (lane == 0) bulk_commit();  // one group per iteration (possibly empty) keeps the counts aligned
+    }
     if (a.loglik != nullptr) {
       const double wsum = warp_sum_f64(ll_thread);
       if (lane == 0) s_ll[gw] = wsum;
-    }
-    if (!STATS) fence_proxy_async();  // make the staging writes visible to the bulk-copy engine
-    group_sync(bar_id, T);            // B3: staging complete
-
-    // ---------------- store: bulk async shared -> global ----------------
-    if (gt == 0) {
-      if (a.loglik != nullptr) {
+      group_sync(bar_id, T);
+      if (gt == 0) {
         double s = 0.0;
         for (int i = 0; i < G; ++i) s += s_ll[i];
         a.loglik[n] = s;
-      }
-      if (!STATS) {
-        if (w_gamma_all) store_row_bulk<float>(a.gamma + (size_t)n * L * K, s_stage, (uint32_t)L * K * 4u);
-        if (w_gamma_one) store_row_bulk<float>(a.gamma + (size_t)n * L, s_out1, (uint32_t)L * 4u);
-        if (w_states) store_row_bulk<int8_t>(a.states + (size_t)n * L, s_st, (uint32_t)L);
-        bulk_commit();
       }
     }
     if (STATS && ((iter + 1) % a.flush_every) == 0) flush_stats();
   }
 
-  if (gt == 0) bulk_wait_all();  // all bulk stores complete before the CTA retires
+  if (!STATS && lane == 0) bulk_wait_all();  // all bulk stores complete before the CTA retires
   if (STATS) {
     flush_stats();
     const double wl = warp_sum_f64(acc_ll);
@@ -706,6 +711,7 @@ __global__ void __launch_bounds__(MAXT) fb2_kernel(const __grid_constant__ FbTab
       a.partials[(size_t)blockIdx.x * a.S + s] = tot;
     }
   }
+  (void)Lpad;
 }
 
 }  // namespace smf

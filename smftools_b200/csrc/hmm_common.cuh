@@ -26,6 +26,19 @@ struct FbTables {
   double l00[kMaxC];
   double dl0[kMaxC];
   double log_pi_sum;  // log(sum_k pi[k])
+  // Fast path (single channel, one transition matrix): column-normalised transitions
+  //   A = Ap diag(s),  s_j = A[j][j],  Ap[j][j] = 1
+  // so a step costs K(K-1) FMAs; s_j/s_0 is folded into the cached emission ratio
+  //   c_j(t) = s_j b_j(o_t) / (s_0 b_0(o_t)) = 2^(rl0p[j] + o*rdl[j][0])   (observed)
+  //                                           = 2^(rmiss[j])                (missing)
+  // and into the start vector pi2[j] = pi[j] s_0 / s_j.  Every step drops the scalar
+  // s_0 b_0(o_t); the log-likelihood adds it back ((L-1) log s_0 + state-0 emission mass).
+  float Ap[K][K];
+  float pi2[K];
+  float rl0p[K];
+  float rmiss[K];
+  double log_s0;
+  double log_pi2_sum;
   int nb;
   int C;
 };

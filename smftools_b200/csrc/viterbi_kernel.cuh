@@ -8,18 +8,23 @@
 // to torch's fp64 CPU result when the log tables come from the same torch ops.
 //
 // Data movement: a CTA of kVitReads reads stages a [reads x kVitTile positions] observation
-// tile through shared memory (coalesced row segments in, conflict-free per-thread rows out).
-// The K two-bit back-pointers of a position are packed into one int8 in a shared-memory tile,
-// which is flushed coalesced to a [N, L] byte scratch in HBM (one read's worth of
-// back-pointers is L bytes; 128 resident reads x 10 kb does not fit on chip), and streamed
-// back tile by tile, in reverse, for the back-trace.  States leave through the same tile.
+// tile through shared memory: each warp fetches whole 128-byte row segments (coalesced) one tile
+// AHEAD into registers, so the loads of tile i+1 are in flight while tile i is being decoded;
+// threads then read their own row (odd row stride: conflict free).  The K two-bit back-pointers
+// of a position are packed into one int8 in a shared-memory tile, which is flushed as 32-bit
+// words to a [N, L] byte scratch in HBM (one read's back-pointers are L bytes; 128 resident
+// reads x 10 kb do not fit on chip) and streamed back tile by tile, in reverse, for the
+// back-trace.  States leave through the same tile.
 #pragma once
+#include <type_traits>
+
 #include "hmm_common.cuh"
 
 namespace smf {
 
 constexpr int kVitReads = 128;  // reads (threads) per CTA
 constexpr int kVitTile = 32;    // positions per staged tile
+constexpr int kVitWarps = kVitReads / 32;
 
 struct VitArgs {
   const void* obs;
@@ -42,37 +47,103 @@ __global__ void __launch_bounds__(kVitReads) viterbi_kernel(const __grid_constan
   const int row_elems = kVitTile * C;
   const int row_stride = row_elems | 1;  // odd stride (in elements): conflict-free per-thread rows
   obs_t* tile = reinterpret_cast<obs_t*>(smem);
-  constexpr int kBpStride = kVitTile + 4;  // bytes; 9 words -> conflict-free byte rows
-  uint8_t* bpt = smem + (size_t)kVitReads * row_stride * sizeof(obs_t);
+  constexpr int kBpStride = kVitTile + 4;  // bytes; 9 words -> conflict-free rows, 4-byte aligned
+  uint8_t* bpt = smem + (((size_t)kVitReads * row_stride * sizeof(obs_t) + 15) & ~(size_t)15);
   int8_t* sbins = reinterpret_cast<int8_t*>(bpt + kVitReads * kBpStride);
 
   const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int wbase = (tid >> 5) * 32;  // first row of this warp
   const long long n0 = (long long)blockIdx.x * kVitReads;
   const int nrows = (int)min((long long)kVitReads, a.N - n0);
   const bool live = tid < nrows;
+  // 32-bit access to the byte matrices needs every row start 4-byte aligned
+  const bool words_ok = ((L & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.bp) & 3) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(a.states) & 3) == 0);
 
   if (BINNED) {
     for (int i = tid; i < L - 1; i += kVitReads) sbins[i] = a.bins[i];
   }
+
+  // ---- observation tile fetch (single channel: register prefetch, one row segment per step) ----
+  obs_t nxt[MULTI ? 1 : 32];
+  auto fetch_tile = [&](int tile0) {
+    if (MULTI) return;
+    const int tw = min(kVitTile, L - tile0);
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      const int row = wbase + r;
+      obs_t v = 0;
+      if (row < nrows && lane < tw) {
+        const long long gidx = (n0 + row) * (long long)L + tile0 + lane;
+        v = WIDE ? (obs_t)load_obs_f64(a.obs, a.obs_dtype, gidx) : (obs_t)load_obs(a.obs, a.obs_dtype, gidx);
+      }
+      nxt[r] = v;
+    }
+  };
+  auto commit_tile = [&]() {
+    if (MULTI) return;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) tile[(wbase + r) * row_stride + lane] = nxt[r];
+  };
+  auto load_tile_multi = [&](int tile0) {
+    const int tw = min(kVitTile, L - tile0);
+    const int n_el = tw * C;
+    for (int r = 0; r < 32; ++r) {
+      const int row = wbase + r;
+      if (row >= nrows) break;
+      const long long gbase = ((n0 + row) * (long long)L + tile0) * C;
+      for (int c = lane; c < n_el; c += 32)
+        tile[row * row_stride + c] =
+            WIDE ? (obs_t)load_obs_f64(a.obs, a.obs_dtype, gbase + c) : (obs_t)load_obs(a.obs, a.obs_dtype, gbase + c);
+    }
+  };
+  // byte tile <-> global: 32-bit words when aligned (8 words per row, 4 rows per warp step)
+  auto tile_to_global = [&](uint8_t* gmat, int tile0, int tw) {
+    if (words_ok && tw == kVitTile) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = wbase + i * 4 + (lane >> 3);
+        if (row < nrows)
+          *reinterpret_cast<uint32_t*>(gmat + (n0 + row) * (long long)L + tile0 + (lane & 7) * 4) =
+              *reinterpret_cast<const uint32_t*>(bpt + row * kBpStride + (lane & 7) * 4);
+      }
+    } else {
+      for (int r = 0; r < 32; ++r) {
+        const int row = wbase + r;
+        if (row < nrows && lane < tw) gmat[(n0 + row) * (long long)L + tile0 + lane] = bpt[row * kBpStride + lane];
+      }
+    }
+  };
+  auto global_to_tile = [&](const uint8_t* gmat, int tile0, int tw) {
+    if (words_ok && tw == kVitTile) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = wbase + i * 4 + (lane >> 3);
+        if (row < nrows)
+          *reinterpret_cast<uint32_t*>(bpt + row * kBpStride + (lane & 7) * 4) =
+              *reinterpret_cast<const uint32_t*>(gmat + (n0 + row) * (long long)L + tile0 + (lane & 7) * 4);
+      }
+    } else {
+      for (int r = 0; r < 32; ++r) {
+        const int row = wbase + r;
+        if (row < nrows && lane < tw) bpt[row * kBpStride + lane] = gmat[(n0 + row) * (long long)L + tile0 + lane];
+      }
+    }
+  };
 
   double delta[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) delta[k] = 0.0;
 
   // ---------------- forward max-plus sweep ----------------
+  fetch_tile(0);
   for (int tile0 = 0; tile0 < L; tile0 += kVitTile) {
     const int tw = min(kVitTile, L - tile0);
-    __syncthreads();  // previous tile fully consumed (and sbins visible)
-    for (int idx = tid; idx < nrows * tw * C; idx += kVitReads) {
-      const int row = idx / (tw * C);
-      const int col = idx - row * (tw * C);
-      const long long gidx = ((n0 + row) * (long long)L + tile0) * C + col;
-      if (WIDE)
-        tile[row * row_stride + col] = (obs_t)load_obs_f64(a.obs, a.obs_dtype, gidx);
-      else
-        tile[row * row_stride + col] = (obs_t)load_obs(a.obs, a.obs_dtype, gidx);
-    }
+    __syncthreads();  // previous tile fully consumed / flushed (and sbins visible)
+    if (MULTI) load_tile_multi(tile0); else commit_tile();
     __syncthreads();
+    if (tile0 + kVitTile < L) fetch_tile(tile0 + kVitTile);  // loads stay in flight during the decode below
     if (live) {
       const obs_t* my = tile + tid * row_stride;
       for (int j = 0; j < tw; ++j) {
@@ -83,19 +154,27 @@ __global__ void __launch_bounds__(kVitReads) viterbi_kernel(const __grid_constan
         if (!MULTI) {
           const double o = (double)my[j];
           if (o == o) {
+            if (o == 0.0) {  // 0*l1 + 1*l0 == l0 exactly
 #pragma unroll
-            for (int k = 0; k < K; ++k)
-              logB[k] = __dadd_rn(__dmul_rn(o, tab.l1[k][0]),
-                                  __dmul_rn(__dsub_rn(1.0, o), tab.l0[k][0]));
+              for (int k = 0; k < K; ++k) logB[k] = tab.l0[k][0];
+            } else if (o == 1.0) {  // 1*l1 + 0*l0 == l1 exactly
+#pragma unroll
+              for (int k = 0; k < K; ++k) logB[k] = tab.l1[k][0];
+            } else {
+              const double om = __dsub_rn(1.0, o);
+#pragma unroll
+              for (int k = 0; k < K; ++k)
+                logB[k] = __dadd_rn(__dmul_rn(o, tab.l1[k][0]), __dmul_rn(om, tab.l0[k][0]));
+            }
           }
         } else {
           for (int c = 0; c < C; ++c) {
             const double o = (double)my[j * C + c];
             if (o == o) {
+              const double om = __dsub_rn(1.0, o);
 #pragma unroll
               for (int k = 0; k < K; ++k)
-                logB[k] = __dadd_rn(logB[k], __dadd_rn(__dmul_rn(o, tab.l1[k][c]),
-                                                       __dmul_rn(__dsub_rn(1.0, o), tab.l0[k][c])));
+                logB[k] = __dadd_rn(logB[k], __dadd_rn(__dmul_rn(o, tab.l1[k][c]), __dmul_rn(om, tab.l0[k][c])));
             }
           }
         }
@@ -128,11 +207,7 @@ __global__ void __launch_bounds__(kVitReads) viterbi_kernel(const __grid_constan
       }
     }
     __syncthreads();
-    for (int idx = tid; idx < nrows * tw; idx += kVitReads) {
-      const int row = idx / tw;
-      const int col = idx - row * tw;
-      a.bp[(n0 + row) * (long long)L + tile0 + col] = bpt[row * kBpStride + col];
-    }
+    tile_to_global(a.bp, tile0, tw);
   }
 
   // last state: first maximum of delta[L-1] (torch.argmax, HMM.py:664)
@@ -152,12 +227,8 @@ __global__ void __launch_bounds__(kVitReads) viterbi_kernel(const __grid_constan
   for (int ti = ntiles - 1; ti >= 0; --ti) {
     const int tile0 = ti * kVitTile;
     const int tw = min(kVitTile, L - tile0);
-    __syncthreads();  // global bp writes of this CTA visible; previous tile flushed
-    for (int idx = tid; idx < nrows * tw; idx += kVitReads) {
-      const int row = idx / tw;
-      const int col = idx - row * tw;
-      bpt[row * kBpStride + col] = a.bp[(n0 + row) * (long long)L + tile0 + col];
-    }
+    __syncthreads();  // this CTA's global bp writes visible; previous tile flushed
+    global_to_tile(a.bp, tile0, tw);
     __syncthreads();
     if (live) {
       uint8_t* my = bpt + tid * kBpStride;
@@ -168,11 +239,7 @@ __global__ void __launch_bounds__(kVitReads) viterbi_kernel(const __grid_constan
       }
     }
     __syncthreads();
-    for (int idx = tid; idx < nrows * tw; idx += kVitReads) {
-      const int row = idx / tw;
-      const int col = idx - row * tw;
-      a.states[(n0 + row) * (long long)L + tile0 + col] = (int8_t)bpt[row * kBpStride + col];
-    }
+    tile_to_global(reinterpret_cast<uint8_t*>(a.states), tile0, tw);
   }
 }
 
