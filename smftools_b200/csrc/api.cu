@@ -306,13 +306,13 @@ static int plan_fb2(int K, int64_t L64, bool stats, int S, int es, bool want_gam
   return SMF_ERR_TOO_LONG;
 }
 
-template <int K, bool STATS, typename ObsT>
+template <int K, bool STATS, typename ObsT, int OUT>
 static int launch_fb2_t(const smf_hmm_tables* t, Fb2Args& a, const Fb2Plan& plan, const DeviceInfo& di,
                         int* nblocks_out, cudaStream_t stream) {
   constexpr int MAXT = STATS ? (K == 2 ? 640 : (K == 3 ? 512 : 384)) : (K == 4 ? 512 : 640);
   FbTables<K> tab;
   build_fb_tables<K>(t, &tab);
-  auto kern = fb2_kernel<K, kFb2Chunk, STATS, ObsT, MAXT>;
+  auto kern = fb2_kernel<K, kFb2Chunk, STATS, ObsT, MAXT, 1, OUT>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem) != cudaSuccess)
     return SMF_ERR_CUDA;
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -335,11 +335,19 @@ static int launch_fb2_t(const smf_hmm_tables* t, Fb2Args& a, const Fb2Plan& plan
 template <bool STATS>
 static int launch_fb2(const smf_hmm_tables* t, int obs_dtype, Fb2Args& a, const Fb2Plan& plan,
                       const DeviceInfo& di, int* nblocks, cudaStream_t stream) {
-#define SMF_FB2_CASE(KV)                                                                                    \
-  case KV:                                                                                                  \
-    if (obs_dtype == SMF_OBS_F32) return launch_fb2_t<KV, STATS, float>(t, a, plan, di, nblocks, stream);   \
-    if (obs_dtype == SMF_OBS_F64) return launch_fb2_t<KV, STATS, double>(t, a, plan, di, nblocks, stream);  \
-    return launch_fb2_t<KV, STATS, unsigned char>(t, a, plan, di, nblocks, stream);
+  // output-set specialisations exist for float observations; everything else decides at run time
+  const int out = (STATS || obs_dtype != SMF_OBS_F32 || a.gamma == nullptr || a.states == nullptr || a.loglik != nullptr)
+                      ? 2
+                      : (a.gamma_state < 0 ? 0 : 1);
+#define SMF_FB2_CASE(KV)                                                                                       \
+  case KV:                                                                                                     \
+    if (obs_dtype == SMF_OBS_F32) {                                                                            \
+      if (!STATS && out == 0) return launch_fb2_t<KV, false, float, 0>(t, a, plan, di, nblocks, stream);       \
+      if (!STATS && out == 1) return launch_fb2_t<KV, false, float, 1>(t, a, plan, di, nblocks, stream);       \
+      return launch_fb2_t<KV, STATS, float, 2>(t, a, plan, di, nblocks, stream);                               \
+    }                                                                                                          \
+    if (obs_dtype == SMF_OBS_F64) return launch_fb2_t<KV, STATS, double, 2>(t, a, plan, di, nblocks, stream);  \
+    return launch_fb2_t<KV, STATS, unsigned char, 2>(t, a, plan, di, nblocks, stream);
   switch (t->n_states) {
     SMF_FB2_CASE(2)
     SMF_FB2_CASE(3)

@@ -120,8 +120,10 @@ __device__ __forceinline__ void store_row_bulk(void* dst, const void* src, uint3
   for (uint32_t i = 0; i < tail / sizeof(UNIT); ++i) d[t0 + i] = s[t0 + i];
 }
 
-template <int K, int CH, bool STATS, typename ObsT, int MAXT>
-__global__ void __launch_bounds__(MAXT) fb2_kernel(const __grid_constant__ FbTables<K> tab,
+// OUT selects the output set at compile time: 0 = all-state posterior + states (decode),
+// 1 = single-state posterior + states (annotate), 2 = decided at run time from the pointers.
+template <int K, int CH, bool STATS, typename ObsT, int MAXT, int MINB, int OUT>
+__global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__ FbTables<K> tab,
                                                    const __grid_constant__ Fb2Args a) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr unsigned kFull = 0xffffffffu;
@@ -202,9 +204,9 @@ __global__ void __launch_bounds__(MAXT) fb2_kernel(const __grid_constant__ FbTab
   const bool first = (t0 == 0);
   const bool want_ll = STATS || (a.loglik != nullptr);
   const int gs = a.gamma_state;
-  const bool w_gamma_all = !STATS && a.gamma != nullptr && gs < 0;
-  const bool w_gamma_one = !STATS && a.gamma != nullptr && gs >= 0;
-  const bool w_states = !STATS && a.states != nullptr;
+  const bool w_gamma_all = !STATS && (OUT == 0 || (OUT == 2 && a.gamma != nullptr && gs < 0));
+  const bool w_gamma_one = !STATS && (OUT == 1 || (OUT == 2 && a.gamma != nullptr && gs >= 0));
+  const bool w_states = !STATS && (OUT != 2 || a.states != nullptr);
   const uint32_t row_bytes = (uint32_t)L * (uint32_t)sizeof(ObsT);
   const char* obs_base = static_cast<const char*>(a.obs);
   // this warp's slice of the read: positions [w0, w1)

@@ -38,7 +38,7 @@ struct VitArgs {
 };
 
 template <int K, bool MULTI, bool BINNED, bool WIDE>
-__global__ void __launch_bounds__(kVitReads) viterbi_kernel(const __grid_constant__ VitTables<K> tab,
+__global__ void __launch_bounds__(kVitReads, 6) viterbi_kernel(const __grid_constant__ VitTables<K> tab,
                                                             const __grid_constant__ VitArgs a) {
   using obs_t = typename std::conditional<WIDE, double, float>::type;
   extern __shared__ __align__(16) unsigned char smem[];
