@@ -276,7 +276,8 @@ static int plan_fb2(int K, int64_t L64, bool stats, int S, int es, bool want_gam
   if (groups < 1) groups = 1;
   if (groups > 8) groups = 8;
   // prefer double-buffered output staging (bulk stores of read i drain while read i+1 computes)
-  for (int nbuf = stats ? 1 : 2; nbuf >= 1; --nbuf) {
+  static const int env_nbuf = [] { const char* e = getenv("SMF_FB2_NBUF"); return e ? atoi(e) : 0; }();
+  for (int nbuf = (stats || env_nbuf == 1) ? 1 : 2; nbuf >= 1; --nbuf) {
     const int group_bytes = bar_b + in_b + nbuf * obuf_b + scan_b;
     for (int gr = groups; gr >= 1; --gr) {
       if (nbuf == 2 && gr < groups && gr > 1) continue;  // only trade groups for buffers at the extremes
@@ -313,6 +314,9 @@ static int launch_fb2_t(const smf_hmm_tables* t, Fb2Args& a, const Fb2Plan& plan
   FbTables<K> tab;
   build_fb_tables<K>(t, &tab);
   auto kern = fb2_kernel<K, kFb2Chunk, STATS, ObsT, MAXT, 1, OUT>;
+  static const int env_minb = [] { const char* e = getenv("SMF_FB2_MINB"); return e ? atoi(e) : 0; }();
+  if (K == 2 && !STATS && OUT == 0 && std::is_same<ObsT, float>::value && env_minb == 3 && plan.block <= 320)
+    kern = fb2_kernel<K, kFb2Chunk, STATS, ObsT, 320, 3, OUT>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem) != cudaSuccess)
     return SMF_ERR_CUDA;
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);

@@ -101,23 +101,25 @@ __device__ __forceinline__ double obs_missing<double>() { return __longlong_as_d
 template <>
 __device__ __forceinline__ unsigned char obs_missing<unsigned char>() { return 255; }
 
-// Store bytes [0, nbytes) of a shared buffer to global: the 16-byte aligned body with one bulk
-// async store (issued by the calling thread), head / tail bytes with plain stores.  `src` and
-// `dst` must be congruent modulo 16.  Called by ONE thread; UNIT is the element size used for
-// the ragged ends.
+// Store bytes [0, nbytes) of a shared buffer to global, called by a whole warp: the 16-byte
+// aligned body goes out as one bulk async store issued by lane 0, the ragged head / tail (< 16
+// bytes each) are copied by lanes 1..31 with plain stores.  `src` and `dst` must be congruent
+// modulo 16; UNIT is the element size (1 or 4) used for the ragged ends.
 template <typename UNIT>
-__device__ __forceinline__ void store_row_bulk(void* dst, const void* src, uint32_t nbytes) {
+__device__ __forceinline__ void store_row_bulk(void* dst, const void* src, uint32_t nbytes, int lane) {
   const uint32_t mis = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(dst) & 15u);
   uint32_t head = (16u - mis) & 15u;
   if (head > nbytes) head = nbytes;
   const uint32_t body = (nbytes - head) & ~15u;
   const uint32_t tail = nbytes - head - body;
-  if (body) bulk_store(static_cast<char*>(dst) + head, static_cast<const char*>(src) + head, body);
+  if (lane == 0 && body) bulk_store(static_cast<char*>(dst) + head, static_cast<const char*>(src) + head, body);
   const UNIT* s = static_cast<const UNIT*>(src);
   UNIT* d = static_cast<UNIT*>(dst);
-  for (uint32_t i = 0; i < head / sizeof(UNIT); ++i) d[i] = s[i];
-  const uint32_t t0 = (head + body) / sizeof(UNIT);
-  for (uint32_t i = 0; i < tail / sizeof(UNIT); ++i) d[t0 + i] = s[t0 + i];
+  const uint32_t nh = head / sizeof(UNIT), nt = tail / sizeof(UNIT);
+  const uint32_t tb = (head + body) / sizeof(UNIT);
+  const uint32_t i = (uint32_t)lane;
+  if (i >= 1 && i - 1 < nh) d[i - 1] = s[i - 1];            // lanes 1..15: head
+  if (i >= 16 && i - 16 < nt) d[tb + i - 16] = s[tb + i - 16];  // lanes 16..31: tail
 }
 
 // OUT selects the output set at compile time: 0 = all-state posterior + states (decode),
@@ -678,12 +680,12 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
     if (!STATS) {
       fence_proxy_async();  // make this lane's staging writes visible to the bulk-copy engine
       __syncwarp();
-      if (lane == 0 && w0 < L) {
+      if (w0 < L) {
         const uint32_t npos = (uint32_t)(w1 - w0);
         if (w_gamma_all)
-          store_row_bulk<float>(a.gamma + ((size_t)n * L + w0) * K, s_stage + (size_t)w0 * K, npos * K * 4u);
-        if (w_gamma_one) store_row_bulk<float>(a.gamma + (size_t)n * L + w0, s_out1 + w0, npos * 4u);
-        if (w_states) store_row_bulk<int8_t>(a.states + (size_t)n * L + w0, s_st + w0, npos);
+          store_row_bulk<float>(a.gamma + ((size_t)n * L + w0) * K, s_stage + (size_t)w0 * K, npos * K * 4u, lane);
+        if (w_gamma_one) store_row_bulk<float>(a.gamma + (size_t)n * L + w0, s_out1 + w0, npos * 4u, lane);
+        if (w_states) store_row_bulk<int8_t>(a.states + (size_t)n * L + w0, s_st + w0, npos, lane);
       }
       if (lane == 0) bulk_commit();  // one group per iteration (possibly empty) keeps the counts aligned
     }
