@@ -666,12 +666,7 @@ class BaseHMM(nn.Module):
             tables = self._host_tables()
             if workspace is None:
                 workspace = engine.estep_workspace(tables, device)
-            total = None
-            for obs in resident:
-                st = engine.estep(tables, obs, bins, workspace=workspace)
-                total = st if total is None else total + st
-            if total is None:
-                total = torch.zeros((engine.stats_len(tables),), dtype=torch.float64, device=device)
+            total = self._estep_local(tables, resident, bins, workspace, device)
             total = self._allreduce_stats(total)
             stats = total.cpu()
             hist.append(float(stats[-1].item()))
@@ -682,6 +677,17 @@ class BaseHMM(nn.Module):
             if len(hist) > 1 and abs(hist[-1] - hist[-2]) < float(tol) * max(abs(hist[-1]), 1.0):
                 break
         return hist
+
+    def _estep_local(self, tables, resident, bins, workspace, device) -> torch.Tensor:
+        """This rank's sufficient statistics [start | trans | emit_num | emit_den | ll] (fp64, on
+        the device) from ``smf_hmm_estep``."""
+        total = None
+        for obs in resident:
+            st = engine.estep(tables, obs, bins, workspace=workspace)
+            total = st if total is None else total + st
+        if total is None:
+            total = torch.zeros((engine.stats_len(tables),), dtype=torch.float64, device=device)
+        return total
 
     def _resident_chunks(self, src, device) -> List[torch.Tensor]:
         if isinstance(src, torch.Tensor) and src.is_cuda:
