@@ -142,8 +142,9 @@ def device_reads(N, L, K, prob, seed, device):
         n = hi - lo
         st = torch.randint(0, K, (n, nb), device=device, generator=gen)
         keep = torch.rand((n, nb), device=device, generator=gen) < 0.6  # sticky: often keep previous block's state
-        for b in range(1, nb):
-            st[:, b] = torch.where(keep[:, b], st[:, b - 1], st[:, b])
+        keep[:, 0] = False
+        src = torch.where(keep, torch.zeros_like(st), torch.arange(nb, device=device)[None, :].expand(n, nb))
+        st = st.gather(1, torch.cummax(src, dim=1).values)  # state of the last block that drew a fresh state
         p = em[st].repeat_interleave(blk, dim=1)[:, :L]
         u = torch.rand((n, L), device=device, generator=gen)
         if prob:
