@@ -400,43 +400,72 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
     if (G > 1) {
       // cross-warp boundary vectors by two threads: u_w = pi2 T_0..T_{w-1} (thread 0) and
       // z_w = T_{w+1}..T_{G-1} 1 (thread 32); G <= 32 short dependent steps each
+      // (the next warp total is fetched while the current step computes; rescale every 4th step)
       if (gt == 0) {
         float x[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) x[k] = tab.pi2[k];
+        float tn[KK];
+#pragma unroll
+        for (int e2 = 0; e2 < KK; ++e2) tn[e2] = s_wtot[e2];
         for (int wv = 0; wv < G; ++wv) {
+          float tc[KK];
+#pragma unroll
+          for (int e2 = 0; e2 < KK; ++e2) tc[e2] = tn[e2];
+          if (wv + 1 < G) {
+#pragma unroll
+            for (int e2 = 0; e2 < KK; ++e2) tn[e2] = s_wtot[(wv + 1) * KK + e2];
+          }
 #pragma unroll
           for (int k = 0; k < K; ++k) s_u[wv * K + k] = x[k];
           float y[K];
 #pragma unroll
           for (int j = 0; j < K; ++j) {
-            float sacc = x[0] * s_wtot[wv * KK + j];
+            float sacc = x[0] * tc[j];
 #pragma unroll
-            for (int i = 1; i < K; ++i) sacc = fmaf(x[i], s_wtot[wv * KK + i * K + j], sacc);
+            for (int i = 1; i < K; ++i) sacc = fmaf(x[i], tc[i * K + j], sacc);
             y[j] = sacc;
           }
-          const float sc = pow2_rescale_noexp(vec_max<K>(y));
+          if ((wv & 3) == 3) {
+            const float sc = pow2_rescale_noexp(vec_max<K>(y));
 #pragma unroll
-          for (int k = 0; k < K; ++k) x[k] = y[k] * sc;
+            for (int k = 0; k < K; ++k) y[k] *= sc;
+          }
+#pragma unroll
+          for (int k = 0; k < K; ++k) x[k] = y[k];
         }
       } else if (gt == 32) {
         float x[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) x[k] = 1.0f;
+        float tn[KK];
+#pragma unroll
+        for (int e2 = 0; e2 < KK; ++e2) tn[e2] = s_wtot[(G - 1) * KK + e2];
         for (int wv = G - 1; wv >= 0; --wv) {
+          float tc[KK];
+#pragma unroll
+          for (int e2 = 0; e2 < KK; ++e2) tc[e2] = tn[e2];
+          if (wv > 0) {
+#pragma unroll
+            for (int e2 = 0; e2 < KK; ++e2) tn[e2] = s_wtot[(wv - 1) * KK + e2];
+          }
 #pragma unroll
           for (int k = 0; k < K; ++k) s_z[wv * K + k] = x[k];
           float y[K];
 #pragma unroll
           for (int i = 0; i < K; ++i) {
-            float sacc = s_wtot[wv * KK + i * K] * x[0];
+            float sacc = tc[i * K] * x[0];
 #pragma unroll
-            for (int j = 1; j < K; ++j) sacc = fmaf(s_wtot[wv * KK + i * K + j], x[j], sacc);
+            for (int j = 1; j < K; ++j) sacc = fmaf(tc[i * K + j], x[j], sacc);
             y[i] = sacc;
           }
-          const float sc = pow2_rescale_noexp(vec_max<K>(y));
+          if (((G - 1 - wv) & 3) == 3) {
+            const float sc = pow2_rescale_noexp(vec_max<K>(y));
 #pragma unroll
-          for (int k = 0; k < K; ++k) x[k] = y[k] * sc;
+            for (int k = 0; k < K; ++k) y[k] *= sc;
+          }
+#pragma unroll
+          for (int k = 0; k < K; ++k) x[k] = y[k];
         }
       }
       group_sync(bar_id, T);  // B2: boundary vectors visible
