@@ -246,8 +246,8 @@ static int launch_fb(const smf_hmm_tables* t, FbArgs& a, const FbPlan& plan, con
 constexpr int kFb2Chunk = 17;
 
 static int fb2_max_threads(int K, bool stats) {
-  if (stats) return K == 2 ? 640 : (K == 3 ? 512 : 384);
-  return K == 4 ? 512 : 640;
+  if (stats) return K == 2 ? 640 : (K == 3 ? 512 : 480);
+  return K == 4 ? 576 : 640;
 }
 
 struct Fb2Plan {
@@ -310,13 +310,14 @@ static int plan_fb2(int K, int64_t L64, bool stats, int S, int es, bool want_gam
 template <int K, bool STATS, typename ObsT, int OUT>
 static int launch_fb2_t(const smf_hmm_tables* t, Fb2Args& a, const Fb2Plan& plan, const DeviceInfo& di,
                         int* nblocks_out, cudaStream_t stream) {
-  constexpr int MAXT = STATS ? (K == 2 ? 640 : (K == 3 ? 512 : 384)) : (K == 4 ? 512 : 640);
+  constexpr int MAXT = STATS ? (K == 2 ? 640 : (K == 3 ? 512 : 480)) : (K == 4 ? 576 : 640);
   FbTables<K> tab;
   build_fb_tables<K>(t, &tab);
   auto kern = fb2_kernel<K, kFb2Chunk, STATS, ObsT, MAXT, 1, OUT>;
   static const int env_minb = [] { const char* e = getenv("SMF_FB2_MINB"); return e ? atoi(e) : 0; }();
-  if (K == 2 && !STATS && OUT == 0 && std::is_same<ObsT, float>::value && env_minb == 3 && plan.block <= 320)
-    kern = fb2_kernel<K, kFb2Chunk, STATS, ObsT, 320, 3, OUT>;
+  if constexpr (K == 2 && !STATS && OUT == 0 && std::is_same<ObsT, float>::value) {
+    if (env_minb == 3 && plan.block <= 320) kern = fb2_kernel<K, kFb2Chunk, STATS, ObsT, 320, 3, OUT>;
+  }
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem) != cudaSuccess)
     return SMF_ERR_CUDA;
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -381,6 +382,15 @@ static int stats_len(const smf_hmm_tables* t) {
 }
 
 
+template <int K, bool MULTI, bool BINNED, int OBSK>
+static int launch_vit_o(const VitTables<K>& tab, const VitArgs& a, size_t smem, long long nblk, cudaStream_t stream) {
+  auto kern = viterbi_kernel<K, MULTI, BINNED, OBSK>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return SMF_ERR_CUDA;
+  kern<<<(int)nblk, kVitReads, smem, stream>>>(tab, a);
+  return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
+}
+
 template <int K, bool MULTI, bool BINNED>
 static int launch_vit_t(const smf_hmm_tables* t, const VitArgs& a, bool wide, const DeviceInfo& di,
                         cudaStream_t stream) {
@@ -394,19 +404,9 @@ static int launch_vit_t(const smf_hmm_tables* t, const VitArgs& a, bool wide, co
   if ((long long)smem > di.max_smem_optin) return SMF_ERR_TOO_LONG;
   const long long nblk = (a.N + kVitReads - 1) / kVitReads;
   if (nblk > 0x7fffffffLL) return SMF_ERR_BAD_ARG;
-  cudaError_t e;
-  if (wide) {
-    auto kern = viterbi_kernel<K, MULTI, BINNED, true>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return SMF_ERR_CUDA;
-    kern<<<(int)nblk, kVitReads, smem, stream>>>(tab, a);
-  } else {
-    auto kern = viterbi_kernel<K, MULTI, BINNED, false>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return SMF_ERR_CUDA;
-    kern<<<(int)nblk, kVitReads, smem, stream>>>(tab, a);
-  }
-  return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
+  if (a.obs_dtype == SMF_OBS_F64) return launch_vit_o<K, MULTI, BINNED, SMF_OBS_F64>(tab, a, smem, nblk, stream);
+  if (a.obs_dtype == SMF_OBS_U8) return launch_vit_o<K, MULTI, BINNED, SMF_OBS_U8>(tab, a, smem, nblk, stream);
+  return launch_vit_o<K, MULTI, BINNED, SMF_OBS_F32>(tab, a, smem, nblk, stream);
 }
 
 template <int K>

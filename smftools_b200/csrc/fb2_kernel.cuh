@@ -130,7 +130,10 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr unsigned kFull = 0xffffffffu;
   constexpr int KK = K * K;
-  constexpr int KR = K - 1;  // cached emission ratios per position
+  constexpr int KR = K - 1;  // emission ratios per position
+  // K = 4 would need 3*CH registers for the cached ratios: keep the observation instead and
+  // recompute the ratios (3 ex2 per position and phase; the kernel is FMA-bound there anyway)
+  constexpr bool RECOMP = (K >= 4);
 
   const int tid = threadIdx.x;
   const int T = a.T;
@@ -274,8 +277,20 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
     mbar_wait(mbar, (uint32_t)(iter & 1));
 
     // ---------------- phase 1: chunk -> registers, transfer-matrix product ----------------
-    float rt[CH][KR];          // c_k(t) = s_k b_k / (s_0 b_0), k = 1..K-1
-    float ov[STATS ? CH : 1];  // observation values (E-step emission statistics)
+    float rt[RECOMP ? 1 : CH][KR];          // c_k(t) = s_k b_k / (s_0 b_0), k = 1..K-1
+    float ov[(STATS || RECOMP) ? CH : 1];  // observation values (NaN = missing)
+    auto ratios = [&](int j, float (&c)[K]) {
+      c[0] = 1.0f;
+      if (RECOMP) {
+        const float o = ov[j];
+        const bool m = (o == o);
+#pragma unroll
+        for (int k = 1; k < K; ++k) c[k] = ex2_approx(m ? fmaf(o, tab.rdl[k][0], tab.rl0p[k]) : tab.rmiss[k]);
+      } else {
+#pragma unroll
+        for (int k = 1; k < K; ++k) c[k] = rt[RECOMP ? 0 : j][k - 1];
+      }
+    };
     unsigned obsmask = 0;      // bit j: position t0+j observed (E-step only)
     float P[K][K];
     mat_set_identity<K>(P);
@@ -305,16 +320,14 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
       for (int j = 0; j < CH; ++j) {
         const float o = obs_to_float<ObsT>(s_in[t0 + j]);
         const bool m = (o == o);
-        if (STATS) {
-          obsmask |= m ? (1u << j) : 0u;
-          ov[j] = m ? o : 0.0f;
-        }
+        if (STATS) obsmask |= m ? (1u << j) : 0u;
+        if (STATS || RECOMP) ov[j] = o;
         float c[K];
         c[0] = 1.0f;
 #pragma unroll
         for (int k = 1; k < K; ++k) {
           c[k] = ex2_approx(m ? fmaf(o, tab.rdl[k][0], tab.rl0p[k]) : tab.rmiss[k]);
-          rt[j][k - 1] = c[k];
+          if (!RECOMP) rt[RECOMP ? 0 : j][k - 1] = c[k];
         }
         if (j == 0) {
           // P = I so far: P <- Ap diag(c), or diag(c) for the first position of the read
@@ -541,19 +554,21 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
 #pragma unroll
       for (int j = 0; j < CH; ++j) {
         float nx[K];
+        float cf[K];
+        ratios(j, cf);
         if (j == 0) {
           float y[K];
           vecA(al, y);
 #pragma unroll
           for (int jj = 0; jj < K; ++jj) {
             const float s = first ? al[jj] : y[jj];  // alpha_0 = pi * b_0: no transition
-            nx[jj] = (jj == 0) ? s : s * rt[0][jj - 1];
+            nx[jj] = (jj == 0) ? s : s * cf[jj];
           }
         } else {
           float y[K];
           vecA(al, y);
 #pragma unroll
-          for (int jj = 0; jj < K; ++jj) nx[jj] = (jj == 0) ? y[jj] : y[jj] * rt[j][jj - 1];
+          for (int jj = 0; jj < K; ++jj) nx[jj] = (jj == 0) ? y[jj] : y[jj] * cf[jj];
         }
         if ((j & 3) == 3) {
           const float sc = want_ll ? pow2_rescale(vec_max<K>(nx), e) : pow2_rescale_noexp(vec_max<K>(nx));
@@ -666,10 +681,11 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
 
         const bool need_step = (j > 0) || STATS;
         if (need_step) {
-          float cb[K], nb[K];
+          float cb[K], nb[K], cr[K];
+          ratios(j, cr);
           cb[0] = bv[0];
 #pragma unroll
-          for (int k = 1; k < K; ++k) cb[k] = rt[j][k - 1] * bv[k];
+          for (int k = 1; k < K; ++k) cb[k] = cr[k] * bv[k];
           Avec(cb, nb);
           if (STATS) {
             // xi_{t-1}(i,jj) ~ alpha_{t-1}(i) Ap[i][jj] cb[jj], t = t0+j > 0, counted when both

@@ -37,9 +37,20 @@ struct VitArgs {
   uint8_t* bp;         // [N, L] packed back-pointers (scratch)
 };
 
-template <int K, bool MULTI, bool BINNED, bool WIDE>
-__global__ void __launch_bounds__(kVitReads, 6) viterbi_kernel(const __grid_constant__ VitTables<K> tab,
+// typed observation load: OBSK = SMF_OBS_F32 / F64 / U8 known at compile time
+template <int OBSK>
+__device__ __forceinline__ typename std::conditional<OBSK == SMF_OBS_F64, double, float>::type vit_load(
+    const void* base, long long idx) {
+  if (OBSK == SMF_OBS_F32) return __ldg(reinterpret_cast<const float*>(base) + idx);
+  if (OBSK == SMF_OBS_F64) return __ldg(reinterpret_cast<const double*>(base) + idx);
+  const unsigned v = __ldg(reinterpret_cast<const unsigned char*>(base) + idx);
+  return v == 0u ? 0.0f : (v == 1u ? 1.0f : __int_as_float(0x7fc00000));
+}
+
+template <int K, bool MULTI, bool BINNED, int OBSK>
+__global__ void __launch_bounds__(kVitReads, 4) viterbi_kernel(const __grid_constant__ VitTables<K> tab,
                                                             const __grid_constant__ VitArgs a) {
+  constexpr bool WIDE = (OBSK == SMF_OBS_F64);
   using obs_t = typename std::conditional<WIDE, double, float>::type;
   extern __shared__ __align__(16) unsigned char smem[];
   const int C = a.C;
@@ -70,15 +81,15 @@ __global__ void __launch_bounds__(kVitReads, 6) viterbi_kernel(const __grid_cons
   auto fetch_tile = [&](int tile0) {
     if (MULTI) return;
     const int tw = min(kVitTile, L - tile0);
+    long long gidx = (n0 + wbase) * (long long)L + tile0 + lane;
+    const bool col_ok = lane < tw;
 #pragma unroll
     for (int r = 0; r < 32; ++r) {
-      const int row = wbase + r;
       obs_t v = 0;
-      if (row < nrows && lane < tw) {
-        const long long gidx = (n0 + row) * (long long)L + tile0 + lane;
-        v = WIDE ? (obs_t)load_obs_f64(a.obs, a.obs_dtype, gidx) : (obs_t)load_obs(a.obs, a.obs_dtype, gidx);
-      }
+      if (col_ok && wbase + r < nrows)
+        v = vit_load<OBSK>(a.obs, gidx);
       nxt[r] = v;
+      gidx += L;
     }
   };
   auto commit_tile = [&]() {
@@ -94,8 +105,7 @@ __global__ void __launch_bounds__(kVitReads, 6) viterbi_kernel(const __grid_cons
       if (row >= nrows) break;
       const long long gbase = ((n0 + row) * (long long)L + tile0) * C;
       for (int c = lane; c < n_el; c += 32)
-        tile[row * row_stride + c] =
-            WIDE ? (obs_t)load_obs_f64(a.obs, a.obs_dtype, gbase + c) : (obs_t)load_obs(a.obs, a.obs_dtype, gbase + c);
+        tile[row * row_stride + c] = vit_load<OBSK>(a.obs, gbase + c);
     }
   };
   // byte tile <-> global: 32-bit words when aligned (8 words per row, 4 rows per warp step)
@@ -146,6 +156,7 @@ __global__ void __launch_bounds__(kVitReads, 6) viterbi_kernel(const __grid_cons
     if (tile0 + kVitTile < L) fetch_tile(tile0 + kVitTile);  // loads stay in flight during the decode below
     if (live) {
       const obs_t* my = tile + tid * row_stride;
+#pragma unroll 4
       for (int j = 0; j < tw; ++j) {
         const int t = tile0 + j;
         double logB[K];
@@ -153,18 +164,20 @@ __global__ void __launch_bounds__(kVitReads, 6) viterbi_kernel(const __grid_cons
         for (int k = 0; k < K; ++k) logB[k] = 0.0;
         if (!MULTI) {
           const double o = (double)my[j];
-          if (o == o) {
-            if (o == 0.0) {  // 0*l1 + 1*l0 == l0 exactly
+          const bool m = (o == o);
+          if (OBSK == SMF_OBS_U8) {
+            // binary code: o is exactly 0 or 1, and 0*l1 + 1*l0 == l0, 1*l1 + 0*l0 == l1 exactly
 #pragma unroll
-              for (int k = 0; k < K; ++k) logB[k] = tab.l0[k][0];
-            } else if (o == 1.0) {  // 1*l1 + 0*l0 == l1 exactly
+            for (int k = 0; k < K; ++k) logB[k] = m ? (o != 0.0 ? tab.l1[k][0] : tab.l0[k][0]) : 0.0;
+          } else {
+            // branch-free (lanes of a warp hold different reads): the three-rounding expression is
+            // also exact for o in {0, 1}
+            const double os = m ? o : 0.0;
+            const double om = __dsub_rn(1.0, os);
 #pragma unroll
-              for (int k = 0; k < K; ++k) logB[k] = tab.l1[k][0];
-            } else {
-              const double om = __dsub_rn(1.0, o);
-#pragma unroll
-              for (int k = 0; k < K; ++k)
-                logB[k] = __dadd_rn(__dmul_rn(o, tab.l1[k][0]), __dmul_rn(om, tab.l0[k][0]));
+            for (int k = 0; k < K; ++k) {
+              const double val = __dadd_rn(__dmul_rn(os, tab.l1[k][0]), __dmul_rn(om, tab.l0[k][0]));
+              logB[k] = m ? val : 0.0;
             }
           }
         } else {
@@ -232,6 +245,7 @@ __global__ void __launch_bounds__(kVitReads, 6) viterbi_kernel(const __grid_cons
     __syncthreads();
     if (live) {
       uint8_t* my = bpt + tid * kBpStride;
+#pragma unroll 4
       for (int j = tw - 1; j >= 0; --j) {
         const unsigned packed = my[j];
         my[j] = (uint8_t)s;  // state at position tile0 + j
