@@ -376,6 +376,45 @@ static bool fb2_aligned(const void* obs, int obs_dtype, const float* gamma, int 
   return true;
 }
 
+// Rescale cadence the scaled fp32 recursions need for this model.  Between two power-of-two
+// rescales an entry that still matters may shrink by f^R (f = worst per-step emission contrast
+// min_k b_k / max_k b_k over o in {0,1}) on top of the g^2 contrast a state switch at both chunk
+// ends costs (g = smallest / largest transition weight in a row); the product has to stay inside
+// the fp32 normal range with margin.  Typical fitted models need R = 4; models with emissions or
+// transitions at the eps clamp need R = 2 or 1 and are routed to the generic kernel.
+static int rescale_cadence(const smf_hmm_tables* t) {
+  const int K = t->n_states, C = t->n_channels;
+  double logf = 0.0;  // log of the worst emission contrast, summed over channels
+  for (int c = 0; c < C; ++c) {
+    double worst = 0.0;
+    for (int o = 0; o < 2; ++o) {
+      double lo = 1e300, hi = -1e300;
+      for (int k = 0; k < K; ++k) {
+        const double v = o ? t->log_emit1[k * C + c] : t->log_emit0[k * C + c];
+        lo = v < lo ? v : lo;
+        hi = v > hi ? v : hi;
+      }
+      if (lo - hi < worst) worst = lo - hi;
+    }
+    logf += worst;
+  }
+  double logg = 0.0;
+  for (int b = 0; b < t->n_bins; ++b)
+    for (int i = 0; i < K; ++i) {
+      double lo = 1e300, hi = -1e300;
+      for (int j = 0; j < K; ++j) {
+        const double v = t->log_trans[(b * K + i) * K + j];
+        lo = v < lo ? v : lo;
+        hi = v > hi ? v : hi;
+      }
+      if (lo - hi < logg) logg = lo - hi;
+    }
+  const double budget = -64.0;  // ln(1e-28): stay well inside fp32's normal range
+  for (int R = 4; R >= 2; R >>= 1)
+    if (2.0 * logg + (R + 1) * logf >= budget) return R;
+  return 1;
+}
+
 static int stats_len(const smf_hmm_tables* t) {
   const int K = t->n_states, C = t->n_channels;
   return K + t->n_bins * K * K + 2 * K * C + 1;
@@ -502,7 +541,8 @@ int smf_hmm_posterior(const smf_hmm_tables* tab, const void* obs, int obs_dtype,
   DeviceInfo di;
   rc = get_device_info(&di);
   if (rc != SMF_OK) return rc;
-  if (tab->n_channels == 1 && tab->n_bins == 1 && !g_force_generic &&
+  const int cadence = rescale_cadence(tab);
+  if (tab->n_channels == 1 && tab->n_bins == 1 && !g_force_generic && cadence == 4 &&
       fb2_aligned(obs, obs_dtype, gamma, tab->n_states, gamma_state)) {
     Fb2Args b;
     memset(&b, 0, sizeof(b));
@@ -541,6 +581,7 @@ int smf_hmm_posterior(const smf_hmm_tables* tab, const void* obs, int obs_dtype,
   a.partials = nullptr;
   a.S = stats_len(tab);
   a.flush_every = 1;
+  a.resc_mask = cadence - 1;
   return launch_fb<false>(tab, a, plan, di, nullptr, (cudaStream_t)stream);
 }
 
@@ -563,7 +604,8 @@ int smf_hmm_estep(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int
   DeviceInfo di;
   rc = get_device_info(&di);
   if (rc != SMF_OK) return rc;
-  if (tab->n_channels == 1 && tab->n_bins == 1 && !g_force_generic &&
+  const int cadence = rescale_cadence(tab);
+  if (tab->n_channels == 1 && tab->n_bins == 1 && !g_force_generic && cadence == 4 &&
       fb2_aligned(obs, obs_dtype, nullptr, tab->n_states, -1)) {
     Fb2Args b;
     memset(&b, 0, sizeof(b));
@@ -605,6 +647,7 @@ int smf_hmm_estep(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int
   a.partials = reinterpret_cast<double*>(workspace);
   a.S = S;
   a.flush_every = 8;
+  a.resc_mask = cadence - 1;
   int nblocks = kMaxEstepBlocks;
   rc = launch_fb<true>(tab, a, plan, di, &nblocks, st);
   if (rc != SMF_OK) return rc;

@@ -42,6 +42,7 @@ struct FbArgs {
   int T;               // threads per group (multiple of 32)
   int groups;          // reads in flight per CTA
   int flush_every;     // STATS: reads between float->double flushes
+  int resc_mask;       // rescale when (step & resc_mask) == resc_mask: 3 = every 4th step, 1, 0 = every step
   // dynamic shared memory layout (byte offsets)
   int off_bins;        // CTA-wide int8 [L]
   int off_sA;          // CTA-wide float [nb*K*K]
@@ -349,7 +350,7 @@ __global__ void __launch_bounds__(MAXT) fb_kernel(const __grid_constant__ FbTabl
         for (int i = 0; i < K; ++i)
 #pragma unroll
           for (int j = 0; j < K; ++j) P[i][j] = Q[i][j];
-        if (((t - t0) & 3) == 3) mat_scale<K>(P, pow2_rescale_noexp(mat_max<K>(P)));
+        if (((t - t0) & a.resc_mask) == a.resc_mask) mat_scale<K>(P, pow2_rescale_noexp(mat_max<K>(P)));
       }
       mat_scale<K>(P, pow2_rescale_noexp(mat_max<K>(P)));
       if (want_ll) {
@@ -587,7 +588,7 @@ __global__ void __launch_bounds__(MAXT) fb_kernel(const __grid_constant__ FbTabl
               nx[j] = s * b[j];
             }
           }
-          if (((t - t0) & 3) == 3) {
+          if (((t - t0) & a.resc_mask) == a.resc_mask) {
             const float sc = pow2_rescale(vec_max<K>(nx), e);
 #pragma unroll
             for (int k = 0; k < K; ++k) nx[k] *= sc;
@@ -746,7 +747,7 @@ __global__ void __launch_bounds__(MAXT) fb_kernel(const __grid_constant__ FbTabl
               }
             }
           }
-          if ((((t1 - 1) - t) & 3) == 3) {
+          if ((((t1 - 1) - t) & a.resc_mask) == a.resc_mask) {
             const float sc = pow2_rescale_noexp(vec_max<K>(nb));
 #pragma unroll
             for (int k = 0; k < K; ++k) nb[k] *= sc;
