@@ -203,22 +203,23 @@ def _cpu_worker(args):
     os.environ["OMP_NUM_THREADS"] = "1"
     os.environ["MKL_NUM_THREADS"] = "1"
     os.environ["OPENBLAS_NUM_THREADS"] = "1"
-    n, L, K, prob, op, seed = args
+    n, L, K, prob, op, seed, reps = args
     from oracle import hmm_oracle as O
 
     X = O.synth_reads(n, L, K, seed, prob=prob, nan_rate=0.3, truncate=False).astype(np.float64)
     p = O.synth_params(K)
     t0 = time.perf_counter()
-    if op == "posterior":
-        O.decode(X, p, None, "marginal")
-    elif op == "viterbi":
-        O.decode(X, p, None, "viterbi")
-    else:
-        O.estep(X, p, None)
+    for _ in range(reps):  # same batch again: bounded memory, more CPU seconds
+        if op == "posterior":
+            O.decode(X, p, None, "marginal")
+        elif op == "viterbi":
+            O.decode(X, p, None, "viterbi")
+        else:
+            O.estep(X, p, None)
     return time.perf_counter() - t0
 
 
-def cpu_baseline(wl, cores=None, reads_per_worker=None):
+def cpu_baseline(wl, cores=None, reads_per_worker=None, reps=4):
     """Time the CPU port on a bounded sample: P single-threaded worker processes (the reference's
     own way of using all cores, parallel_utils.py:25-96), wall = slowest worker."""
     import multiprocessing as mp
@@ -230,15 +231,15 @@ def cpu_baseline(wl, cores=None, reads_per_worker=None):
     if reads_per_worker is None:
         reads_per_worker = max(64, int(8e6 // L))  # ~8e6 read-positions per worker (~10-20 s)
     ctx = mp.get_context("spawn")
-    args = [(reads_per_worker, L, K, wl["prob"], wl["op"], 9000 + i) for i in range(workers)]
+    args = [(reads_per_worker, L, K, wl["prob"], wl["op"], 9000 + i, reps) for i in range(workers)]
     t0 = time.perf_counter()
     with ctx.Pool(workers) as pool:
         times = pool.map(_cpu_worker, args)
     wall_all = time.perf_counter() - t0
-    rp = workers * reads_per_worker * L
+    rp = workers * reads_per_worker * L * reps
     return {
         "value": rp / max(times), "unit": "read-positions/s", "cores": workers, "kind": "port",
-        "sample": f"{workers} workers x {reads_per_worker} reads x {L} positions, K={K}, op={wl['op']}, "
+        "sample": f"{workers} workers x {reps} passes x {reads_per_worker} reads x {L} positions, K={K}, op={wl['op']}, "
                   f"numpy fp64 oracle port, compute time of slowest worker {max(times):.1f}s (pool wall {wall_all:.1f}s)",
     }
 
@@ -253,12 +254,12 @@ def run_reference(args, wl):
     # bounded: the whole run must end within a few minutes
     per = max(32, int(2.5e6 // wl["L"]))
     for i in range(total):
-        last = cpu_baseline(wl, reads_per_worker=per)
+        last = cpu_baseline(wl, reads_per_worker=per, reps=2)
         if i >= args.warmup:
             vals.append(last["value"])
     v = statistics.median(vals)
     last["value"] = v
-    rp_step = last["cores"] * per * wl["L"]
+    rp_step = last["cores"] * per * wl["L"] * 2
     line = {
         "impl": "reference", "metric": "HMM read-positions/sec", "value": v, "unit": "read-positions/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * rp_step / v,

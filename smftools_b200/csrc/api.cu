@@ -140,55 +140,92 @@ struct FbPlan {
   int T, chunk, groups, smem, block;
 };
 
-// Launch-shape selection for the fused forward-backward kernel.
+// Launch-shape selection for the generic forward-backward kernel.  A read that does not fit the
+// on-chip staging at once is cut into nseg <= kMaxSeg segments (two passes, see fb_kernel.cuh).
 static int plan_fb(int K, int C, int nb, int64_t L64, bool stats, int S, int max_smem, FbArgs* a,
                    FbPlan* plan) {
   if (L64 < 1 || L64 > (1 << 24)) return SMF_ERR_TOO_LONG;
   const int L = (int)L64;
   const int maxT = fb_max_threads(K, stats);
-  int T = align_up((L + 16) / 17, 32);
-  if (T > maxT) T = maxT;
-  if (T < 32) T = 32;
-  int chunk = (L + T - 1) / T;
-  if ((chunk & 1) == 0) ++chunk;
-  T = align_up((L + chunk - 1) / chunk, 32);
   const int KK = K * K;
-  const int in_b = align_up(L * C * 4, 16);
-  const int stage_b = align_up(L * K * 4, 16);
-  const int st_b = align_up(L + 16, 16);
-  const int scan_b = align_up(32 * (KK + 2 * K) * 4 + 32 * 8, 16);
-  const int group_bytes = in_b + stage_b + st_b + scan_b;
-  int groups = 256 / T;
-  if (groups < 1) groups = 1;
-  if (groups > 8) groups = 8;
   const bool binned = nb > 1;
-  for (;; --groups) {
-    const int warps = groups * T / 32;
-    const int bins_b = binned ? align_up(L, 16) : 0;
-    const int sA_b = binned ? align_up(nb * KK * 4, 16) : 0;
-    const int wacc_b = stats ? align_up(warps * S * 8, 16) : 0;
-    const int total = bins_b + sA_b + wacc_b + groups * group_bytes;
-    if (total <= max_smem) {
-      a->off_bins = 0;
-      a->off_sA = bins_b;
-      a->off_wacc = bins_b + sA_b;
-      a->off_group0 = bins_b + sA_b + wacc_b;
-      a->group_bytes = group_bytes;
-      a->goff_in = 0;
-      a->goff_stage = in_b;
-      a->goff_st = in_b + stage_b;
-      a->goff_scan = in_b + stage_b + st_b;
-      a->chunk = chunk;
-      a->T = T;
-      a->groups = groups;
-      plan->T = T;
-      plan->chunk = chunk;
-      plan->groups = groups;
-      plan->smem = total;
-      plan->block = T * groups;
-      return SMF_OK;
+  const int scan_b = align_up(32 * (KK + 2 * K) * 4 + 32 * 8 + kMaxSeg * (KK + 2 * K) * 4, 16);
+  const int sA_b = binned ? align_up(nb * KK * 4, 16) : 0;
+  auto bytes_for = [&](int Lseg) {
+    return align_up(Lseg * C * 4, 16) + align_up(Lseg * K * 4, 16) + align_up(Lseg + 16, 16) + scan_b;
+  };
+  // single segment: the layout used since v1
+  {
+    int T = align_up((L + 16) / 17, 32);
+    if (T > maxT) T = maxT;
+    if (T < 32) T = 32;
+    int chunk = (L + T - 1) / T;
+    if ((chunk & 1) == 0) ++chunk;
+    T = align_up((L + chunk - 1) / chunk, 32);
+    const int group_bytes = bytes_for(L);
+    int groups = 256 / T;
+    if (groups < 1) groups = 1;
+    if (groups > 8) groups = 8;
+    for (; groups >= 1; --groups) {
+      const int warps = groups * T / 32;
+      const int bins_b = binned ? align_up(L, 16) : 0;
+      const int wacc_b = stats ? align_up(warps * S * 8, 16) : 0;
+      const int total = bins_b + sA_b + wacc_b + groups * group_bytes;
+      if (total <= max_smem) {
+        a->off_bins = 0;
+        a->off_sA = bins_b;
+        a->off_wacc = bins_b + sA_b;
+        a->off_group0 = bins_b + sA_b + wacc_b;
+        a->group_bytes = group_bytes;
+        a->goff_in = 0;
+        a->goff_stage = align_up(L * C * 4, 16);
+        a->goff_st = a->goff_stage + align_up(L * K * 4, 16);
+        a->goff_scan = a->goff_st + align_up(L + 16, 16);
+        a->chunk = chunk;
+        a->T = T;
+        a->groups = groups;
+        a->nseg = 1;
+        plan->T = T;
+        plan->chunk = chunk;
+        plan->groups = groups;
+        plan->smem = total;
+        plan->block = T * groups;
+        return SMF_OK;
+      }
     }
-    if (groups == 1) return SMF_ERR_TOO_LONG;
+  }
+  // segmented: all threads, the longest odd chunk whose segment fits
+  {
+    const int T = maxT;
+    const int wacc_b = stats ? align_up((T / 32) * S * 8, 16) : 0;
+    int chunk = 1;
+    for (int c = 3; c < 4096; c += 2) {
+      if (sA_b + wacc_b + bytes_for(T * c) > max_smem) break;
+      chunk = c;
+    }
+    const int Lseg = T * chunk;
+    if (sA_b + wacc_b + bytes_for(Lseg) > max_smem) return SMF_ERR_TOO_LONG;
+    const int nseg = (L + Lseg - 1) / Lseg;
+    if (nseg > kMaxSeg) return SMF_ERR_TOO_LONG;
+    a->off_bins = 0;
+    a->off_sA = 0;
+    a->off_wacc = sA_b;
+    a->off_group0 = sA_b + wacc_b;
+    a->group_bytes = bytes_for(Lseg);
+    a->goff_in = 0;
+    a->goff_stage = align_up(Lseg * C * 4, 16);
+    a->goff_st = a->goff_stage + align_up(Lseg * K * 4, 16);
+    a->goff_scan = a->goff_st + align_up(Lseg + 16, 16);
+    a->chunk = chunk;
+    a->T = T;
+    a->groups = 1;
+    a->nseg = nseg;
+    plan->T = T;
+    plan->chunk = chunk;
+    plan->groups = 1;
+    plan->smem = sA_b + wacc_b + bytes_for(Lseg);
+    plan->block = T;
+    return SMF_OK;
   }
 }
 

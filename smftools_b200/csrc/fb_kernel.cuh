@@ -25,6 +25,8 @@
 
 namespace smf {
 
+constexpr int kMaxSeg = 64;  // segments per read the generic kernel can chain
+
 struct FbArgs {
   const void* obs;
   int obs_dtype;
@@ -43,6 +45,7 @@ struct FbArgs {
   int groups;          // reads in flight per CTA
   int flush_every;     // STATS: reads between float->double flushes
   int resc_mask;       // rescale when (step & resc_mask) == resc_mask: 3 = every 4th step, 1, 0 = every step
+  int nseg;            // segments per read (1 = the whole read is staged on chip at once)
   // dynamic shared memory layout (byte offsets)
   int off_bins;        // CTA-wide int8 [L]
   int off_sA;          // CTA-wide float [nb*K*K]
@@ -198,10 +201,19 @@ __global__ void __launch_bounds__(MAXT) fb_kernel(const __grid_constant__ FbTabl
   float* s_u = s_wtot + 32 * KK;                                  // [32][K]
   float* s_z = s_u + 32 * K;                                      // [32][K]
   double* s_ll = reinterpret_cast<double*>(s_z + 32 * K);         // [32]
+  // long reads: per-segment transfer matrices and boundary vectors
+  float* s_segT = reinterpret_cast<float*>(s_ll + 32);            // [kMaxSeg][KK]
+  float* s_useg = s_segT + kMaxSeg * KK;                          // [kMaxSeg][K]
+  float* s_zseg = s_useg + kMaxSeg * K;                           // [kMaxSeg][K]
+  const int nseg = a.nseg;
+  const int Lseg = T * chunk;
+  if (nseg > 1) sbins = a.bins;  // too long for a shared copy: read the bin indices from global
 
-  if (BINNED) {
+  if (BINNED && nseg == 1) {
     int8_t* wb = reinterpret_cast<int8_t*>(smem + a.off_bins);
     for (int i = tid; i < L - 1; i += blockDim.x) wb[i] = a.bins[i];
+  }
+  if (BINNED) {
     float* wA = reinterpret_cast<float*>(smem + a.off_sA);
     for (int i = tid; i < tab.nb * KK; i += blockDim.x) wA[i] = (&tab.A[0][0][0])[i];
   }
@@ -228,9 +240,7 @@ __global__ void __launch_bounds__(MAXT) fb_kernel(const __grid_constant__ FbTabl
     for (int k = 0; k < K; ++k) acc_start[k] = 0.0f;
   }
 
-  const int t0 = gt * chunk;
-  const int t1 = min(t0 + chunk, L);
-  const bool active = t0 < L;
+  const int t0 = gt * chunk;  // segment-local first position of this thread
   const bool want_ll = STATS || (a.loglik != nullptr);
 
   // Flush fp32 register statistics into this warp's fp64 shared accumulators.
@@ -293,11 +303,34 @@ __global__ void __launch_bounds__(MAXT) fb_kernel(const __grid_constant__ FbTabl
   const long long read_stride = (long long)gridDim.x * a.groups;
   int iter = 0;
   for (long long n = (long long)blockIdx.x * a.groups + g; n < a.N; n += read_stride, ++iter) {
+   double ll_read = 0.0;  // thread 0: log-likelihood of the read accumulated over segments
+   // Reads longer than the on-chip staging are cut into `nseg` segments and walked twice:
+   // pass 0 only forms every segment's transfer matrix (phases 1-2), a short chain turns those
+   // into the vectors entering / leaving each segment, pass 1 does the full work per segment.
+   for (int pass = (nseg > 1 ? 0 : 1); pass < 2; ++pass) {
+    for (int seg = 0; seg < nseg; ++seg) {
+    const int seg0 = seg * Lseg;
+    const int Ls = min(Lseg, L - seg0);
+    const int t1 = min(t0 + chunk, Ls);
+    const bool active = t0 < Ls;
+    float u_init[K], z_init[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      u_init[k] = (nseg > 1 && pass == 1) ? s_useg[seg * K + k] : tab.pi[k];
+      z_init[k] = (nseg > 1 && pass == 1) ? s_zseg[seg * K + k] : 1.0f;
+    }
     // ---------------- load: global -> shared (coalesced, converted to fp32) ----------------
     {
-      const long long base = n * (long long)L * C;
-      const int tot = L * C;
+      const long long base = (n * (long long)L + seg0) * C;
+      const int tot = Ls * C;
       for (int i = gt; i < tot; i += T) s_in[i] = load_obs(a.obs, a.obs_dtype, base + i);
+    }
+    bool prevseg_obs = false;  // is the position just before this segment observed? (E-step xi)
+    if (STATS && seg0 > 0 && gt == 0) {
+      for (int c = 0; c < C; ++c) {
+        const float o = load_obs(a.obs, a.obs_dtype, (n * (long long)L + seg0 - 1) * C + c);
+        prevseg_obs |= (o == o);
+      }
     }
     group_sync(bar_id, T);
 
@@ -314,7 +347,7 @@ __global__ void __launch_bounds__(MAXT) fb_kernel(const __grid_constant__ FbTabl
     if (active) {
       int t = t0;
       float b[K];
-      if (t == 0) {
+      if (seg0 + t == 0) {
         emission_rel<K, MULTI>(tab, s_in, 0, C, b);
 #pragma unroll
         for (int j = 0; j < K; ++j) P[j][j] = b[j];
@@ -325,7 +358,7 @@ __global__ void __launch_bounds__(MAXT) fb_kernel(const __grid_constant__ FbTabl
         emission_rel<K, MULTI>(tab, s_in, t, C, b);
         float Q[K][K];
         if (BINNED) {
-          const float* A = sA + (int)sbins[t - 1] * KK;
+          const float* A = sA + (int)sbins[seg0 + t - 1] * KK;
 #pragma unroll
           for (int i = 0; i < K; ++i)
 #pragma unroll
@@ -469,27 +502,35 @@ __global__ void __launch_bounds__(MAXT) fb_kernel(const __grid_constant__ FbTabl
           }
         }
         // exclusive versions: prefix of lane-1, suffix of lane+1
+        if (pass == 0 && lane == G - 1) {
+          // transfer matrix of the whole segment (normalised)
+          const float sc = pow2_rescale_noexp(mat_max<K>(wp));
+#pragma unroll
+          for (int i = 0; i < K; ++i)
+#pragma unroll
+            for (int j = 0; j < K; ++j) s_segT[seg * KK + i * K + j] = wp[i][j] * sc;
+        }
         float uo[K], zo[K];
 #pragma unroll
         for (int j = 0; j < K; ++j) {
-          float s = tab.pi[0] * wp[0][j];
+          float s = u_init[0] * wp[0][j];
 #pragma unroll
-          for (int i = 1; i < K; ++i) s = fmaf(tab.pi[i], wp[i][j], s);
-          uo[j] = s;  // pi * inclusive_prefix(lane)
+          for (int i = 1; i < K; ++i) s = fmaf(u_init[i], wp[i][j], s);
+          uo[j] = s;  // u_init * inclusive_prefix(lane)
         }
 #pragma unroll
         for (int i = 0; i < K; ++i) {
-          float s = ws[i][0];
+          float s = ws[i][0] * z_init[0];
 #pragma unroll
-          for (int j = 1; j < K; ++j) s += ws[i][j];
-          zo[i] = s;  // inclusive_suffix(lane) * 1
+          for (int j = 1; j < K; ++j) s = fmaf(ws[i][j], z_init[j], s);
+          zo[i] = s;  // inclusive_suffix(lane) * z_init
         }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
           float up = __shfl_up_sync(kFull, uo[k], 1);
           float zn = __shfl_down_sync(kFull, zo[k], 1);
-          if (lane == 0) up = tab.pi[k];
-          if (lane == 31) zn = 1.0f;
+          if (lane == 0) up = u_init[k];
+          if (lane == 31) zn = z_init[k];
           s_u[lane * K + k] = up;
           s_z[lane * K + k] = zn;
         }
@@ -498,15 +539,23 @@ __global__ void __launch_bounds__(MAXT) fb_kernel(const __grid_constant__ FbTabl
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         u[k] = s_u[gw * K + k];
-        z[k] = (gw + 1 < G) ? s_z[gw * K + k] : 1.0f;
+        z[k] = (gw + 1 < G) ? s_z[gw * K + k] : z_init[k];
       }
     } else {
+      if (pass == 0 && lane == 31) {
+#pragma unroll
+        for (int i = 0; i < K; ++i)
+#pragma unroll
+          for (int j = 0; j < K; ++j) s_segT[seg * KK + i * K + j] = pre[i][j];
+      }
+      __syncwarp();
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        u[k] = tab.pi[k];
-        z[k] = 1.0f;
+        u[k] = u_init[k];
+        z[k] = z_init[k];
       }
     }
+    if (pass == 0) continue;  // pass 0 stops after the segment's transfer matrix
 
     // thread-exclusive boundary vectors
     float v[K], w[K];
@@ -557,7 +606,7 @@ __global__ void __launch_bounds__(MAXT) fb_kernel(const __grid_constant__ FbTabl
       {
         int t = t0;
         float b[K];
-        if (t == 0) {
+        if (seg0 + t == 0) {
           emission_rel<K, MULTI>(tab, s_in, 0, C, b);
 #pragma unroll
           for (int k = 0; k < K; ++k) {
@@ -571,7 +620,7 @@ __global__ void __launch_bounds__(MAXT) fb_kernel(const __grid_constant__ FbTabl
           emission_rel<K, MULTI>(tab, s_in, t, C, b);
           float nx[K];
           if (BINNED) {
-            const float* A = sA + (int)sbins[t - 1] * KK;
+            const float* A = sA + (int)sbins[seg0 + t - 1] * KK;
 #pragma unroll
             for (int j = 0; j < K; ++j) {
               float s = al[0] * A[j];
@@ -609,7 +658,7 @@ __global__ void __launch_bounds__(MAXT) fb_kernel(const __grid_constant__ FbTabl
 #pragma unroll
         for (int c = 0; c < (MULTI ? kMaxC : 1); ++c)
           if (c < C) ll_thread += (double)ll_cnt[c] * tab.l00[c] + (double)ll_sumo[c] * tab.dl0[c];
-        if (t0 == 0) ll_thread += tab.log_pi_sum;
+        if (seg0 + t0 == 0) ll_thread += tab.log_pi_sum;
       }
 
       // backward sweep
@@ -666,7 +715,7 @@ __global__ void __launch_bounds__(MAXT) fb_kernel(const __grid_constant__ FbTabl
         s_st[t] = (int8_t)best;
 
         if (STATS) {
-          if (t == 0) {
+          if (seg0 + t == 0) {
 #pragma unroll
             for (int k = 0; k < K; ++k) acc_start[k] += gk[k];
           }
@@ -695,14 +744,14 @@ __global__ void __launch_bounds__(MAXT) fb_kernel(const __grid_constant__ FbTabl
           }
         }
 
-        if (has_prev || (STATS && t > 0)) {
+        if (has_prev || (STATS && seg0 + t > 0)) {
           float cb[K], nb[K];
 #pragma unroll
           for (int j = 0; j < K; ++j) cb[j] = b[j] * bv[j];
           float prod[K][K];
           int bin = 0;
           if (BINNED) {
-            bin = (int)sbins[t - 1];
+            bin = (int)sbins[seg0 + t - 1];
             const float* A = sA + bin * KK;
 #pragma unroll
             for (int i = 0; i < K; ++i)
@@ -724,7 +773,7 @@ __global__ void __launch_bounds__(MAXT) fb_kernel(const __grid_constant__ FbTabl
           if (STATS) {
             // xi_{t-1}(i,j) = alpha_{t-1}(i) A_ij b_t(j) beta_t(j) / sum, counted only when both
             // endpoints are observed (HMM.py:1583-1591)
-            const bool valid = m_t && any_observed<MULTI>(s_in, t - 1, C);
+            const bool valid = m_t && (t > 0 ? any_observed<MULTI>(s_in, t - 1, C) : prevseg_obs);
             float s2 = 0.0f;
 #pragma unroll
             for (int i = 0; i < K; ++i) s2 = fmaf(alp[i], nb[i], s2);
@@ -770,27 +819,69 @@ __global__ void __launch_bounds__(MAXT) fb_kernel(const __grid_constant__ FbTabl
 
     // ---------------- store: shared staging -> global (coalesced) ----------------
     if (a.loglik != nullptr && gt == 0) {
-      double s = 0.0;
-      for (int i = 0; i < G; ++i) s += s_ll[i];
-      a.loglik[n] = s;
+      for (int i = 0; i < G; ++i) ll_read += s_ll[i];
+      if (seg == nseg - 1) a.loglik[n] = ll_read;
     }
     if (a.gamma != nullptr) {
       if (a.gamma_state < 0) {
-        float* dst = a.gamma + n * (long long)L * K;
-        const int tot = L * K;
+        float* dst = a.gamma + (n * (long long)L + seg0) * K;
+        const int tot = Ls * K;
         for (int i = gt; i < tot; i += T) dst[i] = s_stage[i];
       } else {
-        float* dst = a.gamma + n * (long long)L;
-        for (int i = gt; i < L; i += T) dst[i] = s_stage[i * K];
+        float* dst = a.gamma + n * (long long)L + seg0;
+        for (int i = gt; i < Ls; i += T) dst[i] = s_stage[i * K];
       }
     }
     if (a.states != nullptr) {
-      int8_t* dst = a.states + n * (long long)L;
-      for (int i = gt; i < L; i += T) dst[i] = s_st[i];
+      int8_t* dst = a.states + n * (long long)L + seg0;
+      for (int i = gt; i < Ls; i += T) dst[i] = s_st[i];
     }
+    if (nseg > 1) group_sync(bar_id, T);  // staging drained before the next segment is decoded
+    }  // segments
+    if (pass == 0) {
+      // chain the segment matrices into the vectors entering (u) / leaving (z) every segment
+      group_sync(bar_id, T);
+      if (gt == 0) {
+        float x[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) x[k] = tab.pi[k];
+        for (int sg = 0; sg < nseg; ++sg) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) s_useg[sg * K + k] = x[k];
+          float y[K];
+#pragma unroll
+          for (int j = 0; j < K; ++j) {
+            float sacc = x[0] * s_segT[sg * KK + j];
+#pragma unroll
+            for (int i = 1; i < K; ++i) sacc = fmaf(x[i], s_segT[sg * KK + i * K + j], sacc);
+            y[j] = sacc;
+          }
+          const float sc = pow2_rescale_noexp(vec_max<K>(y));
+#pragma unroll
+          for (int k = 0; k < K; ++k) x[k] = y[k] * sc;
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) x[k] = 1.0f;
+        for (int sg = nseg - 1; sg >= 0; --sg) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) s_zseg[sg * K + k] = x[k];
+          float y[K];
+#pragma unroll
+          for (int i = 0; i < K; ++i) {
+            float sacc = s_segT[sg * KK + i * K] * x[0];
+#pragma unroll
+            for (int j = 1; j < K; ++j) sacc = fmaf(s_segT[sg * KK + i * K + j], x[j], sacc);
+            y[i] = sacc;
+          }
+          const float sc = pow2_rescale_noexp(vec_max<K>(y));
+#pragma unroll
+          for (int k = 0; k < K; ++k) x[k] = y[k] * sc;
+        }
+      }
+      group_sync(bar_id, T);
+    }
+   }  // passes
     if (STATS && ((iter + 1) % a.flush_every) == 0) flush_stats();
-    // The next iteration's load only writes s_in (nobody reads it after the barrier above) and
-    // its phase-3 writes to s_stage / s_st come after two more group barriers.
   }
 
   if (STATS) {

@@ -524,6 +524,13 @@ class BaseHMM(nn.Module):
         cur = torch.cuda.current_stream(device)
         s_in = torch.cuda.Stream(device)
         s_out = torch.cuda.Stream(device)
+        # The staging buffers below come from the caching allocator and may be memory that
+        # earlier work on `cur` is still using; the side streams must not touch them before
+        # that work has finished.
+        entry = torch.cuda.Event()
+        entry.record(cur)
+        s_in.wait_event(entry)
+        s_out.wait_event(entry)
         nbuf = 2
         obs_shape = (rows, L) if src_t.dim() == 2 else (rows, L, C)
         d_obs = [None] * nbuf if on_device else [torch.empty(obs_shape, dtype=src_t.dtype, device=device) for _ in range(nbuf)]
@@ -535,6 +542,18 @@ class BaseHMM(nn.Module):
         ev_in = [None] * nbuf
         ev_cmp = [None] * nbuf
         ev_out = [None] * nbuf
+        try:
+            self._decode_chunks(src_t, st_t, g_t, tables, bins, use_viterbi, on_device, widen_g, widen_s, rows, N,
+                                cur, s_in, s_out, d_obs, d_g, d_s, d_gw, d_sw, ws, ev_in, ev_cmp, ev_out, nbuf)
+        finally:
+            # also on errors: nothing may still be in flight on the side streams when the staging
+            # buffers go back to the allocator
+            s_in.synchronize()
+            s_out.synchronize()
+            cur.synchronize()
+
+    def _decode_chunks(self, src_t, st_t, g_t, tables, bins, use_viterbi, on_device, widen_g, widen_s, rows, N,
+                       cur, s_in, s_out, d_obs, d_g, d_s, d_gw, d_sw, ws, ev_in, ev_cmp, ev_out, nbuf):
         for i, lo in enumerate(range(0, N, rows)):
             hi = min(N, lo + rows)
             n = hi - lo
@@ -571,8 +590,6 @@ class BaseHMM(nn.Module):
                 st_t[lo:hi].copy_(s_src, non_blocking=True)
                 ev_out[b] = torch.cuda.Event()
                 ev_out[b].record(s_out)
-        s_out.synchronize()
-        cur.synchronize()
 
     # ---- EM fit (HMM.py:724-821, 1518-1630) ----------------------------------------------------
     def fit(

@@ -94,19 +94,35 @@ def test_extreme_parameters_stay_finite():
     assert np.abs(g - g_ref).max() <= 1e-5
 
 
-@pytest.mark.parametrize("K,L", [(2, 12000), (3, 11000), (4, 9000)])
-def test_long_reads_use_the_generic_kernel(K, L):
-    """Beyond the fast path's thread budget the generic kernel takes over (same results)."""
-    N = 5
-    X32 = O.synth_reads(N, L, K, 55 + K, prob=(K == 3))
-    p = O.synth_params(K)
-    m = model_from_params(p)
-    st, g = m.decode(X32, compact=True)
-    g_ref, _ = O.posterior(X32.astype(np.float64), p)
+@pytest.mark.parametrize("arch,K,L", [("single", 2, 12000), ("single", 3, 11000), ("single", 4, 9000),
+                                      ("single", 2, 20000), ("single", 3, 41003), ("single", 4, 30001),
+                                      ("single_distance_binned", 2, 25000), ("multi", 2, 19000)])
+def test_long_reads_use_the_generic_kernel(arch, K, L):
+    """Beyond the fast path's thread budget the generic kernel takes over; beyond its on-chip
+    staging it walks the read in segments (two passes).  Same results either way."""
+    from smftools_b200 import engine
+
+    N = 3
+    C = 2 if arch == "multi" else 1
+    X32 = O.synth_reads(N, L, K, 55 + K, prob=(K == 3), n_channels=C)
+    coords = O.synth_coords(L, 9) if arch == "single_distance_binned" else np.arange(L)
+    p = O.synth_params(K, arch=arch, n_channels=C)
+    m = model_from_params(p, arch)
+    X = X32.astype(np.float64)
+    g_ref, ll_ref = O.posterior(X, p, coords)
+    st, g = m.decode(X32, coords, compact=True)
     assert np.abs(g - g_ref).max() <= 1e-5
-    hist = m.fit(X32, max_iter=2, tol=0.0)
-    _, hist_ref = O.fit(X32.astype(np.float64), p, max_iter=2, tol=0.0)
-    assert np.allclose(hist, hist_ref, rtol=1e-6)
+    assert_states_match_up_to_ties(st.astype(np.int64), g_ref.argmax(2), g_ref)
+    t = m._host_tables()
+    obs = torch.from_numpy(X32).to(DEV)
+    bins = m._bins_for(coords, L, torch.device(DEV))
+    _, _, ll = engine.posterior(t, obs, bins, want_gamma=False, want_states=False, want_loglik=True)
+    assert np.allclose(ll.cpu().numpy(), ll_ref, rtol=1e-6)
+    g1, _, _ = engine.posterior(t, obs, bins, gamma_state=K - 1, want_states=False)
+    assert np.abs(g1.cpu().numpy() - g_ref[:, :, K - 1]).max() <= 1e-5
+    stats = engine.estep(t, obs, bins).cpu().numpy()
+    ref = O.stats_vector(O.estep(X, p, coords))
+    assert np.all(np.abs(stats - ref) / np.maximum(np.abs(ref), 1.0) <= 2e-6)
 
 
 def test_reads_that_do_not_fit_raise_value_error():
@@ -115,12 +131,12 @@ def test_reads_that_do_not_fit_raise_value_error():
     m = model_from_params(O.synth_params(4))
     t = m._host_tables()
     lim = engine.max_positions(t)
-    assert 9000 < lim < 40000
+    assert lim > 300_000  # 64 segments of the on-chip staging
     with pytest.raises(ValueError, match="too long"):
-        m.decode(np.zeros((2, lim + 64), dtype=np.float32))
+        m.decode(np.zeros((1, lim + 64), dtype=np.float32))
     # Viterbi has no such limit
-    sv = engine.viterbi(t, torch.zeros((2, lim + 64), device=DEV), None)
-    assert sv.shape == (2, lim + 64)
+    sv = engine.viterbi(t, torch.zeros((1, lim + 64), device=DEV), None)
+    assert sv.shape == (1, lim + 64)
 
 
 def test_generic_and_fast_kernels_agree(monkeypatch):
