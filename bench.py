@@ -44,7 +44,8 @@ WORKLOADS = {
     "c3p_k3": dict(N=65_536, L=10_000, K=3, prob=True, op="posterior",
                    desc="1M x 10 kb m6A probabilistic, 3-state posterior decode, one 65,536-read chunk"),
     "c3v": dict(N=262_144, L=10_000, K=3, prob=True, op="viterbi",
-                desc="BASELINE configs[2]: 1M x 10 kb m6A probabilistic 3-state Viterbi, one 262,144-read chunk"),
+                desc="BASELINE configs[2]: 1M x 10 kb m6A probabilistic 3-state Viterbi + footprint interval calling, "
+                     "one 262,144-read chunk"),
     "c4": dict(N=262_144, L=8_000, K=4, prob=False, op="estep",
                desc="BASELINE configs[3]: 4-state Baum-Welch iteration, 262,144 reads x 8 kb per GPU"),
 }
@@ -305,6 +306,19 @@ def run_ours(args, wl):
         ws = engine.estep_workspace(tables, device)
         stats = torch.empty((engine.stats_len(tables),), dtype=torch.float64, device=device)
 
+    feat = None
+    if op == "viterbi":
+        # BASELINE configs[2]: Viterbi + footprint interval calling on the decoded states.  Sites every
+        # ~4 bp on a grid of 4*L columns; default footprint size classes; compacted interval records.
+        coords_h = np.sort(np.random.default_rng(5).choice(np.arange(4 * L), size=L, replace=False)).astype(np.int64)
+        full_h = np.arange(4 * L, dtype=np.int64)
+        feat = dict(
+            coords=torch.from_numpy(coords_h).to(device),
+            left=torch.from_numpy(np.searchsorted(full_h, coords_h, side="left").astype(np.int32)).to(device),
+            right=torch.from_numpy(np.searchsorted(full_h, coords_h, side="right").astype(np.int32)).to(device),
+            V=4 * L, ranges=[(6, 40), (40, 100), (100, 200), (200, float("inf"))], target=1,
+            max_intervals=int(N) * 64)
+
     launches = {"n": 0}
 
     def step():
@@ -313,7 +327,10 @@ def run_ours(args, wl):
             launches["n"] += 1
         elif op == "viterbi":
             engine.viterbi(tables, obs, None, out_states=states, workspace=ws)
-            launches["n"] += 1
+            engine.call_features(states=states, post=None, target=feat["target"], threshold=0.0, coords=feat["coords"],
+                                 grid_left=feat["left"], grid_right=feat["right"], n_grid=feat["V"],
+                                 ranges=feat["ranges"], want_dense=False, max_intervals=feat["max_intervals"])
+            launches["n"] += 2
         else:
             engine.estep(tables, obs, None, out_stats=stats, workspace=ws)
             launches["n"] += 2

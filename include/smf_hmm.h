@@ -134,7 +134,8 @@ int smf_hmm_estep(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int
  * the run length of a cell is the same in the all_{group}_features layer and in its class
  * layer (HMM.py:1361-1370); the host mirror checks this and otherwise uses its own slow path.
  * Outputs (all device, row-major [N, V]):
- *   class_out   uint8: 0 = no feature, c+1 = size class c       (dense "which layer is 1")
+ *   class_out   uint8: 0 = no feature, c+1 = size class c       (dense "which layer is 1"); may be NULL
+ *               when only the compacted interval records are wanted (then run_len must be NULL too)
  *   run_len     int32: run length in grid columns of the run covering the cell, else 0; may be NULL
  *   intervals   int32 [max_intervals,4] = (read, grid_start, grid_end, class) compacted runs; may be NULL
  *   n_intervals device uint64 counter (zeroed by the caller); total runs found, may exceed max_intervals

@@ -736,7 +736,8 @@ int smf_hmm_call_features(const int8_t* states, const float* post, int target_st
   if (n_reads < 0 || n_pos < 0 || n_grid < 0) return SMF_ERR_BAD_ARG;
   if (n_reads == 0 || n_grid == 0) return SMF_OK;
   if ((states == nullptr) == (post == nullptr)) return SMF_ERR_BAD_ARG;  // exactly one of them
-  if (!coords || !grid_left || !grid_right || !class_out) return SMF_ERR_BAD_ARG;
+  if (!coords || !grid_left || !grid_right) return SMF_ERR_BAD_ARG;
+  if (class_out == nullptr && (run_len != nullptr || intervals == nullptr)) return SMF_ERR_BAD_ARG;
   if (intervals != nullptr && n_intervals == nullptr) return SMF_ERR_BAD_ARG;
   if (n_pos > 0x3fffffff || n_grid > 0x3fffffff) return SMF_ERR_TOO_LONG;
   ClassTable ct;
@@ -771,6 +772,16 @@ int smf_hmm_call_features(const int8_t* states, const float* post, int target_st
   a.intervals = intervals;
   a.max_intervals = max_intervals;
   a.n_intervals = n_intervals;
+  if (class_out == nullptr) {
+    // interval records only: warp-per-read kernel without shared-memory run tables
+    if (reinterpret_cast<uintptr_t>(intervals) & 15u) return SMF_ERR_ALIGN;
+    const long long warps_needed = n_reads;
+    long long blocks = (warps_needed + kFeatWarps - 1) / kFeatWarps;
+    const long long capb = (long long)di.num_sms * 8;
+    if (blocks > capb) blocks = capb;
+    call_intervals_kernel<<<(int)blocks, kFeatThreads, 0, (cudaStream_t)stream>>>(ct, a);
+    return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
+  }
   long long cap = (long long)di.num_sms * occ;
   const int nblocks = (int)(n_reads < cap ? n_reads : cap);
   call_features_kernel<<<nblocks, kFeatThreads, smem, (cudaStream_t)stream>>>(ct, a);

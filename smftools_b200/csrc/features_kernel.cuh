@@ -151,20 +151,80 @@ __global__ void __launch_bounds__(kFeatThreads) call_features_kernel(const __gri
       }
     }
     __syncthreads();
-    uint8_t* crow = a.class_out + n * (long long)a.V;
-    int* lrow = a.run_len ? a.run_len + n * (long long)a.V : nullptr;
-    for (int v = tid; v < a.V; v += kFeatThreads) {
-      const int r = find_run(rs, R, v);
-      uint8_t c = 0;
-      int len = 0;
-      if (r >= 0 && v < re[r] && rcls[r] >= 0) {
-        c = (uint8_t)(rcls[r] + 1);
-        len = re[r] - rs[r];
+    if (a.class_out != nullptr) {  // dense layers are optional: interval records alone are enough downstream
+      uint8_t* crow = a.class_out + n * (long long)a.V;
+      int* lrow = a.run_len ? a.run_len + n * (long long)a.V : nullptr;
+      for (int v = tid; v < a.V; v += kFeatThreads) {
+        const int r = find_run(rs, R, v);
+        uint8_t c = 0;
+        int len = 0;
+        if (r >= 0 && v < re[r] && rcls[r] >= 0) {
+          c = (uint8_t)(rcls[r] + 1);
+          len = re[r] - rs[r];
+        }
+        crow[v] = c;
+        if (lrow) lrow[v] = len;
       }
-      crow[v] = c;
-      if (lrow) lrow[v] = len;
     }
     __syncthreads();
+  }
+}
+
+// Interval-only feature calling: one WARP per read, no shared memory and no CTA barriers.
+// 32 positions per step: the membership ballot gives run starts / ends as bit masks; the lane
+// that sees a run end finds the matching start in the same mask (or the start carried over from
+// earlier words), classifies the run and appends one (read, grid_start, grid_end, class) record
+// through a warp-aggregated atomic.  Same records as call_features_kernel.
+__global__ void __launch_bounds__(kFeatThreads) call_intervals_kernel(const __grid_constant__ ClassTable ct,
+                                                                       const __grid_constant__ FeatArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  for (long long n = warp0; n < a.N; n += nwarps) {
+    const int8_t* srow = a.states ? a.states + n * (long long)a.L : nullptr;
+    const float* prow = a.post ? a.post + n * (long long)a.L : nullptr;
+    unsigned carry = 0;   // membership of the position just before this word
+    int open_start = 0;   // start of the run that is open when the word begins
+    for (int base = 0; base <= a.L; base += 32) {
+      const int t = base + lane;
+      bool cur = false;
+      if (t < a.L) cur = prow ? (__ldg(prow + t) >= a.thr) : ((int)__ldg(srow + t) == a.target);
+      const unsigned m = __ballot_sync(0xffffffffu, cur);
+      const unsigned shifted = (m << 1) | carry;
+      const unsigned starts = m & ~shifted;
+      const unsigned ends = ~m & shifted;  // bit i: a run ended at position base+i (exclusive)
+      bool keep = false;
+      int gs = 0, ge = 0, cls = -1;
+      if ((ends >> lane) & 1u) {
+        const unsigned before = starts & lt;
+        const int s0 = before ? (base + 31 - __clz(before)) : open_start;
+        const int e0 = t;
+        const long long glen = __ldg(a.coords + e0 - 1) - __ldg(a.coords + s0) + 1;
+        gs = __ldg(a.grid_left + s0);
+        ge = __ldg(a.grid_right + e0 - 1);
+        if (glen > 0) cls = pick_class(ct, (double)glen);
+        keep = (cls >= 0) && (gs < ge);
+      }
+      const unsigned bk = __ballot_sync(0xffffffffu, keep);
+      if (bk) {
+        unsigned long long basei = 0;
+        if (lane == 0) basei = atomicAdd(a.n_intervals, (unsigned long long)__popc(bk));
+        basei = __shfl_sync(0xffffffffu, basei, 0);
+        if (keep) {
+          const unsigned long long slot = basei + __popc(bk & lt);
+          if (slot < (unsigned long long)a.max_intervals) {
+            int4 rec = make_int4((int)n, gs, ge, cls);
+            *reinterpret_cast<int4*>(a.intervals + slot * 4) = rec;
+          }
+        }
+      }
+      if (starts) {
+        const int hs = 31 - __clz(starts);
+        if (ends == 0u || hs > 31 - __clz(ends)) open_start = base + hs;  // that run is still open
+      }
+      carry = m >> 31;
+    }
   }
 }
 

@@ -165,6 +165,7 @@ def call_features(
     n_grid: int,
     ranges: Sequence[Tuple[float, float]],
     want_len: bool = True,
+    want_dense: bool = True,
     max_intervals: int = 0,
 ):
     """Feature calling (``smf_hmm_call_features``).
@@ -186,8 +187,10 @@ def call_features(
         if t.dtype != dt_ or t.numel() != L or not t.is_contiguous():
             raise ValueError(f"{nm} must be contiguous {dt_} of length L")
     V = int(n_grid)
-    cls = torch.empty((N, V), dtype=torch.uint8, device=dev)
-    rlen = torch.empty((N, V), dtype=torch.int32, device=dev) if want_len else None
+    if not want_dense and max_intervals <= 0:
+        raise ValueError("interval-only calling needs max_intervals > 0")
+    cls = torch.empty((N, V), dtype=torch.uint8, device=dev) if want_dense else None
+    rlen = torch.empty((N, V), dtype=torch.int32, device=dev) if (want_len and want_dense) else None
     ivals = cnt = None
     if max_intervals > 0:
         ivals = torch.empty((max_intervals, 4), dtype=torch.int32, device=dev)

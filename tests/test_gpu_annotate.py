@@ -104,6 +104,14 @@ def test_feature_kernels_against_oracle(N, L, seed):
             assert (dense[r, s:e] == 0).all()
             dense[r, s:e] = c + 1
         np.testing.assert_array_equal(dense, cls_h)
+        # interval-only mode returns the same records without writing dense layers
+        _, _, iv2 = engine.call_features(
+            states=torch.from_numpy(states).to(dev), post=None, target=target, threshold=0.0,
+            coords=torch.from_numpy(coords).to(dev), grid_left=torch.from_numpy(left).to(dev),
+            grid_right=torch.from_numpy(right).to(dev), n_grid=V, ranges=ranges, want_dense=False,
+            max_intervals=N * (L // 2 + 2))
+        key = lambda a: a[np.lexsort((a[:, 1], a[:, 0]))]  # noqa: E731
+        np.testing.assert_array_equal(key(iv2.cpu().numpy()), key(iv))
         # posterior-threshold membership gives the same result as the equivalent state test
         post = np.where(member, 0.75, 0.25).astype(np.float32)
         cls_p, len_p, _ = engine.call_features(
