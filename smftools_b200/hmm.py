@@ -211,9 +211,9 @@ def _span_validity(adata, *, start_key: str, end_key: str, use_original_var_name
             raise ValueError("Start/end positions must be numeric.") from exc
         valid = engine.span_mask(
             adata.n_obs, adata.n_vars, dev,
-            coords=torch.from_numpy(np.ascontiguousarray(coords, dtype=np.int64)).to(dev),
-            start=torch.from_numpy(np.ascontiguousarray(starts, dtype=np.float64)).to(dev),
-            end=torch.from_numpy(np.ascontiguousarray(ends, dtype=np.float64)).to(dev),
+            coords=torch.from_numpy(np.array(coords, dtype=np.int64, copy=True)).to(dev),
+            start=torch.from_numpy(np.array(starts, dtype=np.float64, copy=True)).to(dev),
+            end=torch.from_numpy(np.array(ends, dtype=np.float64, copy=True)).to(dev),
         )
     return valid.cpu().numpy().astype(bool)
 
