@@ -1,17 +1,26 @@
-"""Build ``libsmfhmm.so`` in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+"""Build ``libsmfhmm.so`` in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+The kernels are heavily templated (fully unrolled per-chunk loops), so the library is split into
+one translation unit per state count and kernel family; they are compiled in parallel and linked
+into a single shared object.
+"""
 from __future__ import annotations
 
 import os
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
 OUT = os.path.join(HERE, "libsmfhmm.so")
-SOURCES = ["api.cu"]
-HEADERS = ["hmm_common.cuh", "fb_kernel.cuh", "fb2_kernel.cuh", "viterbi_kernel.cuh", "features_kernel.cuh"]
+SOURCES = ["api.cu"] + [f"{fam}_k{k}.cu" for fam in ("fb2", "fb", "vit") for k in (2, 3, 4)]
+HEADERS = ["hmm_common.cuh", "fb_kernel.cuh", "fb2_kernel.cuh", "viterbi_kernel.cuh", "features_kernel.cuh",
+           "launch.h", "fb2_launch.inc", "fb_launch.inc", "vit_launch.inc"]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
 def _nvcc() -> str:
@@ -21,30 +30,46 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
+def _deps():
+    return [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(ROOT, "include", "smf_hmm.h")]
+
+
 def needs_build() -> bool:
     if not os.path.isfile(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(ROOT, "include", "smf_hmm.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return any(os.path.getmtime(d) > t for d in _deps())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
-        return OUT
-    cmd = [
-        _nvcc(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-        "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-        "-o", OUT,
-    ] + [os.path.join(CSRC, s) for s in SOURCES]
+def _compile(src: str, verbose: bool):
+    obj = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
+    cmd = [_nvcc(), "-O3", "-std=c++17", *ARCH, "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"),
+           "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     res = subprocess.run(cmd, capture_output=True, text=True)
+    return src, obj, res
+
+
+def build(force: bool = False, verbose: bool = False, jobs: int | None = None) -> str:
+    if not force and not needs_build():
+        return OUT
+    os.makedirs(OBJ, exist_ok=True)
+    jobs = jobs or min(len(SOURCES), max(1, (os.cpu_count() or 2)))
+    objs = []
+    with ThreadPoolExecutor(max_workers=jobs) as pool:
+        for src, obj, res in pool.map(lambda s: _compile(s, verbose), SOURCES):
+            if res.returncode != 0:
+                sys.stderr.write(res.stdout + res.stderr)
+                raise RuntimeError(f"nvcc failed on {src}")
+            if verbose:
+                sys.stderr.write(res.stderr)
+            objs.append(obj)
+    link = [_nvcc(), "-shared", *ARCH, "-Xcompiler", "-fPIC", "-o", OUT] + objs
+    res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libsmfhmm.so")
-    if verbose:
-        sys.stderr.write(res.stderr)
+        raise RuntimeError("nvcc failed linking libsmfhmm.so")
     return OUT
 
 

@@ -1,30 +1,30 @@
-// C-ABI of libsmfhmm.so (see include/smf_hmm.h): argument checks, table conversion,
-// launch-shape selection and kernel launches.  No torch, no allocation, no global state
-// other than cached device attributes.
+// C-ABI of libsmfhmm.so (see include/smf_hmm.h): argument checks, launch-shape selection and
+// dispatch to the per-K launchers.  No torch, no allocation, no global state other than cached
+// device attributes.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 
-#include <type_traits>
-
-#include "fb2_kernel.cuh"
-#include "fb_kernel.cuh"
 #include "features_kernel.cuh"
+#include "launch.h"
 #include "smf_hmm.h"
-#include "viterbi_kernel.cuh"
 
 namespace smf {
 
+// Fixed-order reduction of the per-CTA partial statistics.
+__global__ void reduce_partials_kernel(const double* __restrict__ partials, int nblocks, int S,
+                                       double* __restrict__ stats) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  double tot = 0.0;
+  for (int b = 0; b < nblocks; ++b) tot += partials[(size_t)b * S + s];
+  stats[s] = tot;
+}
+
 // E-step workspace: per-CTA partial statistics, for at most this many CTAs.
 static const int kMaxEstepBlocks = 148 * 8;
-
-struct DeviceInfo {
-  int device = -1;
-  int num_sms = 0;
-  int max_smem_optin = 0;
-};
 
 static int get_device_info(DeviceInfo* out) {
   static DeviceInfo cache[64];
@@ -59,86 +59,8 @@ static int check_tables(const smf_hmm_tables* t) {
   return SMF_OK;
 }
 
-template <int K>
-static void build_fb_tables(const smf_hmm_tables* t, FbTables<K>* out) {
-  memset(out, 0, sizeof(*out));
-  const int C = t->n_channels;
-  const double log2e = 1.4426950408889634074;
-  double pisum = 0.0;
-  for (int k = 0; k < K; ++k) {
-    const double p = exp(t->log_start[k]);
-    out->pi[k] = (float)p;
-    pisum += (double)out->pi[k];
-  }
-  out->log_pi_sum = log(pisum);
-  for (int b = 0; b < t->n_bins; ++b)
-    for (int i = 0; i < K; ++i)
-      for (int j = 0; j < K; ++j) out->A[b][i][j] = (float)exp(t->log_trans[(b * K + i) * K + j]);
-  for (int c = 0; c < C; ++c) {
-    const double l0_0 = t->log_emit0[0 * C + c];
-    const double d_0 = t->log_emit1[0 * C + c] - l0_0;
-    out->l00[c] = l0_0;
-    out->dl0[c] = d_0;
-    for (int k = 0; k < K; ++k) {
-      const double l0 = t->log_emit0[k * C + c];
-      const double d = t->log_emit1[k * C + c] - l0;
-      out->rl0[k][c] = (float)((l0 - l0_0) * log2e);
-      out->rdl[k][c] = (float)((d - d_0) * log2e);
-    }
-  }
-  // fast-path tables (bin 0, channel 0)
-  {
-    double sdiag[K];
-    for (int j = 0; j < K; ++j) sdiag[j] = exp(t->log_trans[j * K + j]);
-    for (int i = 0; i < K; ++i)
-      for (int j = 0; j < K; ++j) out->Ap[i][j] = (i == j) ? 1.0f : (float)(exp(t->log_trans[i * K + j]) / sdiag[j]);
-    double p2sum = 0.0;
-    const double l0_0 = t->log_emit0[0];
-    const double d_0 = t->log_emit1[0] - l0_0;
-    (void)d_0;
-    for (int k = 0; k < K; ++k) {
-      const double ratio = sdiag[k] / sdiag[0];
-      out->pi2[k] = (float)(exp(t->log_start[k]) / ratio);
-      p2sum += (double)out->pi2[k];
-      const double l0 = t->log_emit0[k * C];
-      out->rl0p[k] = (float)((l0 - l0_0) * log2e + log2(ratio));
-      out->rmiss[k] = (float)log2(ratio);
-    }
-    out->log_s0 = t->log_trans[0];
-    out->log_pi2_sum = log(p2sum);
-  }
-  out->nb = t->n_bins;
-  out->C = C;
-}
-
-template <int K>
-static void build_vit_tables(const smf_hmm_tables* t, VitTables<K>* out) {
-  memset(out, 0, sizeof(*out));
-  const int C = t->n_channels;
-  for (int k = 0; k < K; ++k) out->log_pi[k] = t->log_start[k];
-  for (int b = 0; b < t->n_bins; ++b)
-    for (int i = 0; i < K; ++i)
-      for (int j = 0; j < K; ++j) out->logA[b][i][j] = t->log_trans[(b * K + i) * K + j];
-  for (int k = 0; k < K; ++k)
-    for (int c = 0; c < C; ++c) {
-      out->l1[k][c] = t->log_emit1[k * C + c];
-      out->l0[k][c] = t->log_emit0[k * C + c];
-    }
-  out->nb = t->n_bins;
-  out->C = C;
-}
-
-static inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
-
-// Threads a group may use for a given model / mode (register budget; matches launch bounds).
-static int fb_max_threads(int K, bool stats) {
-  if (stats) return K == 2 ? 640 : (K == 3 ? 512 : 384);
-  return K == 4 ? 512 : 640;
-}
-
-struct FbPlan {
-  int T, chunk, groups, smem, block;
-};
+static int fb_max_threads(int K, bool stats) { return fb_max_threads_c(K, stats); }
+static int fb2_max_threads(int K, bool stats) { return fb2_max_threads_c(K, stats); }
 
 // Launch-shape selection for the generic forward-backward kernel.  A read that does not fit the
 // on-chip staging at once is cut into nseg <= kMaxSeg segments (two passes, see fb_kernel.cuh).
@@ -229,72 +151,12 @@ static int plan_fb(int K, int C, int nb, int64_t L64, bool stats, int S, int max
   }
 }
 
-template <int K, bool MULTI, bool BINNED, bool STATS>
-static int launch_fb_t(const smf_hmm_tables* t, FbArgs& a, const FbPlan& plan, const DeviceInfo& di,
-                       int* nblocks_out, cudaStream_t stream) {
-  constexpr int MAXT = STATS ? (K == 2 ? 640 : (K == 3 ? 512 : 384)) : (K == 4 ? 512 : 640);
-  FbTables<K> tab;
-  build_fb_tables<K>(t, &tab);
-  auto kern = fb_kernel<K, MULTI, BINNED, STATS, MAXT>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem) != cudaSuccess)
-    return SMF_ERR_CUDA;
-  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, plan.block, plan.smem) != cudaSuccess)
-    return SMF_ERR_CUDA;
-  if (occ < 1) return SMF_ERR_CUDA;
-  long long want = (a.N + plan.groups - 1) / plan.groups;
-  long long cap = (long long)di.num_sms * occ;
-  int nblocks = (int)(want < cap ? want : cap);
-  if (nblocks < 1) nblocks = 1;
-  if (nblocks_out) {
-    if (*nblocks_out > 0 && nblocks > *nblocks_out) nblocks = *nblocks_out;  // workspace cap
-    *nblocks_out = nblocks;
-  }
-  kern<<<nblocks, plan.block, plan.smem, stream>>>(tab, a);
-  return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
-}
-
-template <int K, bool STATS>
-static int launch_fb_k(const smf_hmm_tables* t, FbArgs& a, const FbPlan& plan, const DeviceInfo& di,
-                       int* nblocks, cudaStream_t stream) {
-  const bool multi = t->n_channels > 1;
-  const bool binned = t->n_bins > 1;
-  if (multi && binned) return launch_fb_t<K, true, true, STATS>(t, a, plan, di, nblocks, stream);
-  if (multi) return launch_fb_t<K, true, false, STATS>(t, a, plan, di, nblocks, stream);
-  if (binned) return launch_fb_t<K, false, true, STATS>(t, a, plan, di, nblocks, stream);
-  return launch_fb_t<K, false, false, STATS>(t, a, plan, di, nblocks, stream);
-}
-
-template <bool STATS>
-static int launch_fb(const smf_hmm_tables* t, FbArgs& a, const FbPlan& plan, const DeviceInfo& di,
-                     int* nblocks, cudaStream_t stream) {
-  switch (t->n_states) {
-    case 2: return launch_fb_k<2, STATS>(t, a, plan, di, nblocks, stream);
-    case 3: return launch_fb_k<3, STATS>(t, a, plan, di, nblocks, stream);
-    case 4: return launch_fb_k<4, STATS>(t, a, plan, di, nblocks, stream);
-  }
-  return SMF_ERR_BAD_ARG;
-}
-
 // ---------------------------------------------------------------------------------------
-// fast path (fb2_kernel): single channel, homogeneous transitions, compile-time chunk
+// fast path (fb2_kernel): single channel, homogeneous transitions, compile-time chunk (17 or 33)
 // ---------------------------------------------------------------------------------------
-constexpr int kFb2Chunk = 17;
-
-static int fb2_max_threads(int K, bool stats) {
-  if (stats) return K == 2 ? 640 : (K == 3 ? 512 : 480);
-  return K == 4 ? 576 : 640;
-}
-
-struct Fb2Plan {
-  int block, smem;
-};
-
-static int plan_fb2(int K, int64_t L64, bool stats, int S, int es, bool want_gamma_one, bool want_states,
-                    int max_smem, Fb2Args* a, Fb2Plan* plan) {
+static int plan_fb2_chunk(int K, int CH, int64_t L64, bool stats, int S, int es, bool want_gamma_one,
+                          bool want_states, int max_smem, Fb2Args* a, Fb2Plan* plan) {
   if (L64 < 1) return SMF_ERR_TOO_LONG;
-  const int CH = kFb2Chunk;
   if (L64 > (int64_t)CH * 1024) return SMF_ERR_TOO_LONG;
   const int L = (int)L64;
   const int Tact = (L + CH - 1) / CH;
@@ -337,6 +199,7 @@ static int plan_fb2(int K, int64_t L64, bool stats, int S, int es, bool want_gam
         a->groups = gr;
         plan->block = T * gr;
         plan->smem = total;
+        plan->chunk = CH;
         return SMF_OK;
       }
     }
@@ -344,58 +207,49 @@ static int plan_fb2(int K, int64_t L64, bool stats, int S, int es, bool want_gam
   return SMF_ERR_TOO_LONG;
 }
 
-template <int K, bool STATS, typename ObsT, int OUT>
-static int launch_fb2_t(const smf_hmm_tables* t, Fb2Args& a, const Fb2Plan& plan, const DeviceInfo& di,
-                        int* nblocks_out, cudaStream_t stream) {
-  constexpr int MAXT = STATS ? (K == 2 ? 640 : (K == 3 ? 512 : 480)) : (K == 4 ? 576 : 640);
-  FbTables<K> tab;
-  build_fb_tables<K>(t, &tab);
-  auto kern = fb2_kernel<K, kFb2Chunk, STATS, ObsT, MAXT, 1, OUT>;
-  static const int env_minb = [] { const char* e = getenv("SMF_FB2_MINB"); return e ? atoi(e) : 0; }();
-  if constexpr (K == 2 && !STATS && OUT == 0 && std::is_same<ObsT, float>::value) {
-    if (env_minb == 3 && plan.block <= 320) kern = fb2_kernel<K, kFb2Chunk, STATS, ObsT, 320, 3, OUT>;
-  }
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem) != cudaSuccess)
-    return SMF_ERR_CUDA;
-  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, plan.block, plan.smem) != cudaSuccess)
-    return SMF_ERR_CUDA;
-  if (occ < 1) return SMF_ERR_CUDA;
-  long long want = (a.N + a.groups - 1) / a.groups;
-  long long cap = (long long)di.num_sms * occ;
-  int nblocks = (int)(want < cap ? want : cap);
-  if (nblocks < 1) nblocks = 1;
-  if (nblocks_out) {
-    if (*nblocks_out > 0 && nblocks > *nblocks_out) nblocks = *nblocks_out;
-    *nblocks_out = nblocks;
-  }
-  kern<<<nblocks, plan.block, plan.smem, stream>>>(tab, a);
-  return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
+// chunk 17 whenever the read fits its thread budget; chunk 33 (K = 2, 4) for reads up to twice as long
+static int plan_fb2(int K, int64_t L64, bool stats, int S, int es, bool want_gamma_one, bool want_states,
+                    int max_smem, Fb2Args* a, Fb2Plan* plan) {
+  // Measured on B200 (profiles/r01_chunk_sweep.txt): for K = 2 the longer chunk wins from ~4 kb on
+  // (half the scan / barrier overhead per position outweighs the halved warp count); for short
+  // reads, for K = 4 (register pressure) and for the E-step (more live registers) chunk 17 is
+  // faster.  SMF_FB2_CHUNK overrides.
+  static const int env_ch = [] { const char* e = getenv("SMF_FB2_CHUNK"); return e ? atoi(e) : 0; }();
+  const bool can33 = (K != 3);
+  const bool prefer33 = can33 && (env_ch == 33 || (env_ch == 0 && K == 2 && !stats && L64 >= 4000));
+  if (prefer33 &&
+      plan_fb2_chunk(K, 33, L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan) == SMF_OK)
+    return SMF_OK;
+  if (plan_fb2_chunk(K, 17, L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan) == SMF_OK)
+    return SMF_OK;
+  if (can33 && plan_fb2_chunk(K, 33, L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan) == SMF_OK)
+    return SMF_OK;
+  return SMF_ERR_TOO_LONG;
 }
 
-template <bool STATS>
-static int launch_fb2(const smf_hmm_tables* t, int obs_dtype, Fb2Args& a, const Fb2Plan& plan,
+static int launch_fb2(bool stats, const smf_hmm_tables* t, int obs_dtype, Fb2Args& a, const Fb2Plan& plan,
                       const DeviceInfo& di, int* nblocks, cudaStream_t stream) {
   // output-set specialisations exist for float observations; everything else decides at run time
-  const int out = (STATS || obs_dtype != SMF_OBS_F32 || a.gamma == nullptr || a.states == nullptr || a.loglik != nullptr)
+  const int out = (stats || obs_dtype != SMF_OBS_F32 || a.gamma == nullptr || a.states == nullptr ||
+                   a.loglik != nullptr)
                       ? 2
                       : (a.gamma_state < 0 ? 0 : 1);
-#define SMF_FB2_CASE(KV)                                                                                       \
-  case KV:                                                                                                     \
-    if (obs_dtype == SMF_OBS_F32) {                                                                            \
-      if (!STATS && out == 0) return launch_fb2_t<KV, false, float, 0>(t, a, plan, di, nblocks, stream);       \
-      if (!STATS && out == 1) return launch_fb2_t<KV, false, float, 1>(t, a, plan, di, nblocks, stream);       \
-      return launch_fb2_t<KV, STATS, float, 2>(t, a, plan, di, nblocks, stream);                               \
-    }                                                                                                          \
-    if (obs_dtype == SMF_OBS_F64) return launch_fb2_t<KV, STATS, double, 2>(t, a, plan, di, nblocks, stream);  \
-    return launch_fb2_t<KV, STATS, unsigned char, 2>(t, a, plan, di, nblocks, stream);
+  static const int env_minb = [] { const char* e = getenv("SMF_FB2_MINB"); return e ? atoi(e) : 0; }();
   switch (t->n_states) {
-    SMF_FB2_CASE(2)
-    SMF_FB2_CASE(3)
-    SMF_FB2_CASE(4)
+    case 2: return launch_fb2_k2(plan.chunk, stats, obs_dtype, out, env_minb, t, a, plan, di, nblocks, stream);
+    case 3: return launch_fb2_k3(plan.chunk, stats, obs_dtype, out, env_minb, t, a, plan, di, nblocks, stream);
+    case 4: return launch_fb2_k4(plan.chunk, stats, obs_dtype, out, env_minb, t, a, plan, di, nblocks, stream);
   }
-#undef SMF_FB2_CASE
+  return SMF_ERR_BAD_ARG;
+}
+
+static int launch_fb(bool stats, const smf_hmm_tables* t, FbArgs& a, const FbPlan& plan, const DeviceInfo& di,
+                     int* nblocks, cudaStream_t stream) {
+  switch (t->n_states) {
+    case 2: return launch_fb_k2(stats, t, a, plan, di, nblocks, stream);
+    case 3: return launch_fb_k3(stats, t, a, plan, di, nblocks, stream);
+    case 4: return launch_fb_k4(stats, t, a, plan, di, nblocks, stream);
+  }
   return SMF_ERR_BAD_ARG;
 }
 
@@ -455,45 +309,6 @@ static int rescale_cadence(const smf_hmm_tables* t) {
 static int stats_len(const smf_hmm_tables* t) {
   const int K = t->n_states, C = t->n_channels;
   return K + t->n_bins * K * K + 2 * K * C + 1;
-}
-
-
-template <int K, bool MULTI, bool BINNED, int OBSK>
-static int launch_vit_o(const VitTables<K>& tab, const VitArgs& a, size_t smem, long long nblk, cudaStream_t stream) {
-  auto kern = viterbi_kernel<K, MULTI, BINNED, OBSK>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-    return SMF_ERR_CUDA;
-  kern<<<(int)nblk, kVitReads, smem, stream>>>(tab, a);
-  return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
-}
-
-template <int K, bool MULTI, bool BINNED>
-static int launch_vit_t(const smf_hmm_tables* t, const VitArgs& a, bool wide, const DeviceInfo& di,
-                        cudaStream_t stream) {
-  VitTables<K> tab;
-  build_vit_tables<K>(t, &tab);
-  const int C = a.C;
-  const int row_stride = (kVitTile * C) | 1;
-  const size_t elem = wide ? 8 : 4;
-  const size_t smem = (((size_t)kVitReads * row_stride * elem + 15) & ~(size_t)15) +
-                      (size_t)kVitReads * (kVitTile + 4) + (BINNED ? (size_t)align_up(a.L, 16) : 0);
-  if ((long long)smem > di.max_smem_optin) return SMF_ERR_TOO_LONG;
-  const long long nblk = (a.N + kVitReads - 1) / kVitReads;
-  if (nblk > 0x7fffffffLL) return SMF_ERR_BAD_ARG;
-  if (a.obs_dtype == SMF_OBS_F64) return launch_vit_o<K, MULTI, BINNED, SMF_OBS_F64>(tab, a, smem, nblk, stream);
-  if (a.obs_dtype == SMF_OBS_U8) return launch_vit_o<K, MULTI, BINNED, SMF_OBS_U8>(tab, a, smem, nblk, stream);
-  return launch_vit_o<K, MULTI, BINNED, SMF_OBS_F32>(tab, a, smem, nblk, stream);
-}
-
-template <int K>
-static int launch_vit_k(const smf_hmm_tables* t, const VitArgs& a, bool wide, const DeviceInfo& di,
-                        cudaStream_t stream) {
-  const bool multi = t->n_channels > 1;
-  const bool binned = t->n_bins > 1;
-  if (multi && binned) return launch_vit_t<K, true, true>(t, a, wide, di, stream);
-  if (multi) return launch_vit_t<K, true, false>(t, a, wide, di, stream);
-  if (binned) return launch_vit_t<K, false, true>(t, a, wide, di, stream);
-  return launch_vit_t<K, false, false>(t, a, wide, di, stream);
 }
 
 static int fill_class_table(const double* lo, const double* hi, int n, ClassTable* ct) {
@@ -596,7 +411,7 @@ int smf_hmm_posterior(const smf_hmm_tables* tab, const void* obs, int obs_dtype,
       b.partials = nullptr;
       b.S = stats_len(tab);
       b.flush_every = 1;
-      return launch_fb2<false>(tab, obs_dtype, b, p2, di, nullptr, (cudaStream_t)stream);
+      return launch_fb2(false, tab, obs_dtype, b, p2, di, nullptr, (cudaStream_t)stream);
     }
   }
   FbArgs a;
@@ -619,7 +434,7 @@ int smf_hmm_posterior(const smf_hmm_tables* tab, const void* obs, int obs_dtype,
   a.S = stats_len(tab);
   a.flush_every = 1;
   a.resc_mask = cadence - 1;
-  return launch_fb<false>(tab, a, plan, di, nullptr, (cudaStream_t)stream);
+  return launch_fb(false, tab, a, plan, di, nullptr, (cudaStream_t)stream);
 }
 
 int smf_hmm_estep(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int64_t n_reads,
@@ -660,7 +475,7 @@ int smf_hmm_estep(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int
       b.S = S;
       b.flush_every = 8;
       int nb2 = kMaxEstepBlocks;
-      rc = launch_fb2<true>(tab, obs_dtype, b, p2, di, &nb2, st);
+      rc = launch_fb2(true, tab, obs_dtype, b, p2, di, &nb2, st);
       if (rc != SMF_OK) return rc;
       reduce_partials_kernel<<<(S + 127) / 128, 128, 0, st>>>(b.partials, nb2, S, stats);
       return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
@@ -686,7 +501,7 @@ int smf_hmm_estep(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int
   a.flush_every = 8;
   a.resc_mask = cadence - 1;
   int nblocks = kMaxEstepBlocks;
-  rc = launch_fb<true>(tab, a, plan, di, &nblocks, st);
+  rc = launch_fb(true, tab, a, plan, di, &nblocks, st);
   if (rc != SMF_OK) return rc;
   reduce_partials_kernel<<<(S + 127) / 128, 128, 0, st>>>(a.partials, nblocks, S, stats);
   return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
@@ -716,12 +531,11 @@ int smf_hmm_viterbi(const smf_hmm_tables* tab, const void* obs, int obs_dtype, i
   a.bins = bins;
   a.states = states;
   a.bp = reinterpret_cast<uint8_t*>(workspace);
-  const bool wide = obs_dtype == SMF_OBS_F64;
   cudaStream_t st = (cudaStream_t)stream;
   switch (tab->n_states) {
-    case 2: return launch_vit_k<2>(tab, a, wide, di, st);
-    case 3: return launch_vit_k<3>(tab, a, wide, di, st);
-    case 4: return launch_vit_k<4>(tab, a, wide, di, st);
+    case 2: return launch_vit_k2(tab, a, di, st);
+    case 3: return launch_vit_k3(tab, a, di, st);
+    case 4: return launch_vit_k4(tab, a, di, st);
   }
   return SMF_ERR_BAD_ARG;
 }

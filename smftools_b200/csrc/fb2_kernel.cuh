@@ -14,6 +14,7 @@
 //     observations, which leave every posterior of the real positions unchanged (beta of the
 //     last position stays uniform up to fp32 rounding, ~1e-7) and contribute no statistics.
 #pragma once
+#include <type_traits>
 #include "fb_kernel.cuh"
 
 namespace smf {
@@ -291,7 +292,8 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
         for (int k = 1; k < K; ++k) c[k] = rt[RECOMP ? 0 : j][k - 1];
       }
     };
-    unsigned obsmask = 0;      // bit j: position t0+j observed (E-step only)
+    using mask_t = typename std::conditional<(CH > 32), unsigned long long, unsigned>::type;
+    mask_t obsmask = 0;        // bit j: position t0+j observed (E-step only)
     float P[K][K];
     mat_set_identity<K>(P);
     float ll_sumo = 0.0f;
@@ -320,7 +322,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
       for (int j = 0; j < CH; ++j) {
         const float o = obs_to_float<ObsT>(s_in[t0 + j]);
         const bool m = (o == o);
-        if (STATS) obsmask |= m ? (1u << j) : 0u;
+        if (STATS) obsmask |= m ? ((mask_t)1 << j) : (mask_t)0;
         if (STATS || RECOMP) ov[j] = o;
         float c[K];
         c[0] = 1.0f;
@@ -670,7 +672,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
 #pragma unroll
             for (int k = 0; k < K; ++k) acc_start[k] += gk[k];
           }
-          if ((obsmask >> j) & 1u) {
+          if ((obsmask >> j) & (mask_t)1) {
 #pragma unroll
             for (int k = 0; k < K; ++k) {
               acc_num[k] = fmaf(gk[k], ov[j], acc_num[k]);
@@ -690,8 +692,8 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
           if (STATS) {
             // xi_{t-1}(i,jj) ~ alpha_{t-1}(i) Ap[i][jj] cb[jj], t = t0+j > 0, counted when both
             // endpoints are observed (HMM.py:1583-1591)
-            const bool prev_obs = (j > 0) ? (((obsmask >> (j > 0 ? j - 1 : 0)) & 1u) != 0u) : prev_obs0;
-            const bool valid = ((obsmask >> j) & 1u) && prev_obs;
+            const bool prev_obs = (j > 0) ? (((obsmask >> (j > 0 ? j - 1 : 0)) & (mask_t)1) != 0) : prev_obs0;
+            const bool valid = ((obsmask >> j) & (mask_t)1) && prev_obs;
             float s2 = 0.0f;
 #pragma unroll
             for (int i = 0; i < K; ++i) s2 = fmaf(alp[i], nb[i], s2);

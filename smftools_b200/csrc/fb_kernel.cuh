@@ -898,14 +898,4 @@ __global__ void __launch_bounds__(MAXT) fb_kernel(const __grid_constant__ FbTabl
   }
 }
 
-// Fixed-order reduction of the per-CTA partial statistics.
-__global__ void reduce_partials_kernel(const double* __restrict__ partials, int nblocks, int S,
-                                       double* __restrict__ stats) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= S) return;
-  double tot = 0.0;
-  for (int b = 0; b < nblocks; ++b) tot += partials[(size_t)b * S + s];
-  stats[s] = tot;
-}
-
 }  // namespace smf

@@ -1,0 +1,121 @@
+// Host-side launch plumbing shared by the translation units of libsmfhmm.so.
+// Kernels are instantiated in per-K .cu files (compiled in parallel); api.cu only plans and dispatches.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "fb2_kernel.cuh"
+#include "fb_kernel.cuh"
+#include "smf_hmm.h"
+#include "viterbi_kernel.cuh"
+
+namespace smf {
+
+struct DeviceInfo {
+  int device = -1;
+  int num_sms = 0;
+  int max_smem_optin = 0;
+};
+
+struct FbPlan {
+  int T, chunk, groups, smem, block;
+};
+struct Fb2Plan {
+  int block, smem, chunk;
+};
+
+// Threads a group may use for a given model / mode (register budget; equals the kernels' launch bounds).
+constexpr int fb_max_threads_c(int K, bool stats) {
+  return stats ? (K == 2 ? 640 : (K == 3 ? 512 : 384)) : (K == 4 ? 512 : 640);
+}
+constexpr int fb2_max_threads_c(int K, bool stats) {
+  return stats ? (K == 2 ? 640 : (K == 3 ? 512 : 480)) : (K == 4 ? 576 : 640);
+}
+
+template <int K>
+static void build_fb_tables(const smf_hmm_tables* t, FbTables<K>* out) {
+  memset(out, 0, sizeof(*out));
+  const int C = t->n_channels;
+  const double log2e = 1.4426950408889634074;
+  double pisum = 0.0;
+  for (int k = 0; k < K; ++k) {
+    const double p = exp(t->log_start[k]);
+    out->pi[k] = (float)p;
+    pisum += (double)out->pi[k];
+  }
+  out->log_pi_sum = log(pisum);
+  for (int b = 0; b < t->n_bins; ++b)
+    for (int i = 0; i < K; ++i)
+      for (int j = 0; j < K; ++j) out->A[b][i][j] = (float)exp(t->log_trans[(b * K + i) * K + j]);
+  for (int c = 0; c < C; ++c) {
+    const double l0_0 = t->log_emit0[0 * C + c];
+    const double d_0 = t->log_emit1[0 * C + c] - l0_0;
+    out->l00[c] = l0_0;
+    out->dl0[c] = d_0;
+    for (int k = 0; k < K; ++k) {
+      const double l0 = t->log_emit0[k * C + c];
+      const double d = t->log_emit1[k * C + c] - l0;
+      out->rl0[k][c] = (float)((l0 - l0_0) * log2e);
+      out->rdl[k][c] = (float)((d - d_0) * log2e);
+    }
+  }
+  // fast-path tables (bin 0, channel 0)
+  {
+    double sdiag[K];
+    for (int j = 0; j < K; ++j) sdiag[j] = exp(t->log_trans[j * K + j]);
+    for (int i = 0; i < K; ++i)
+      for (int j = 0; j < K; ++j) out->Ap[i][j] = (i == j) ? 1.0f : (float)(exp(t->log_trans[i * K + j]) / sdiag[j]);
+    double p2sum = 0.0;
+    const double l0_0 = t->log_emit0[0];
+    const double d_0 = t->log_emit1[0] - l0_0;
+    (void)d_0;
+    for (int k = 0; k < K; ++k) {
+      const double ratio = sdiag[k] / sdiag[0];
+      out->pi2[k] = (float)(exp(t->log_start[k]) / ratio);
+      p2sum += (double)out->pi2[k];
+      const double l0 = t->log_emit0[k * C];
+      out->rl0p[k] = (float)((l0 - l0_0) * log2e + log2(ratio));
+      out->rmiss[k] = (float)log2(ratio);
+    }
+    out->log_s0 = t->log_trans[0];
+    out->log_pi2_sum = log(p2sum);
+  }
+  out->nb = t->n_bins;
+  out->C = C;
+}
+
+template <int K>
+static void build_vit_tables(const smf_hmm_tables* t, VitTables<K>* out) {
+  memset(out, 0, sizeof(*out));
+  const int C = t->n_channels;
+  for (int k = 0; k < K; ++k) out->log_pi[k] = t->log_start[k];
+  for (int b = 0; b < t->n_bins; ++b)
+    for (int i = 0; i < K; ++i)
+      for (int j = 0; j < K; ++j) out->logA[b][i][j] = t->log_trans[(b * K + i) * K + j];
+  for (int k = 0; k < K; ++k)
+    for (int c = 0; c < C; ++c) {
+      out->l1[k][c] = t->log_emit1[k * C + c];
+      out->l0[k][c] = t->log_emit0[k * C + c];
+    }
+  out->nb = t->n_bins;
+  out->C = C;
+}
+
+
+// per-K launchers (fb2_k*.cu, fb_k*.cu, vit_k*.cu)
+#define SMF_DECLARE_K(KV)                                                                                      \
+  int launch_fb2_k##KV(int chunk, bool stats, int obs_dtype, int out_mode, int minb, const smf_hmm_tables* t, \
+                       Fb2Args& a, const Fb2Plan& plan, const DeviceInfo& di, int* nblocks, cudaStream_t s);  \
+  int launch_fb_k##KV(bool stats, const smf_hmm_tables* t, FbArgs& a, const FbPlan& plan, const DeviceInfo& di, \
+                      int* nblocks, cudaStream_t s);                                                           \
+  int launch_vit_k##KV(const smf_hmm_tables* t, const VitArgs& a, const DeviceInfo& di, cudaStream_t s);
+SMF_DECLARE_K(2)
+SMF_DECLARE_K(3)
+SMF_DECLARE_K(4)
+#undef SMF_DECLARE_K
+
+static inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
+
+}  // namespace smf
