@@ -154,6 +154,16 @@ static int plan_fb(int K, int C, int nb, int64_t L64, bool stats, int S, int max
 // ---------------------------------------------------------------------------------------
 // fast path (fb2_kernel): single channel, homogeneous transitions, compile-time chunk (17 or 33)
 // ---------------------------------------------------------------------------------------
+// Resident reads per SM for a candidate layout: shared memory (228 KB per SM, 1 KB reserved per CTA),
+// registers (64 K per SM) and the 32-CTA limit.
+static int fb2_resident(int total_smem, int block, int groups, int regs) {
+  const int by_smem = (228 * 1024) / (total_smem + 1024);
+  const int by_regs = 65536 / (regs * block);
+  int ctas = by_smem < by_regs ? by_smem : by_regs;
+  if (ctas > 32) ctas = 32;
+  return ctas * groups;
+}
+
 static int plan_fb2_chunk(int K, int CH, int64_t L64, bool stats, int S, int es, bool want_gamma_one,
                           bool want_states, int max_smem, Fb2Args* a, Fb2Plan* plan) {
   if (L64 < 1) return SMF_ERR_TOO_LONG;
@@ -164,47 +174,66 @@ static int plan_fb2_chunk(int K, int CH, int64_t L64, bool stats, int S, int es,
   if (T > fb2_max_threads(K, stats)) return SMF_ERR_TOO_LONG;
   const int Lpad = Tact * CH;
   const int KK = K * K;
+  const int regs = (stats && K >= 3) || (K == 4 && stats) ? 128 : 96;
   const int bar_b = 16;
   const int in_b = align_up((Lpad + 16) * es + 16, 16);
   const int stage_b = align_up((Lpad * K + 4) * 4, 16);
   const int out1_b = want_gamma_one ? align_up((Lpad + 4) * 4, 16) : 0;
   const int st_b = want_states ? align_up(Lpad + 32, 16) : 0;
   const int scan_b = align_up(32 * (KK + 2 * K) * 4 + 32 * 8, 16);
-  const int obuf_b = stage_b + out1_b + st_b;  // one output staging set
   int groups = 256 / T;
   if (groups < 1) groups = 1;
   if (groups > 8) groups = 8;
-  // prefer double-buffered output staging (bulk stores of read i drain while read i+1 computes)
   static const int env_nbuf = [] { const char* e = getenv("SMF_FB2_NBUF"); return e ? atoi(e) : 0; }();
-  for (int nbuf = (stats || env_nbuf == 1) ? 1 : 2; nbuf >= 1; --nbuf) {
-    const int group_bytes = bar_b + in_b + nbuf * obuf_b + scan_b;
+  static const int env_alias = [] { const char* e = getenv("SMF_FB2_ALIAS"); return e ? atoi(e) : -1; }();
+  // Candidate layouts, in order of preference at equal residency:
+  //   double-buffered staging + prefetch  <  single-buffered + prefetch  <  single-buffered, obs aliased
+  // The layout that keeps the most reads resident per SM wins (measured: profiles/r01_chunk_sweep.txt).
+  int best_res = -1;
+  for (int cand = 0; cand < 3; ++cand) {
+    const int nbuf = (cand == 0 && !stats) ? 2 : 1;
+    const bool alias = (cand == 2);
+    if (cand == 0 && stats) continue;
+    if (env_nbuf == 1 && nbuf == 2) continue;
+    if (env_nbuf == 2 && nbuf == 1) continue;
+    // measured: losing the prefetch costs more than the extra resident reads bring (C2 0.71 vs 0.80,
+    // 10 kb 0.60 vs 0.64 of HBM peak), so the aliased layout is opt-in (SMF_FB2_ALIAS=1) for now
+    // ... it is still the only fast-path layout for the longest reads (e.g. 20 kb, K = 2)
+    if (env_alias != 1 && alias && best_res > 0) continue;
+    if (env_alias == 1 && !alias) continue;
+    const int stage_eff = alias ? (stage_b > in_b ? stage_b : in_b) : stage_b;
+    const int obuf_b = stage_eff + out1_b + st_b;  // one output staging set
+    const int group_bytes = bar_b + (alias ? 0 : in_b) + nbuf * obuf_b + scan_b;
     for (int gr = groups; gr >= 1; --gr) {
-      if (nbuf == 2 && gr < groups && gr > 1) continue;  // only trade groups for buffers at the extremes
       const int warps = gr * T / 32;
       const int wacc_b = stats ? align_up(warps * S * 8, 16) : 0;
       const int total = wacc_b + gr * group_bytes;
-      if (total <= max_smem) {
+      if (total > max_smem) continue;
+      const int res = fb2_resident(total, T * gr, gr, regs);
+      if (res > best_res) {
+        best_res = res;
         a->off_wacc = 0;
         a->off_group0 = wacc_b;
         a->group_bytes = group_bytes;
         a->goff_bar = 0;
         a->goff_in = bar_b;
-        a->goff_stage = bar_b + in_b;
-        a->goff_out1 = bar_b + in_b + stage_b;
-        a->goff_st = bar_b + in_b + stage_b + out1_b;
-        a->goff_scan = bar_b + in_b + nbuf * obuf_b;
+        a->goff_stage = alias ? bar_b : bar_b + in_b;
+        a->goff_out1 = a->goff_stage + stage_eff;
+        a->goff_st = a->goff_out1 + out1_b;
+        a->goff_scan = a->goff_stage + nbuf * obuf_b;
         a->nbuf = nbuf;
+        a->alias_in = alias ? 1 : 0;
         a->obuf_bytes = obuf_b;
         a->T = T;
         a->groups = gr;
         plan->block = T * gr;
         plan->smem = total;
         plan->chunk = CH;
-        return SMF_OK;
       }
+      break;  // the largest group count that fits is the candidate for this layout
     }
   }
-  return SMF_ERR_TOO_LONG;
+  return best_res > 0 ? SMF_OK : SMF_ERR_TOO_LONG;
 }
 
 // chunk 17 whenever the read fits its thread budget; chunk 33 (K = 2, 4) for reads up to twice as long

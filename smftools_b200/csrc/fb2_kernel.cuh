@@ -32,6 +32,8 @@ struct Fb2Args {
   int T;            // threads per group (multiple of 32)
   int groups;       // reads in flight per CTA
   int flush_every;
+  int alias_in;     // 1: the observation buffer shares memory with the staging buffer (no prefetch; the next
+                    //    read is loaded once this read's stores have left shared memory)
   int nbuf;         // output staging buffers per group (2 = a read's bulk stores drain while the next read computes)
   int obuf_bytes;   // bytes between the two staging sets (stage | out1 | st)
   int off_wacc;     // CTA-wide double [warps][S]
@@ -407,7 +409,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
     } else {
       __syncwarp();
     }
-    if (gt == 0) {
+    if (gt == 0 && !a.alias_in) {
       // the observation buffer is free: prefetch the next read of this group
       const long long nn = n + read_stride;
       if (nn < a.N) issue_load(nn);
@@ -747,6 +749,16 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
       }
     }
     if (STATS && ((iter + 1) % a.flush_every) == 0) flush_stats();
+    if (a.alias_in) {
+      // the staging buffer doubles as the observation buffer: the next read may only be loaded once
+      // every warp's bulk stores have finished reading it
+      if (!STATS && lane == 0) bulk_wait_read_all();
+      group_sync(bar_id, T);
+      if (gt == 0) {
+        const long long nn = n + read_stride;
+        if (nn < a.N) issue_load(nn);
+      }
+    }
   }
 
   if (!STATS && lane == 0) bulk_wait_all();  // all bulk stores complete before the CTA retires
