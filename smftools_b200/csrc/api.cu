@@ -239,13 +239,19 @@ static int plan_fb2_chunk(int K, int CH, int64_t L64, bool stats, int S, int es,
 // chunk 17 whenever the read fits its thread budget; chunk 33 (K = 2, 4) for reads up to twice as long
 static int plan_fb2(int K, int64_t L64, bool stats, int S, int es, bool want_gamma_one, bool want_states,
                     int max_smem, Fb2Args* a, Fb2Plan* plan) {
-  // Measured on B200 (profiles/r01_chunk_sweep.txt): for K = 2 the longer chunk wins from ~4 kb on
-  // (half the scan / barrier overhead per position outweighs the halved warp count); for short
-  // reads, for K = 4 (register pressure) and for the E-step (more live registers) chunk 17 is
-  // faster.  SMF_FB2_CHUNK overrides.
+  // Measured on B200 (profiles/r01_chunk_sweep.txt): for K = 2 posterior decode the longer chunk wins
+  // whenever it keeps the lanes about as busy (half the scan / barrier overhead per position outweighs
+  // the halved warp count); for K = 4 (register pressure) and for the E-step (more live registers)
+  // chunk 17 is faster.  SMF_FB2_CHUNK overrides.
   static const int env_ch = [] { const char* e = getenv("SMF_FB2_CHUNK"); return e ? atoi(e) : 0; }();
   const bool can33 = (K != 3);
-  const bool prefer33 = can33 && (env_ch == 33 || (env_ch == 0 && K == 2 && !stats && L64 >= 4000));
+  // lane utilisation of the two chunk lengths (threads are allocated in whole warps)
+  auto lane_eff = [&](int ch) {
+    const long long tact = (L64 + ch - 1) / ch;
+    const long long t = (tact + 31) / 32 * 32;
+    return (double)L64 / (double)(t * ch);
+  };
+  const bool prefer33 = can33 && (env_ch == 33 || (env_ch == 0 && K == 2 && !stats && lane_eff(33) >= 0.9 * lane_eff(17)));
   if (prefer33 &&
       plan_fb2_chunk(K, 33, L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan) == SMF_OK)
     return SMF_OK;
