@@ -516,8 +516,9 @@ def run_ours(args, wl):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
                          "algorithmic_bytes_per_read_position": algo, "kernel_ms": k_ms,
-                         "kernel": {"posterior": "fb_kernel<K,...,STATS=false>", "viterbi": "viterbi_kernel",
-                                    "estep": "fb_kernel<K,...,STATS=true>"}[op]},
+                         "kernel": {"posterior": "smf::fb2_kernel<K, CH, STATS=false, ...> (one launch per step)",
+                                    "viterbi": "smf::viterbi_kernel (+ smf::call_intervals_kernel)",
+                                    "estep": "smf::fb2_kernel<K, CH, STATS=true, ...> (+ reduce_partials_kernel)"}[op]},
             "baum_welch": bw,
         }
         if world == 1 and not args.no_cpu:
