@@ -706,10 +706,27 @@ class BaseHMM(nn.Module):
             total = torch.zeros((engine.stats_len(tables),), dtype=torch.float64, device=device)
         return total
 
-    def _resident_chunks(self, src, device) -> List[torch.Tensor]:
+    def _resident_chunks(self, src, device):
+        """Observations for the EM loop: device-resident read chunks (uploaded once, reused by every
+        iteration), or -- when the input does not fit in the free device memory -- a generator that
+        streams the chunks from the host in every iteration."""
         if isinstance(src, torch.Tensor) and src.is_cuda:
             return [src.contiguous()]
-        return [self._to_device(src, device)]
+        N = int(src.shape[0])
+        row_bytes = int(np.prod(src.shape[1:])) * (src.element_size() if isinstance(src, torch.Tensor)
+                                                   else src.dtype.itemsize)
+        rows = max(1, int(self.device_chunk_bytes // max(row_bytes, 1)))
+        bounds = [(lo, min(N, lo + rows)) for lo in range(0, N, rows)]
+        free, _total = torch.cuda.mem_get_info(device)
+        if N * row_bytes <= 0.8 * free:
+            return [self._to_device(src[lo:hi], device) for lo, hi in bounds]
+
+        class _Streamed:
+            def __iter__(inner):
+                for lo, hi in bounds:
+                    yield self._to_device(src[lo:hi], device)
+
+        return _Streamed()
 
     def _allreduce_stats(self, stats: torch.Tensor) -> torch.Tensor:
         if self.process_group is None and not self.distributed:
@@ -967,15 +984,6 @@ class BaseHMM(nn.Module):
         n_obs, n_vars = adata.n_obs, adata.n_vars
         use_viterbi = str(decode).lower() == "viterbi"
 
-        # -- decode on the device; everything below consumes device tensors --
-        tables = self._host_tables()
-        bins = self._bins_for(coords, L, device)
-        obs = self._to_device(src, device)
-        gamma_d, states_d, _ = engine.posterior(tables, obs, bins, want_gamma=True, want_states=not use_viterbi)
-        if use_viterbi:
-            states_d = engine.viterbi(tables, obs, bins)
-        del obs
-
         full_coords, full_int = _safe_int_coords(adata.var_names)
         masked_idx = np.nonzero(var_mask)[0]
         masked_coords, _ = _safe_int_coords(adata.var_names[var_mask])
@@ -990,47 +998,25 @@ class BaseHMM(nn.Module):
             if name not in appended:
                 appended.append(name)
 
+        # ---- allocate / register the output layers in the reference's order (HMM.py:1256-1315) ----
         states_name = f"{prefix}_states"
         if states_name not in adata.layers:
             adata.layers[states_name] = np.full((n_obs, n_vars), -1, dtype=np.int8)
-        states_h = states_d.cpu().numpy()
-        adata.layers[states_name][:, masked_idx] = states_h[:, take]
         note(states_name)
-
+        post_name = None
+        t_post = None
         if write_posterior:
-            t_idx = self.resolve_target_state_index(posterior_state)
+            t_post = self.resolve_target_state_index(posterior_state)
             tag = str(posterior_state).strip().lower().replace(" ", "_").replace("-", "_")
             post_name = f"{prefix}_posterior_{tag}"
             if post_name not in adata.layers:
                 adata.layers[post_name] = np.zeros((n_obs, n_vars), dtype=np.float32)
-            post_h = gamma_d[:, :, t_idx].contiguous().cpu().numpy()
-            adata.layers[post_name][:, masked_idx] = post_h[:, take]
             note(post_name)
 
         if feature_sets is None:
             feature_sets = normalize_hmm_feature_sets(self._cfg_to_dict(config).get("hmm_feature_sets", None))
-        if not feature_sets:
-            adata.uns[uns_key] = appended
-            adata.uns[uns_flag] = True
-            return None
-
-        # can the device span-fill kernel be used?  (sites strictly increasing and on the grid)
-        kernel_ok = bool(span_fill and full_int and L > 0)
-        if kernel_ok:
-            left = np.searchsorted(full_coords, coords, side="left")
-            right = np.searchsorted(full_coords, coords, side="right")
-            kernel_ok = bool(
-                np.all(np.diff(coords) > 0)
-                and np.all(np.diff(full_coords) >= 0)
-                and np.all(left < n_vars)
-                and np.all(full_coords[np.minimum(left, n_vars - 1)] == coords)
-            )
-        if kernel_ok:
-            coords_d = torch.from_numpy(np.ascontiguousarray(coords, dtype=np.int64)).to(device)
-            left_d = torch.from_numpy(np.ascontiguousarray(left, dtype=np.int32)).to(device)
-            right_d = torch.from_numpy(np.ascontiguousarray(right, dtype=np.int32)).to(device)
-
-        for group, fs in feature_sets.items():
+        groups = []
+        for group, fs in (feature_sets or {}).items():
             fmap = fs.get("features", {}) or {}
             if not fmap:
                 continue
@@ -1053,52 +1039,99 @@ class BaseHMM(nn.Module):
                     adata.layers[f"{nm}_lengths"] = np.zeros((n_obs, n_vars), dtype=np.int32)
                 note(nm)
                 note(f"{nm}_lengths")
-
-            target_idx = self.resolve_target_state_index(fs.get("state", "Modified"))
             feats = list(fmap.keys())
-            ranges = [fmap[f] for f in feats]
-            clean = not pre_existing
+            groups.append(dict(name=group, all_layer=all_layer, feats=feats, ranges=[fmap[f] for f in feats],
+                               target=self.resolve_target_state_index(fs.get("state", "Modified")),
+                               clean=not pre_existing))
 
-            if kernel_ok:
-                if use_viterbi:
-                    cls_d, len_d, _ = engine.call_features(
-                        states=states_d, post=None, target=target_idx, threshold=0.0, coords=coords_d,
-                        grid_left=left_d, grid_right=right_d, n_grid=n_vars, ranges=ranges)
+        # can the device span-fill kernel be used?  (sites strictly increasing and on the grid)
+        kernel_ok = bool(groups and span_fill and full_int and L > 0)
+        if kernel_ok:
+            left = np.searchsorted(full_coords, coords, side="left")
+            right = np.searchsorted(full_coords, coords, side="right")
+            kernel_ok = bool(
+                np.all(np.diff(coords) > 0)
+                and np.all(np.diff(full_coords) >= 0)
+                and np.all(left < n_vars)
+                and np.all(full_coords[np.minimum(left, n_vars - 1)] == coords)
+            )
+        if kernel_ok:
+            coords_d = torch.from_numpy(np.array(coords, dtype=np.int64, copy=True)).to(device)
+            left_d = torch.from_numpy(np.ascontiguousarray(left, dtype=np.int32)).to(device)
+            right_d = torch.from_numpy(np.ascontiguousarray(right, dtype=np.int32)).to(device)
+
+        # ---- decode + feature calling on the device, one chunk of reads at a time ----
+        tables = self._host_tables()
+        bins = self._bins_for(coords, L, device)
+        K = self.n_states
+        C = int(src.shape[2]) if src.ndim == 3 else 1
+        item = src.element_size() if isinstance(src, torch.Tensor) else src.dtype.itemsize
+        per_read = L * (C * item + 4 * K + 2) + n_vars * 5 * max(1, len(groups)) + 64
+        rows = max(1, int(self.device_chunk_bytes // per_read))
+        for lo in range(0, N, rows):
+            hi = min(N, lo + rows)
+            obs = self._to_device(src[lo:hi], device)
+            gamma_d, states_d, _ = engine.posterior(tables, obs, bins, want_gamma=True,
+                                                    want_states=not use_viterbi)
+            if use_viterbi:
+                states_d = engine.viterbi(tables, obs, bins)
+            del obs
+            states_h = states_d.cpu().numpy()
+            adata.layers[states_name][lo:hi, masked_idx] = states_h[:, take]
+            if post_name is not None:
+                post_h = gamma_d[:, :, t_post].contiguous().cpu().numpy()
+                adata.layers[post_name][lo:hi, masked_idx] = post_h[:, take]
+            for gr in groups:
+                all_layer, feats, ranges, target_idx = gr["all_layer"], gr["feats"], gr["ranges"], gr["target"]
+                if kernel_ok:
+                    if use_viterbi:
+                        cls_d, len_d, _ = engine.call_features(
+                            states=states_d, post=None, target=target_idx, threshold=0.0, coords=coords_d,
+                            grid_left=left_d, grid_right=right_d, n_grid=n_vars, ranges=ranges)
+                    else:
+                        post_d = gamma_d[:, :, target_idx].contiguous()
+                        cls_d, len_d, _ = engine.call_features(
+                            states=None, post=post_d, target=target_idx, threshold=float(prob_threshold),
+                            coords=coords_d, grid_left=left_d, grid_right=right_d, n_grid=n_vars, ranges=ranges)
+                    cls_h = cls_d.cpu().numpy()
+                    len_h = len_d.cpu().numpy()
+                    any_hit = cls_h > 0
+                    if gr["clean"]:
+                        adata.layers[all_layer][lo:hi] = any_hit.astype(np.uint8)
+                        adata.layers[f"{all_layer}_lengths"][lo:hi] = np.where(any_hit, len_h, 0).astype(np.int32)
+                        for ci, feat in enumerate(feats):
+                            hit = cls_h == (ci + 1)
+                            adata.layers[f"{prefix}_{feat}"][lo:hi] = hit.astype(np.uint8)
+                            adata.layers[f"{prefix}_{feat}_lengths"][lo:hi] = np.where(hit, len_h, 0).astype(np.int32)
+                    else:
+                        # layers carried over from an earlier annotation: OR the new runs in and
+                        # recompute run lengths on the union (HMM.py:1348-1370)
+                        lay = np.asarray(adata.layers[all_layer])
+                        lay[lo:hi][any_hit] = 1
+                        adata.layers[all_layer] = lay
+                        adata.layers[f"{all_layer}_lengths"][lo:hi] = _run_lengths_np(lay[lo:hi])
+                        for ci, feat in enumerate(feats):
+                            lay = np.asarray(adata.layers[f"{prefix}_{feat}"])
+                            lay[lo:hi][cls_h == (ci + 1)] = 1
+                            adata.layers[f"{prefix}_{feat}"] = lay
+                            adata.layers[f"{prefix}_{feat}_lengths"][lo:hi] = _run_lengths_np(lay[lo:hi])
                 else:
-                    post_d = gamma_d[:, :, target_idx].contiguous()
-                    cls_d, len_d, _ = engine.call_features(
-                        states=None, post=post_d, target=target_idx, threshold=float(prob_threshold),
-                        coords=coords_d, grid_left=left_d, grid_right=right_d, n_grid=n_vars, ranges=ranges)
-                cls_h = cls_d.cpu().numpy()
-                len_h = len_d.cpu().numpy()
-                any_hit = cls_h > 0
-                if clean:
-                    adata.layers[all_layer] = any_hit.astype(np.uint8)
-                    adata.layers[f"{all_layer}_lengths"] = np.where(any_hit, len_h, 0).astype(np.int32)
-                    for ci, feat in enumerate(feats):
-                        hit = cls_h == (ci + 1)
-                        adata.layers[f"{prefix}_{feat}"] = hit.astype(np.uint8)
-                        adata.layers[f"{prefix}_{feat}_lengths"] = np.where(hit, len_h, 0).astype(np.int32)
-                else:
-                    # layers carried over from an earlier annotation: OR the new runs in and
-                    # recompute run lengths on the union (HMM.py:1348-1370)
-                    lay = np.asarray(adata.layers[all_layer])
-                    lay[any_hit] = 1
-                    adata.layers[all_layer] = lay
-                    adata.layers[f"{all_layer}_lengths"] = _run_lengths_np(lay)
-                    for ci, feat in enumerate(feats):
-                        lay = np.asarray(adata.layers[f"{prefix}_{feat}"])
-                        lay[cls_h == (ci + 1)] = 1
-                        adata.layers[f"{prefix}_{feat}"] = lay
-                        adata.layers[f"{prefix}_{feat}_lengths"] = _run_lengths_np(lay)
-            else:
-                membership = (
-                    (states_h == target_idx) if use_viterbi
-                    else (gamma_d[:, :, target_idx].contiguous().cpu().numpy().astype(np.float64)
-                          >= float(prob_threshold))
-                )
-                self._fill_features_host(adata, prefix, group, feats, ranges, membership, coords, full_coords,
-                                         bool(span_fill and full_int), masked_idx, masked_coords_good)
+                    membership = (
+                        (states_h == target_idx) if use_viterbi
+                        else (gamma_d[:, :, target_idx].contiguous().cpu().numpy().astype(np.float64)
+                              >= float(prob_threshold))
+                    )
+                    self._fill_features_host(adata, prefix, gr["name"], feats, ranges, membership, coords,
+                                             full_coords, bool(span_fill and full_int), masked_idx,
+                                             masked_coords_good, lo)
+            del gamma_d, states_d
+
+        if not feature_sets:
+            # no feature sets: only states / posterior are written and, like the reference, no
+            # read-span masking is applied (HMM.py:1280-1283)
+            adata.uns[uns_key] = appended
+            adata.uns[uns_flag] = True
+            return None
 
         if mask_to_read_span and appended:
             mask_layers_outside_read_span(adata, appended, use_original_var_names=mask_use_original_var_names)
@@ -1109,14 +1142,15 @@ class BaseHMM(nn.Module):
 
     @staticmethod
     def _fill_features_host(adata, prefix, group, feats, ranges, membership, coords, full_coords, span_ok,
-                            masked_idx, masked_coords):
+                            masked_idx, masked_coords, row0=0):
         """Generic (slow) span-fill used when the site grid does not satisfy the kernel's
         preconditions (unsorted / off-grid coordinates, ``span_fill=False``, non-integer var names)."""
         all_layer = f"{prefix}_all_{group}_features"
         lo = np.array([float(r[0]) for r in ranges])
         hi = np.array([float(r[1]) for r in ranges])
-        for i in range(membership.shape[0]):
-            for s, e in BaseHMM._runs_from_bool(membership[i]):
+        for r in range(membership.shape[0]):
+            i = row0 + r
+            for s, e in BaseHMM._runs_from_bool(membership[r]):
                 glen = int(coords[e - 1]) - int(coords[s]) + 1 if e > s else 0
                 if glen <= 0:
                     continue

@@ -69,6 +69,38 @@ def test_annotate_adata_layers_match_reference(name):
         np.testing.assert_array_equal(np.asarray(ad.layers[k]), v)
 
 
+@pytest.mark.parametrize("name", ANNOT)
+def test_annotate_in_small_read_chunks_gives_identical_layers(name):
+    """Force the chunked device pipeline (a few reads per chunk) and the multi-chunk EM path."""
+    g = load_golden(name)
+    p = params_from_golden(g)
+    m = model_from_params(p)
+    m.device_chunk_bytes = 40_000  # ~3 reads per chunk
+    ad = _adata_from_golden(g)
+    m.annotate_adata(ad, prefix="GpC", X=g["X"].astype(np.float64), coords=g["coords"], var_mask=g["var_mask"],
+                     decode=str(g["decode"]), feature_sets=_feature_sets(g), prob_threshold=0.5)
+    for nm in [str(a) for a in g["appended"]]:
+        if "posterior" in nm:
+            np.testing.assert_allclose(ad.layers[nm], g[f"layer__{nm}"], rtol=0, atol=1e-5, equal_nan=True)
+        else:
+            np.testing.assert_array_equal(ad.layers[nm], g[f"layer__{nm}"], err_msg=nm)
+    # fit with the observations split over several resident chunks == one chunk
+    X = g["X"].astype(np.float64)
+    m1 = model_from_params(p)
+    m2 = model_from_params(p)
+    m2.device_chunk_bytes = 3 * X.shape[1] * 8
+    h1 = m1.fit(X, g["coords"], max_iter=3, tol=0.0)
+    h2 = m2.fit(X, g["coords"], max_iter=3, tol=0.0)
+    assert np.allclose(h1, h2, rtol=1e-12)
+    assert np.abs(m1.emission.detach().numpy() - m2.emission.detach().numpy()).max() < 1e-12
+    # feature sets absent -> only states / posterior, unmasked (HMM.py:1280-1283)
+    ad2 = _adata_from_golden(g)
+    m.annotate_adata(ad2, prefix="GpC", X=X, coords=g["coords"], var_mask=g["var_mask"], decode=str(g["decode"]),
+                     feature_sets={})
+    assert list(ad2.uns["hmm_appended_layers"]) == ["GpC_states", "GpC_posterior_modified"]
+    assert ad2.layers["GpC_states"].dtype == np.int8 and not np.isnan(ad2.layers["GpC_posterior_modified"]).any()
+
+
 @pytest.mark.parametrize("N,L,seed", [(257, 700, 1), (64, 3001, 2), (1, 40, 3), (300, 5, 4)])
 def test_feature_kernels_against_oracle(N, L, seed):
     from smftools_b200 import engine
