@@ -274,7 +274,7 @@ def run_reference(args, wl):
         "e2e": {"value": v, "unit": "read-positions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------
@@ -328,14 +328,14 @@ def run_groups(args, wl):
     ms = float(t.item()) / steps
     rp = float(sum(N * int(lengths[g]) * 6 for g in range(16)))  # 5 E-steps + 1 decode per position
     if rank == 0:
-        print(json.dumps({
+        emit({
             "metric": "HMM read-positions/sec", "value": rp / (ms * 1e-3), "unit": "read-positions/s", "n_gpus": world,
             "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "op": "5x Baum-Welch iteration + posterior decode per group",
                        "groups": 16, "reads_per_group": N, "lengths": [int(x) for x in lengths], "K": K},
             "gpu_launches": steps * len(mine) * 11,
-        }), flush=True)
+        })
     if world > 1:
         dist.destroy_process_group()
 
@@ -525,12 +525,35 @@ def run_ours(args, wl):
             line["cpu_baseline"] = cpu_baseline(wl)
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Route everything that writes to fd 1 (NCCL's version banner, library chatter) to stderr so
+    that the ONE JSON line is the only thing on stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
