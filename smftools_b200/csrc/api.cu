@@ -174,7 +174,7 @@ static int plan_fb2_chunk(int K, int CH, int64_t L64, bool stats, int S, int es,
   if (T > fb2_max_threads(K, stats)) return SMF_ERR_TOO_LONG;
   const int Lpad = Tact * CH;
   const int KK = K * K;
-  const int regs = (stats && K >= 3) || (K == 4 && stats) ? 128 : 96;
+  const int regs = ((stats && K >= 3) || K == 4) ? 128 : 96;  // registers/thread of the instantiation (ptxas)
   const int bar_b = 16;
   const int in_b = align_up((Lpad + 16) * es + 16, 16);
   const int stage_b = align_up((Lpad * K + 4) * 4, 16);

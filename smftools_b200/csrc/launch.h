@@ -31,7 +31,7 @@ constexpr int fb_max_threads_c(int K, bool stats) {
   return stats ? (K == 2 ? 640 : (K == 3 ? 512 : 384)) : (K == 4 ? 512 : 640);
 }
 constexpr int fb2_max_threads_c(int K, bool stats) {
-  return stats ? (K == 2 ? 640 : (K == 3 ? 512 : 480)) : (K == 4 ? 576 : 640);
+  return stats ? (K == 2 ? 640 : (K == 3 ? 512 : 480)) : (K == 4 ? 512 : 640);
 }
 
 template <int K>
