@@ -369,7 +369,7 @@ def run_ours(args, wl):
     if op == "viterbi":
         ws = torch.empty((N * L,), dtype=torch.uint8, device=device)
     if op == "estep":
-        ws = engine.estep_workspace(tables, device)
+        ws = engine.estep_workspace(tables, device, N, L)
         stats = torch.empty((engine.stats_len(tables),), dtype=torch.float64, device=device)
 
     feat = None
@@ -473,7 +473,7 @@ def run_ours(args, wl):
     bw = None
     if op == "posterior" and not args.no_bw:
         n_bw = N
-        wsb = engine.estep_workspace(tables, device)
+        wsb = engine.estep_workspace(tables, device, n_bw, L)
         stats = torch.empty((engine.stats_len(tables),), dtype=torch.float64, device=device)
 
         def bw_iter():

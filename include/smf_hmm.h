@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SMF_HMM_ABI_VERSION 1
+#define SMF_HMM_ABI_VERSION 2
 
 #define SMF_MAX_STATES 4
 #define SMF_MAX_CHANNELS 4
@@ -78,6 +78,15 @@ typedef struct smf_hmm_tables {
 int smf_hmm_abi_version(void);
 const char* smf_hmm_strerror(int code);
 
+/*
+ * Process-wide tuning knobs (not needed for correct results).  Keys:
+ *   "walk"   -1 (default) let the library choose between the single-kernel and the two-kernel
+ *            forward-backward path from its measured policy; 0 never / 1 whenever possible use the
+ *            two-kernel path.  smf_hmm_workspace_bytes() follows the setting.
+ * Returns SMF_ERR_BAD_ARG for an unknown key or value.
+ */
+int smf_hmm_set_option(const char* key, int value);
+
 /* Bytes of caller-owned device workspace an operation needs (0 = none). */
 size_t smf_hmm_workspace_bytes(int op, const smf_hmm_tables* tab, int64_t n_reads, int64_t n_pos);
 
@@ -92,10 +101,16 @@ int64_t smf_hmm_max_positions(const smf_hmm_tables* tab, int want_all_states);
  *   gamma       device float [N, L, K] (gamma_state < 0) or [N, L] holding state `gamma_state`; may be NULL
  *   states      device int8 [N, L] = argmax_k gamma (first maximum), may be NULL
  *   loglik      device double [N] = log P(read), may be NULL
+ *   workspace   optional device scratch of smf_hmm_workspace_bytes(SMF_OP_POSTERIOR, ...) bytes.
+ *               That size is non-zero for large batches of K >= 3 single-channel models: with it
+ *               the library runs the two-kernel path (per-read boundary walk + local sweeps,
+ *               DESIGN.md section 4) which is faster there.  NULL always works (single-kernel path);
+ *               a non-NULL workspace smaller than required is SMF_ERR_WORKSPACE.
  */
 int smf_hmm_posterior(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int64_t n_reads,
                       int64_t n_pos, const int8_t* bins, float* gamma, int gamma_state,
-                      int8_t* states, double* loglik, void* stream);
+                      int8_t* states, double* loglik, void* workspace, size_t workspace_bytes,
+                      void* stream);
 
 /*
  * Viterbi decode.  Replaces BaseHMM._viterbi (HMM.py:631-671; binned 2190-2236).

@@ -9,7 +9,7 @@ K, N, L = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 dev = torch.device("cuda", 0)
 m = bench.make_model(K, dev); t = m._host_tables()
 obs = bench.device_reads(N, L, K, False, 1, dev)
-ws = engine.estep_workspace(t, dev)
+ws = engine.estep_workspace(t, dev, N, L)
 for _ in range(4):
     s = engine.estep(t, obs, None, workspace=ws)
 torch.cuda.synchronize()

@@ -27,6 +27,7 @@ MAX_STATES, MAX_CHANNELS, MAX_BINS = 4, 4, 16
 
 EXPORTS = (
     "smf_hmm_abi_version",
+    "smf_hmm_set_option",
     "smf_hmm_strerror",
     "smf_hmm_workspace_bytes",
     "smf_hmm_max_positions",
@@ -91,6 +92,9 @@ def library_built() -> bool:
     return os.path.isfile(LIB_PATH)
 
 
+ABI_VERSION = 2
+
+
 def load():
     """Load libsmfhmm.so (once).  Raises if it has not been built -- there is no fallback."""
     global _lib
@@ -107,6 +111,8 @@ def load():
     lib.smf_hmm_abi_version.argtypes = []
     lib.smf_hmm_strerror.restype = c_char_p
     lib.smf_hmm_strerror.argtypes = [c_int]
+    lib.smf_hmm_set_option.restype = c_int
+    lib.smf_hmm_set_option.argtypes = [c_char_p, c_int]
     lib.smf_hmm_workspace_bytes.restype = c_size_t
     lib.smf_hmm_workspace_bytes.argtypes = [c_int, T, c_int64, c_int64]
     lib.smf_hmm_max_positions.restype = c_int64
@@ -115,7 +121,7 @@ def load():
     lib.smf_hmm_stats_len.argtypes = [T]
     lib.smf_hmm_posterior.restype = c_int
     lib.smf_hmm_posterior.argtypes = [T, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int,
-                                      c_void_p, c_void_p, c_void_p]
+                                      c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.smf_hmm_viterbi.restype = c_int
     lib.smf_hmm_viterbi.argtypes = [T, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                     c_size_t, c_void_p]
@@ -133,7 +139,7 @@ def load():
     lib.smf_hmm_span_mask.restype = c_int
     lib.smf_hmm_span_mask.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p,
                                       c_void_p]
-    if lib.smf_hmm_abi_version() != 1:
+    if lib.smf_hmm_abi_version() != ABI_VERSION:
         raise RuntimeError("libsmfhmm.so ABI version mismatch; rebuild the extension")
     _lib = lib
     return lib

@@ -10,6 +10,8 @@
 #include "features_kernel.cuh"
 #include "launch.h"
 #include "smf_hmm.h"
+#include "sweep_kernel.cuh"
+#include "walk_kernel.cuh"
 
 namespace smf {
 
@@ -58,6 +60,11 @@ static int check_tables(const smf_hmm_tables* t) {
   if (!t->log_start || !t->log_trans || !t->log_emit1 || !t->log_emit0) return SMF_ERR_BAD_ARG;
   return SMF_OK;
 }
+
+// two-kernel path selection: -1 = measured policy (walk_eligible), 0 = never, 1 = whenever possible.
+// Initialised from SMF_FB2_WALK, changed at run time with smf_hmm_set_option("walk", v).
+static int g_walk_mode = [] { const char* e = getenv("SMF_FB2_WALK"); return e ? atoi(e) : -1; }();
+static int rescale_cadence(const smf_hmm_tables* t);
 
 static int fb_max_threads(int K, bool stats) { return fb_max_threads_c(K, stats); }
 static int fb2_max_threads(int K, bool stats) { return fb2_max_threads_c(K, stats); }
@@ -156,6 +163,7 @@ static int plan_fb(int K, int C, int nb, int64_t L64, bool stats, int S, int max
 // ---------------------------------------------------------------------------------------
 // Resident reads per SM for a candidate layout: shared memory (228 KB per SM, 1 KB reserved per CTA),
 // registers (64 K per SM) and the 32-CTA limit.
+constexpr int kWalkChunkDefault = 17;
 static int fb2_resident(int total_smem, int block, int groups, int regs) {
   const int by_smem = (228 * 1024) / (total_smem + 1024);
   const int by_regs = 65536 / (regs * block);
@@ -165,16 +173,17 @@ static int fb2_resident(int total_smem, int block, int groups, int regs) {
 }
 
 static int plan_fb2_chunk(int K, int CH, int64_t L64, bool stats, int S, int es, bool want_gamma_one,
-                          bool want_states, int max_smem, Fb2Args* a, Fb2Plan* plan) {
+                          bool want_states, int max_smem, Fb2Args* a, Fb2Plan* plan, bool walk = false) {
   if (L64 < 1) return SMF_ERR_TOO_LONG;
   if (L64 > (int64_t)CH * 1024) return SMF_ERR_TOO_LONG;
   const int L = (int)L64;
   const int Tact = (L + CH - 1) / CH;
   const int T = align_up(Tact, 32);
-  if (T > fb2_max_threads(K, stats)) return SMF_ERR_TOO_LONG;
+  if (T > (walk ? fb2w_max_threads_c(K, stats) : fb2_max_threads(K, stats))) return SMF_ERR_TOO_LONG;
   const int Lpad = Tact * CH;
   const int KK = K * K;
-  const int regs = ((stats && K >= 3) || K == 4) ? 128 : 96;  // registers/thread of the instantiation (ptxas)
+  // registers/thread of the instantiation (ptxas)
+  const int regs = walk ? (stats ? 128 : 96) : (((stats && K >= 3) || K == 4) ? 128 : 96);
   const int bar_b = 16;
   const int in_b = align_up((Lpad + 16) * es + 16, 16);
   const int stage_b = align_up((Lpad * K + 4) * 4, 16);
@@ -225,6 +234,7 @@ static int plan_fb2_chunk(int K, int CH, int64_t L64, bool stats, int S, int es,
         a->alias_in = alias ? 1 : 0;
         a->obuf_bytes = obuf_b;
         a->T = T;
+        a->Tact = Tact;
         a->groups = gr;
         plan->block = T * gr;
         plan->smem = total;
@@ -238,12 +248,21 @@ static int plan_fb2_chunk(int K, int CH, int64_t L64, bool stats, int S, int es,
 
 // chunk 17 whenever the read fits its thread budget; chunk 33 (K = 2, 4) for reads up to twice as long
 static int plan_fb2(int K, int64_t L64, bool stats, int S, int es, bool want_gamma_one, bool want_states,
-                    int max_smem, Fb2Args* a, Fb2Plan* plan) {
+                    int max_smem, Fb2Args* a, Fb2Plan* plan, bool walk = false) {
   // Measured on B200 (profiles/r01_chunk_sweep.txt): for K = 2 posterior decode the longer chunk wins
   // whenever it keeps the lanes about as busy (half the scan / barrier overhead per position outweighs
   // the halved warp count); for K = 4 (register pressure) and for the E-step (more live registers)
   // chunk 17 is faster.  SMF_FB2_CHUNK overrides.
   static const int env_ch = [] { const char* e = getenv("SMF_FB2_CHUNK"); return e ? atoi(e) : 0; }();
+  if (walk) {
+    // two-kernel path: no chunk matrices, so the chunk length only trades lane utilisation and
+    // boundary-vector traffic against registers
+    const int first = (env_ch == 17 || env_ch == 33) ? env_ch : kWalkChunkDefault;
+    const int second = first == 33 ? 17 : 33;
+    if (plan_fb2_chunk(K, first, L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan, true) == SMF_OK)
+      return SMF_OK;
+    return plan_fb2_chunk(K, second, L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan, true);
+  }
   const bool can33 = (K != 3);
   // lane utilisation of the two chunk lengths (threads are allocated in whole warps)
   auto lane_eff = [&](int ch) {
@@ -260,6 +279,62 @@ static int plan_fb2(int K, int64_t L64, bool stats, int S, int es, bool want_gam
   if (can33 && plan_fb2_chunk(K, 33, L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan) == SMF_OK)
     return SMF_OK;
   return SMF_ERR_TOO_LONG;
+}
+
+// ---------------------------------------------------------------------------------------
+// two-kernel path (K >= 3): walk_kernel (boundary vectors, log-likelihood) + fb2_kernel<WALK>
+// ---------------------------------------------------------------------------------------
+constexpr int64_t kWalkMinReads = 8192;  // below this the sequential walk has too little parallelism
+
+// Measured on B200 (profiles/r01_walk.txt): the extra pass over the observations pays off where the
+// single-kernel path is FMA/register bound -- K = 4 E-steps at every length (x1.2 at 500 positions,
+// x3 at 8 kb where the single kernel has left its chunk-17 range), K = 4 posterior decode up to
+// ~6 kb (x2 at 170 positions, x1.3 at 500, break-even near 8 kb), and K = 3 E-steps beyond the
+// chunk-17 reach (x1.3 at 10 kb).  K = 3 elsewhere is faster in one kernel.  SMF_FB2_WALK=0/1 or
+// smf_hmm_set_option("walk", 0/1) force it off/on.
+static bool walk_eligible(const smf_hmm_tables* t, int64_t N, int64_t L, bool stats) {
+  const int env_walk = g_walk_mode;
+  if (env_walk == 0 || g_force_generic) return false;
+  const int K = t->n_states;
+  if (K < 3 || t->n_channels != 1 || t->n_bins != 1) return false;
+  if (L < 2 || L > (1 << 24)) return false;
+  if (!stats && L > (int64_t)33 * fb2w_max_threads_c(K, false)) return false;
+  if (rescale_cadence(t) != 4) return false;
+  if (env_walk == 1) return true;
+  if (N < kWalkMinReads) return false;
+  if (stats) return K == 4 || L > (int64_t)17 * fb2_max_threads_c(K, true);
+  return K == 4 && L <= 6000;
+}
+// boundary vectors for the shorter chunk (an upper bound for the longer one) + per-read log-likelihoods
+static size_t walk_ws_bytes(int K, int64_t N, int64_t L) {
+  const size_t tact = (size_t)((L + 16) / 17);
+  return 2 * tact * (size_t)N * K * sizeof(float) + (size_t)N * sizeof(double);
+}
+
+static int launch_walk_path(bool stats, const smf_hmm_tables* t, int obs_dtype, Fb2Args& a, const Fb2Plan& plan,
+                            const DeviceInfo& di, void* ws, int* nblocks, cudaStream_t stream) {
+  const int K = t->n_states;
+  WalkArgs w;
+  w.obs = a.obs;
+  w.N = a.N;
+  w.L = a.L;
+  w.CH = plan.chunk;
+  w.Tact = a.Tact;
+  const size_t nb = (size_t)a.Tact * (size_t)a.N * K;
+  w.bnd_v = reinterpret_cast<float*>(ws);
+  w.bnd_w = w.bnd_v + nb;
+  double* ll = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 2 * ((size_t)((a.L + 16) / 17)) * (size_t)a.N * K * sizeof(float));
+  w.ll = stats ? ll : a.loglik;
+  int rc = (K == 3) ? launch_walk_k3(obs_dtype, t, w, stream) : launch_walk_k4(obs_dtype, t, w, stream);
+  if (rc != SMF_OK) return rc;
+  a.bnd_v = w.bnd_v;
+  a.bnd_w = w.bnd_w;
+  a.ll_in = ll;
+  const int out = (stats || obs_dtype != SMF_OBS_F32 || a.gamma == nullptr || a.states == nullptr)
+                      ? 2
+                      : (a.gamma_state < 0 ? 0 : 1);
+  return (K == 3) ? launch_fb2w_k3(plan.chunk, stats, obs_dtype, out, t, a, plan, di, nblocks, stream)
+                  : launch_fb2w_k4(plan.chunk, stats, obs_dtype, out, t, a, plan, di, nblocks, stream);
 }
 
 static int launch_fb2(bool stats, const smf_hmm_tables* t, int obs_dtype, Fb2Args& a, const Fb2Plan& plan,
@@ -378,6 +453,16 @@ const char* smf_hmm_strerror(int code) {
   return "unknown error";
 }
 
+int smf_hmm_set_option(const char* key, int value) {
+  if (key == nullptr) return SMF_ERR_BAD_ARG;
+  if (strcmp(key, "walk") == 0) {
+    if (value < -1 || value > 1) return SMF_ERR_BAD_ARG;
+    g_walk_mode = value;
+    return SMF_OK;
+  }
+  return SMF_ERR_BAD_ARG;
+}
+
 int64_t smf_hmm_stats_len(const smf_hmm_tables* tab) {
   if (check_tables(tab) != SMF_OK) return -1;
   return stats_len(tab);
@@ -387,9 +472,15 @@ size_t smf_hmm_workspace_bytes(int op, const smf_hmm_tables* tab, int64_t n_read
   if (n_reads < 0 || n_pos < 0) return 0;
   switch (op) {
     case SMF_OP_VITERBI: return (size_t)n_reads * (size_t)n_pos;
-    case SMF_OP_ESTEP:
+    case SMF_OP_ESTEP: {
       if (check_tables(tab) != SMF_OK) return 0;
-      return (size_t)kMaxEstepBlocks * (size_t)stats_len(tab) * sizeof(double);
+      size_t b = (size_t)kMaxEstepBlocks * (size_t)stats_len(tab) * sizeof(double);
+      if (walk_eligible(tab, n_reads, n_pos, true)) b += walk_ws_bytes(tab->n_states, n_reads, n_pos);
+      return b;
+    }
+    case SMF_OP_POSTERIOR:
+      if (check_tables(tab) != SMF_OK) return 0;
+      return walk_eligible(tab, n_reads, n_pos, false) ? walk_ws_bytes(tab->n_states, n_reads, n_pos) : 0;
     default: return 0;
   }
 }
@@ -416,7 +507,7 @@ int64_t smf_hmm_max_positions(const smf_hmm_tables* tab, int want_all_states) {
 
 int smf_hmm_posterior(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int64_t n_reads,
                       int64_t n_pos, const int8_t* bins, float* gamma, int gamma_state,
-                      int8_t* states, double* loglik, void* stream) {
+                      int8_t* states, double* loglik, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_tables(tab);
   if (rc != SMF_OK) return rc;
   if (n_reads < 0 || n_pos < 0) return SMF_ERR_BAD_ARG;
@@ -434,6 +525,25 @@ int smf_hmm_posterior(const smf_hmm_tables* tab, const void* obs, int obs_dtype,
     Fb2Args b;
     memset(&b, 0, sizeof(b));
     Fb2Plan p2;
+    // two-kernel path when the caller provided the boundary-vector workspace
+    if (workspace != nullptr && walk_eligible(tab, n_reads, n_pos, false)) {
+      if (workspace_bytes < walk_ws_bytes(tab->n_states, n_reads, n_pos)) return SMF_ERR_WORKSPACE;
+      if (plan_fb2(tab->n_states, n_pos, false, stats_len(tab), obs_elem_size(obs_dtype),
+                   gamma != nullptr && gamma_state >= 0, states != nullptr, di.max_smem_optin, &b, &p2,
+                   true) == SMF_OK) {
+        b.obs = obs;
+        b.N = n_reads;
+        b.L = (int)n_pos;
+        b.gamma = gamma;
+        b.gamma_state = gamma_state;
+        b.states = states;
+        b.loglik = loglik;
+        b.S = stats_len(tab);
+        b.flush_every = 1;
+        return launch_walk_path(false, tab, obs_dtype, b, p2, di, workspace, nullptr, (cudaStream_t)stream);
+      }
+      memset(&b, 0, sizeof(b));
+    }
     if (plan_fb2(tab->n_states, n_pos, false, stats_len(tab), obs_elem_size(obs_dtype),
                  gamma != nullptr && gamma_state >= 0, states != nullptr, di.max_smem_optin, &b, &p2) == SMF_OK) {
       b.obs = obs;
@@ -497,6 +607,45 @@ int smf_hmm_estep(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int
     Fb2Args b;
     memset(&b, 0, sizeof(b));
     Fb2Plan p2;
+    if (walk_eligible(tab, n_reads, n_pos, true)) {
+      // two-kernel path: boundary walk, then warp-independent sweeps
+      static const int env_sch = [] { const char* e = getenv("SMF_SWEEP_CHUNK"); return e ? atoi(e) : 0; }();
+      const int K = tab->n_states;
+      const int CH = (env_sch >= 17 && (env_sch & 1)) ? env_sch : 17;
+      char* wws = reinterpret_cast<char*>(workspace) + (size_t)kMaxEstepBlocks * (size_t)S * sizeof(double);
+      const size_t cap = (size_t)((n_pos + 16) / 17) * (size_t)n_reads * K;
+      WalkArgs w;
+      w.obs = obs;
+      w.N = n_reads;
+      w.L = (int)n_pos;
+      w.CH = CH;
+      w.Tact = (int)((n_pos + CH - 1) / CH);
+      w.bnd_v = reinterpret_cast<float*>(wws);
+      w.bnd_w = w.bnd_v + cap;
+      w.ll = reinterpret_cast<double*>(wws + 2 * cap * sizeof(float));
+      rc = (K == 3) ? launch_walk_k3(obs_dtype, tab, w, st) : launch_walk_k4(obs_dtype, tab, w, st);
+      if (rc != SMF_OK) return rc;
+      SweepArgs sa;
+      memset(&sa, 0, sizeof(sa));
+      sa.obs = obs;
+      sa.N = n_reads;
+      sa.L = (int)n_pos;
+      sa.CH = CH;
+      sa.Tact = w.Tact;
+      sa.slices = (w.Tact + 31) / 32;
+      sa.bnd_v = w.bnd_v;
+      sa.bnd_w = w.bnd_w;
+      sa.ll_in = w.ll;
+      sa.partials = reinterpret_cast<double*>(workspace);
+      sa.S = S;
+      sa.flush_every = 8;
+      int nb2 = kMaxEstepBlocks;
+      rc = (K == 3) ? launch_sweep_k3(obs_dtype, tab, sa, di, &nb2, st) : launch_sweep_k4(obs_dtype, tab, sa, di, &nb2, st);
+      if (rc != SMF_OK) return rc;
+      reduce_partials_kernel<<<(S + 127) / 128, 128, 0, st>>>(sa.partials, nb2, S, stats);
+      return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
+    }
+    memset(&b, 0, sizeof(b));
     if (plan_fb2(tab->n_states, n_pos, true, S, obs_elem_size(obs_dtype), false, false, di.max_smem_optin, &b,
                  &p2) == SMF_OK) {
       b.obs = obs;

@@ -41,6 +41,11 @@ struct Fb2Args {
   int group_bytes;
   // offsets inside a group region (all 16-byte aligned)
   int goff_bar, goff_in, goff_stage, goff_out1, goff_st, goff_scan;
+  // WALK variant: chunk boundary vectors from walk_kernel ([chunk][read][K]) and per-read log-likelihoods
+  const float* bnd_v;
+  const float* bnd_w;
+  const double* ll_in;
+  int Tact;  // chunks per read
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -127,7 +132,10 @@ __device__ __forceinline__ void store_row_bulk(void* dst, const void* src, uint3
 
 // OUT selects the output set at compile time: 0 = all-state posterior + states (decode),
 // 1 = single-state posterior + states (annotate), 2 = decided at run time from the pointers.
-template <int K, int CH, bool STATS, typename ObsT, int MAXT, int MINB, int OUT>
+//
+// WALK = true: the chunk boundary vectors come from walk_kernel (walk_kernel.cuh) instead of the
+// chunk-product + scan phases; the kernel is then just the load / local sweeps / store pipeline.
+template <int K, int CH, bool STATS, typename ObsT, int MAXT, int MINB, int OUT, bool WALK = false>
 __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__ FbTables<K> tab,
                                                    const __grid_constant__ Fb2Args a) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -202,7 +210,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
 #pragma unroll
     for (int i = 0; i < NXI; ++i) {
       const float r = warp_sum_f32(acc_xi[i]);
-      if (lane == 0) my[K + i] += (double)r;
+      if (lane == 0) my[K + i] += (double)r * (double)tab.Ap[(i / K) % K][i % K];
       acc_xi[i] = 0.0f;
     }
   };
@@ -210,7 +218,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
   const int t0 = gt * CH;
   const bool active = t0 < L;
   const bool first = (t0 == 0);
-  const bool want_ll = STATS || (a.loglik != nullptr);
+  const bool want_ll = !WALK && (STATS || (a.loglik != nullptr));
   const int gs = a.gamma_state;
   const bool w_gamma_all = !STATS && (OUT == 0 || (OUT == 2 && a.gamma != nullptr && gs < 0));
   const bool w_gamma_one = !STATS && (OUT == 1 || (OUT == 2 && a.gamma != nullptr && gs >= 0));
@@ -277,6 +285,19 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
     if (w_gamma_one) s_out1 += (reinterpret_cast<uintptr_t>(a.gamma + (size_t)n * L) & 15u) >> 2;
     if (w_states) s_st += reinterpret_cast<uintptr_t>(a.states + (size_t)n * L) & 15u;
 
+    float bvv[WALK ? K : 1], bww[WALK ? K : 1];
+    if (WALK) {
+      // boundary vectors of this thread's chunk (issued before waiting for the observations)
+      const bool has_v = active && !first;
+      const bool has_w = active && gt < a.Tact - 1;
+      const size_t boff = ((size_t)gt * (size_t)a.N + (size_t)n) * K;
+#pragma unroll
+      for (int k = 0; k < (WALK ? K : 1); ++k) {
+        bvv[k] = has_v ? __ldg(a.bnd_v + boff + k) : tab.pi2[k];
+        bww[k] = has_w ? __ldg(a.bnd_w + boff + k) : 1.0f;
+      }
+    }
+
     mbar_wait(mbar, (uint32_t)(iter & 1));
 
     // ---------------- phase 1: chunk -> registers, transfer-matrix product ----------------
@@ -301,6 +322,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
     float ll_sumo = 0.0f;
     int ll_cnt = 0;
     bool prev_obs0 = false;  // observation just before this chunk present? (E-step xi validity)
+    unsigned in_dep = 0;
     if (active) {
       if (STATS && !first) {
         const float op = obs_to_float<ObsT>(s_in[t0 - 1]);
@@ -333,6 +355,14 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
           c[k] = ex2_approx(m ? fmaf(o, tab.rdl[k][0], tab.rl0p[k]) : tab.rmiss[k]);
           if (!RECOMP) rt[RECOMP ? 0 : j][k - 1] = c[k];
         }
+        if (WALK) {
+          // Nothing consumes the observation before the barrier below when the ratios are
+          // recomputed later, and a barrier does not wait for shared-memory loads still in
+          // flight: the prefetch (async proxy) could overwrite the buffer under them.  Fold the
+          // values into a word that is tested before the barrier so the loads must have landed.
+          if (RECOMP) in_dep ^= __float_as_uint(o);
+          continue;
+        }
         if (j == 0) {
           // P = I so far: P <- Ap diag(c), or diag(c) for the first position of the read
 #pragma unroll
@@ -354,6 +384,21 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
         if ((j & 3) == 3 || j == CH - 1) mat_scale<K>(P, pow2_rescale_noexp(mat_max<K>(P)));
       }
     }
+
+    float v[K], w[K];
+    if constexpr (WALK) {
+      if (RECOMP && in_dep == 0x7fa5a5a5u) __nanosleep(1);  // (never-taken in practice) consumer of the loads
+      if (G > 1) group_sync(bar_id, T); else __syncwarp();  // B1: chunk registers loaded by everyone
+      if (gt == 0 && !a.alias_in) {
+        const long long nn = n + read_stride;
+        if (nn < a.N) issue_load(nn);
+      }
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        v[k] = bvv[k];
+        w[k] = bww[k];
+      }
+    } else {
 
     // ---------------- phase 2: warp-shuffle scans of the chunk matrices ----------------
     // Kogge-Stone over the 32 lanes, inclusive prefix (pre) and suffix (suf); branch-free, with a
@@ -500,7 +545,6 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
       }
     }
 
-    float v[K], w[K];
     {
       float vo[K], wo[K];
 #pragma unroll
@@ -524,6 +568,9 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
         if (lane == 0) v[k] = u[k];
         if (lane == 31) w[k] = z[k];
       }
+    }
+    }  // !WALK
+    {
       float sv = v[0], sw = w[0];
 #pragma unroll
       for (int k = 1; k < K; ++k) {
@@ -700,14 +747,12 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
 #pragma unroll
             for (int i = 0; i < K; ++i) s2 = fmaf(alp[i], nb[i], s2);
             const float r2 = valid ? rcp_approx(s2) : 0.0f;
+            // the constant factor Ap[i][jj] is applied once per flush (flush_stats)
 #pragma unroll
             for (int i = 0; i < K; ++i) {
               const float ai = alp[i] * r2;
 #pragma unroll
-              for (int jj = 0; jj < K; ++jj) {
-                const float pij = (i == jj) ? cb[jj] : A[i][jj] * cb[jj];
-                acc_xi[i * K + jj] = fmaf(ai, pij, acc_xi[i * K + jj]);
-              }
+              for (int jj = 0; jj < K; ++jj) acc_xi[i * K + jj] = fmaf(ai, cb[jj], acc_xi[i * K + jj]);
             }
           }
           if ((((CH - 1) - j) & 3) == 3) {
@@ -723,7 +768,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
       }
     }
 
-    if (STATS) acc_ll += ll_thread;
+    if (STATS) acc_ll += (WALK ? ((active && first) ? a.ll_in[n] : 0.0) : ll_thread);
 
     // ---------------- store: every warp bulk-stores its own slice (no CTA barrier) ----------------
     if (!STATS) {
@@ -738,7 +783,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
       }
       if (lane == 0) bulk_commit();  // one group per iteration (possibly empty) keeps the counts aligned
     }
-    if (a.loglik != nullptr) {
+    if (!WALK && a.loglik != nullptr) {
       const double wsum = warp_sum_f64(ll_thread);
       if (lane == 0) s_ll[gw] = wsum;
       group_sync(bar_id, T);

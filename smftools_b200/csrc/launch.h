@@ -34,6 +34,9 @@ constexpr int fb2_max_threads_c(int K, bool stats) {
   return stats ? (K == 2 ? 640 : (K == 3 ? 512 : 480)) : (K == 4 ? 512 : 640);
 }
 
+// WALK variant (no chunk matrices live): launch bounds of fb2_kernel<..., WALK = true>
+constexpr int fb2w_max_threads_c(int K, bool stats) { return stats ? 512 : 640; }
+
 template <int K>
 static void build_fb_tables(const smf_hmm_tables* t, FbTables<K>* out) {
   memset(out, 0, sizeof(*out));
@@ -115,6 +118,17 @@ SMF_DECLARE_K(2)
 SMF_DECLARE_K(3)
 SMF_DECLARE_K(4)
 #undef SMF_DECLARE_K
+struct WalkArgs;
+struct SweepArgs;
+#define SMF_DECLARE_WK(KV)                                                                                   \
+  int launch_walk_k##KV(int obs_dtype, const smf_hmm_tables* t, const WalkArgs& a, cudaStream_t s);         \
+  int launch_sweep_k##KV(int obs_dtype, const smf_hmm_tables* t, SweepArgs& a, const DeviceInfo& di,        \
+                         int* nblocks, cudaStream_t s);                                                     \
+  int launch_fb2w_k##KV(int chunk, bool stats, int obs_dtype, int out_mode, const smf_hmm_tables* t,       \
+                        Fb2Args& a, const Fb2Plan& plan, const DeviceInfo& di, int* nblocks, cudaStream_t s);
+SMF_DECLARE_WK(3)
+SMF_DECLARE_WK(4)
+#undef SMF_DECLARE_WK
 
 static inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
 

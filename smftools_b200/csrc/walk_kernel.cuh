@@ -1,0 +1,217 @@
+// Boundary-walk kernel of the two-kernel forward-backward path (K >= 3).
+//
+// For K >= 3 the chunk-product + matrix-scan phases of fb2_kernel cost ~K^3 FMAs per position and a
+// K x K register matrix per thread; the E-step variant additionally carries K^2 + 3K accumulators
+// and spills.  With >= ~10^4 reads per launch there is enough read-level parallelism to get the
+// chunk boundary vectors the cheap way instead: ONE THREAD PER READ AND DIRECTION walks the read
+// sequentially (K(K-1) FMAs per position, scaled fp32, the same column-normalised tables as
+// fb2_kernel) and records
+//     v_i = alpha just before chunk i            (forward CTAs, blockIdx.y == 0; chunk 0 starts from pi2)
+//     w_i = beta at the last position of chunk i (backward CTAs, blockIdx.y == 1; the last chunk ends in 1)
+// chunk-major ([i][n][K]: coalesced across the reads of a warp), plus the read's log-likelihood.
+// fb2_kernel<..., WALK = true> then only runs its thread-local sweeps from those vectors: no chunk
+// matrices, no scans, no cross-warp hand-off.  Observations are staged through shared memory like in
+// viterbi_kernel (coalesced 128-byte row segments, one tile prefetched into registers, odd row
+// stride).  Cost: one extra forward and one extra backward read of the observations (2 x 4 B per
+// position for fp32 input) and 2 * 8K / CH bytes per position of boundary vectors (written + read).
+#pragma once
+#include "hmm_common.cuh"
+#include "viterbi_kernel.cuh"
+
+namespace smf {
+
+struct WalkArgs {
+  const void* obs;
+  long long N;
+  int L;
+  int CH;         // chunk length of the consumer kernel
+  int Tact;       // chunks per read = ceil(L / CH)
+  float* bnd_v;   // [Tact][N][K]
+  float* bnd_w;   // [Tact][N][K]
+  double* ll;     // [N] log-likelihood per read (may be nullptr)
+};
+
+template <int K, int OBSK>
+__global__ void __launch_bounds__(kVitReads, 6) walk_kernel(const __grid_constant__ FbTables<K> tab,
+                                                            const __grid_constant__ WalkArgs a) {
+  using src_t = typename std::conditional<OBSK == SMF_OBS_F64, double,
+                                          typename std::conditional<OBSK == SMF_OBS_U8, unsigned char, float>::type>::type;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int L = a.L;
+  constexpr int row_stride = kVitTile | 1;
+  float* tile = reinterpret_cast<float*>(smem);
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int wbase = (tid >> 5) * 32;
+  const long long n0 = (long long)blockIdx.x * kVitReads;
+  const int nrows = (int)min((long long)kVitReads, a.N - n0);
+  const bool live = tid < nrows;
+  const long long n = n0 + tid;
+  const size_t bstride = (size_t)a.N * K;  // floats between consecutive chunks
+  const bool backward = (blockIdx.y != 0);
+  // rows of this warp that exist; rows beyond are clamped to the last valid one (loads stay in bounds,
+  // the values are never used)
+  const int rows_w = max(0, min(32, nrows - wbase));
+
+  float A[K][K];
+#pragma unroll
+  for (int i = 0; i < K; ++i)
+#pragma unroll
+    for (int j = 0; j < K; ++j) A[i][j] = tab.Ap[i][j];
+
+  float nxt[32];
+  const src_t* wsrc = reinterpret_cast<const src_t*>(a.obs) + (n0 + wbase) * (long long)L;
+  auto fetch_tile = [&](int tile0) {
+    if (rows_w == 0) return;
+    const int col = min(tile0 + lane, L - 1);  // clamped: columns past the end are never consumed
+    const src_t* p = wsrc + col;
+    if (rows_w == 32) {
+#pragma unroll
+      for (int r = 0; r < 32; ++r) nxt[r] = obs_to_float<src_t>(__ldg(p + (size_t)r * L));
+    } else {
+#pragma unroll
+      for (int r = 0; r < 32; ++r) nxt[r] = obs_to_float<src_t>(__ldg(p + (size_t)min(r, rows_w - 1) * L));
+    }
+  };
+  auto commit_tile = [&]() {
+#pragma unroll
+    for (int r = 0; r < 32; ++r) tile[(wbase + r) * row_stride + lane] = nxt[r];
+  };
+  auto ratios = [&](float o, float (&c)[K]) {
+    const bool m = (o == o);
+#pragma unroll
+    for (int k = 1; k < K; ++k) c[k] = ex2_approx(m ? fmaf(o, tab.rdl[k][0], tab.rl0p[k]) : tab.rmiss[k]);
+    return m;
+  };
+  const int ntiles = (L + kVitTile - 1) / kVitTile;
+  const float* my = tile + tid * row_stride;
+
+  if (!backward) {
+    // ---------------- forward walk ----------------
+    float al[K];
+    {
+      float s = 0.0f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) s += tab.pi2[k];
+      const float r = 1.0f / s;
+#pragma unroll
+      for (int k = 0; k < K; ++k) al[k] = tab.pi2[k] * r;
+    }
+    int e = 0;          // power-of-two exponent taken out of alpha so far
+    int cnt = 0;        // observed positions
+    double sumo = 0.0;  // sum of observed values (state-0 emission mass)
+    int next_emit = a.CH - 1;  // v_{chunk_i} = alpha after this position
+    int chunk_i = 1;
+    float* dstv = a.bnd_v + bstride + (size_t)n * K;
+    fetch_tile(0);
+    for (int ti = 0; ti < ntiles; ++ti) {
+      const int tile0 = ti * kVitTile;
+      const int tw = min(kVitTile, L - tile0);
+      __syncthreads();
+      commit_tile();
+      __syncthreads();
+      if (ti + 1 < ntiles) fetch_tile(tile0 + kVitTile);
+      if (live) {
+        float tsum = 0.0f;  // per-tile partial of sumo (<= 32 terms in fp32, then fp64)
+#pragma unroll 4
+        for (int j = 0; j < tw; ++j) {
+          const int t = tile0 + j;
+          const float o = my[j];
+          float c[K];
+          const bool m = ratios(o, c);
+          cnt += m ? 1 : 0;
+          tsum += m ? o : 0.0f;
+          float y[K];
+#pragma unroll
+          for (int jj = 0; jj < K; ++jj) {
+            float s = al[jj];
+#pragma unroll
+            for (int i = 0; i < K; ++i)
+              if (i != jj) s = fmaf(al[i], A[i][jj], s);
+            y[jj] = (t == 0) ? al[jj] : s;  // alpha_0 = pi2 * c: no transition
+          }
+#pragma unroll
+          for (int k = 1; k < K; ++k) y[k] *= c[k];
+          if ((t & 3) == 3) {
+            const float sc = pow2_rescale(vec_max<K>(y), e);
+#pragma unroll
+            for (int k = 0; k < K; ++k) y[k] *= sc;
+          }
+#pragma unroll
+          for (int k = 0; k < K; ++k) al[k] = y[k];
+          if (t == next_emit) {
+            if (chunk_i < a.Tact) {
+#pragma unroll
+              for (int k = 0; k < K; ++k) dstv[k] = al[k];
+            }
+            ++chunk_i;
+            dstv += bstride;
+            next_emit += a.CH;
+          }
+        }
+        sumo += (double)tsum;
+      }
+    }
+    if (live && a.ll != nullptr) {
+      float s = al[0];
+#pragma unroll
+      for (int k = 1; k < K; ++k) s += al[k];
+      a.ll[n] = (double)logf(s) + (double)e * 0.6931471805599453094 + tab.log_pi2_sum + (double)cnt * tab.l00[0] +
+                sumo * tab.dl0[0] + (double)(L - 1) * tab.log_s0;
+    }
+  } else {
+    // ---------------- backward walk ----------------
+    float bv[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) bv[k] = 1.0f / K;
+    int wi = a.Tact - 1;       // next boundary to record is w_{wi-1} ...
+    int wpos = wi * a.CH - 1;  // ... = beta at the last position of chunk wi-1
+    float* dstw = a.bnd_w + (size_t)(wi > 0 ? wi - 1 : 0) * bstride + (size_t)n * K;
+    fetch_tile((ntiles - 1) * kVitTile);
+    for (int ti = ntiles - 1; ti >= 0; --ti) {
+      const int tile0 = ti * kVitTile;
+      const int tw = min(kVitTile, L - tile0);
+      __syncthreads();
+      commit_tile();
+      __syncthreads();
+      if (ti > 0) fetch_tile(tile0 - kVitTile);
+      if (live) {
+#pragma unroll 4
+        for (int j = tw - 1; j >= 0; --j) {
+          const int t = tile0 + j;
+          if (t == wpos) {  // bv == beta_t
+#pragma unroll
+            for (int k = 0; k < K; ++k) dstw[k] = bv[k];
+            dstw -= bstride;
+            wpos -= a.CH;
+          }
+          const float o = my[j];
+          float c[K];
+          ratios(o, c);
+          float cb[K], nb[K];
+          cb[0] = bv[0];
+#pragma unroll
+          for (int k = 1; k < K; ++k) cb[k] = c[k] * bv[k];
+#pragma unroll
+          for (int i = 0; i < K; ++i) {
+            float s = cb[i];
+#pragma unroll
+            for (int jj = 0; jj < K; ++jj)
+              if (jj != i) s = fmaf(A[i][jj], cb[jj], s);
+            nb[i] = s;
+          }
+          if ((t & 3) == 0) {
+            const float sc = pow2_rescale_noexp(vec_max<K>(nb));
+#pragma unroll
+            for (int k = 0; k < K; ++k) nb[k] *= sc;
+          }
+#pragma unroll
+          for (int k = 0; k < K; ++k) bv[k] = nb[k];
+        }
+      }
+    }
+  }
+}
+
+}  // namespace smf

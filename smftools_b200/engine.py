@@ -62,6 +62,11 @@ def _bins_arg(bins: Optional[torch.Tensor], tables: _lib.HostTables, L: int) -> 
     return int(bins.data_ptr())
 
 
+def set_option(key: str, value: int) -> None:
+    """Process-wide tuning knob of the library (``smf_hmm_set_option``), e.g. ``set_option("walk", 1)``."""
+    _lib.check(_lib.load().smf_hmm_set_option(key.encode(), int(value)), "smf_hmm_set_option")
+
+
 def max_positions(tables: _lib.HostTables) -> int:
     return int(_lib.load().smf_hmm_max_positions(tables.ref, 1))
 
@@ -77,8 +82,15 @@ def posterior(
     want_loglik: bool = False,
     out_gamma: Optional[torch.Tensor] = None,
     out_states: Optional[torch.Tensor] = None,
+    workspace: Optional[torch.Tensor] = None,
+    use_workspace: bool = True,
 ):
-    """Posterior decode (``smf_hmm_posterior``): returns (gamma, states, loglik), any may be None."""
+    """Posterior decode (``smf_hmm_posterior``): returns (gamma, states, loglik), any may be None.
+
+    ``workspace`` (uint8 device tensor) is only used by the two-kernel path the library picks for
+    large K >= 3 batches; it is allocated here when the library asks for one and none is passed
+    (``use_workspace=False`` withholds it, which selects the single-kernel path).
+    """
     lib = _lib.load()
     N, L, dt = _obs_args(obs, tables)
     dev = obs.device
@@ -95,9 +107,14 @@ def posterior(
             raise ValueError("out_states has the wrong shape / dtype")
     if want_loglik:
         ll = torch.empty((N,), dtype=torch.float64, device=dev)
+    need = int(lib.smf_hmm_workspace_bytes(_lib.OP_POSTERIOR, tables.ref, N, L)) if use_workspace else 0
+    if need > 0 and (workspace is None or workspace.numel() * workspace.element_size() < need):
+        workspace = torch.empty((need,), dtype=torch.uint8, device=dev)
+    ws_bytes = workspace.numel() * workspace.element_size() if (need > 0 and workspace is not None) else 0
     with torch.cuda.device(dev):
         rc = lib.smf_hmm_posterior(tables.ref, _ptr(obs), dt, N, L, _bins_arg(bins, tables, L), _ptr(gamma),
-                                   int(gamma_state), _ptr(states), _ptr(ll), _stream_ptr(dev))
+                                   int(gamma_state), _ptr(states), _ptr(ll),
+                                   _ptr(workspace) if ws_bytes else None, ws_bytes, _stream_ptr(dev))
     _lib.check(rc, "smf_hmm_posterior")
     return gamma, states, ll
 
@@ -141,8 +158,10 @@ def estep(tables: _lib.HostTables, obs: torch.Tensor, bins: Optional[torch.Tenso
     return stats
 
 
-def estep_workspace(tables: _lib.HostTables, device) -> torch.Tensor:
-    need = int(_lib.load().smf_hmm_workspace_bytes(_lib.OP_ESTEP, tables.ref, 1, 1))
+def estep_workspace(tables: _lib.HostTables, device, n_reads: int = 1, n_pos: int = 1) -> torch.Tensor:
+    """E-step scratch for batches of up to ``n_reads`` x ``n_pos`` (per-CTA partial statistics, plus the
+    boundary vectors of the two-kernel path when the library would pick it for that batch shape)."""
+    need = int(_lib.load().smf_hmm_workspace_bytes(_lib.OP_ESTEP, tables.ref, int(n_reads), int(n_pos)))
     return torch.empty((max(need // 8, 1),), dtype=torch.float64, device=device)
 
 

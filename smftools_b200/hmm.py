@@ -682,7 +682,9 @@ class BaseHMM(nn.Module):
         for it in range(1, int(max_iter) + 1):
             tables = self._host_tables()
             if workspace is None:
-                workspace = engine.estep_workspace(tables, device)
+                # sized for the largest resident chunk (includes the two-kernel path's boundary vectors)
+                workspace = engine.estep_workspace(tables, device, getattr(resident, "max_rows", None) or max(
+                    (int(o.shape[0]) for o in resident), default=1), L)
             total = self._estep_local(tables, resident, bins, workspace, device)
             total = self._allreduce_stats(total)
             stats = total.cpu()
@@ -722,6 +724,8 @@ class BaseHMM(nn.Module):
             return [self._to_device(src[lo:hi], device) for lo, hi in bounds]
 
         class _Streamed:
+            max_rows = max(hi - lo for lo, hi in bounds)
+
             def __iter__(inner):
                 for lo, hi in bounds:
                     yield self._to_device(src[lo:hi], device)

@@ -29,7 +29,7 @@ def _oracle_estep_patch(model, X_local, coords):
     model._resident_chunks = lambda src, device: [src]
     import smftools_b200.hmm as H
 
-    H.engine.estep_workspace = lambda tables, device: torch.zeros(1, dtype=torch.float64)
+    H.engine.estep_workspace = lambda tables, device, n_reads=1, n_pos=1: torch.zeros(1, dtype=torch.float64)
 
 
 def _worker(rank, world, port, arch, q):

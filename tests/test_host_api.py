@@ -171,7 +171,7 @@ def test_c_abi_exports_every_declared_symbol():
     for name in sorted(declared):
         assert getattr(lib, name) is not None
     lib = _lib.load()
-    assert lib.smf_hmm_abi_version() == 1
+    assert lib.smf_hmm_abi_version() == _lib.ABI_VERSION
     assert b"too long" in lib.smf_hmm_strerror(_lib.SMF_ERR_TOO_LONG)
     # argument validation happens before any CUDA call
     m = S.create_hmm({"hmm_n_states": 4}, arch="single_distance_binned")
@@ -182,7 +182,7 @@ def test_c_abi_exports_every_declared_symbol():
     assert lib.smf_hmm_max_positions(t.ref, 1) > 5000
     bad = _lib.HostTables(np.zeros(5), np.zeros((1, 5, 5)), np.zeros((5, 1)), np.zeros((5, 1)))
     assert lib.smf_hmm_stats_len(bad.ref) == -1
-    assert lib.smf_hmm_posterior(bad.ref, None, 0, 1, 1, None, None, -1, None, None, None) == _lib.SMF_ERR_BAD_ARG
+    assert lib.smf_hmm_posterior(bad.ref, None, 0, 1, 1, None, None, -1, None, None, None, 0, None) == _lib.SMF_ERR_BAD_ARG
     with pytest.raises(ValueError):
         _lib.check(_lib.SMF_ERR_BAD_ARG, "x")
     with pytest.raises(RuntimeError):
