@@ -178,6 +178,26 @@ int smf_hmm_merge_runs(const uint8_t* layer, int64_t n_reads, int64_t n_grid,
                        int32_t* len_cls, void* stream);
 
 /*
+ * Fused merge chain: what tools/partitioned_hmm.py:78-108 (_apply_merges) does to one aggregate
+ * feature layer -- merge_intervals_to_new_layer (HMM.py:1006-1067), write_size_class_layers_from_binary
+ * on the merged layer (HMM.py:1069-1123) and mask_layers_outside_read_span (HMM.py:148-231) over all
+ * layers of the chain -- in ONE pass over the layer, with a packed result the caller expands lazily:
+ *   code_out  uint8 [N, V]: bits 0-3 = size class of the merged run + 1 (0 = no class matched),
+ *             0x40 = cell belongs to a merged run, 0x80 = cell inside the read span (not NaN-masked)
+ *   run_len   int32 [N, V]: length of the merged run in grid columns, 0 outside runs
+ * so that  {layer}_merged = (code & 0x40) != 0,  its _lengths = run_len,  class layer c =
+ * (code & 15) == c + 1,  its _lengths = run_len there, and every layer is NaN where (code & 0x80) == 0.
+ * Read span: `covered` uint8 [N, V] (non-zero = keep) when given, else a cell is kept iff
+ * int(read_start[n]) <= span_coords[v] <= int(read_end[n]) (all kept when either bound is not finite).
+ * n_classes <= 15.
+ */
+int smf_hmm_merge_chain(const uint8_t* layer, int64_t n_reads, int64_t n_grid, const int64_t* coords,
+                        int coords_are_ints, int64_t distance_threshold, const double* class_lo_host,
+                        const double* class_hi_host, int n_classes, const uint8_t* covered,
+                        const int64_t* span_coords, const double* read_start, const double* read_end,
+                        uint8_t* code_out, int32_t* run_len, void* stream);
+
+/*
  * Read-span masking.  Replaces mask_layers_outside_read_span (HMM.py:148-231):
  *   valid_out[n,v] = covered[n,v] != 0                          (covered != NULL)
  *                  = !(coords[v] < start[n] || coords[v] > end[n])  (non-finite start/end => all valid)

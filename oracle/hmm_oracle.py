@@ -435,6 +435,27 @@ def span_valid(coords, starts, ends, covered=None):
     return valid
 
 
+def merge_chain(layer, coords, distance_threshold, ranges, valid, coords_are_ints=True):
+    """The per-layer body of ``_apply_merges`` (tools/partitioned_hmm.py:78-108): merge_runs ->
+    size_classes_from_binary on the merged layer -> NaN outside ``valid`` (span_valid) on every layer.
+
+    Returns float64 arrays in the reference's creation order:
+    [merged, merged_lengths, class_0, class_0_lengths, class_1, ...]."""
+    merged, mlen = merge_runs(layer, coords, distance_threshold, coords_are_ints)
+    out = [merged, mlen]
+    if len(ranges):
+        cl, cll = size_classes_from_binary(merged, coords, ranges, coords_are_ints)
+        for c in range(len(ranges)):
+            out.extend([cl[c], cll[c]])
+    res = []
+    drop = ~np.asarray(valid, dtype=bool)
+    for a in out:
+        f = np.asarray(a).astype(np.float64)
+        f[drop] = np.nan
+        res.append(f)
+    return res
+
+
 # --------------------------------------------------------------------------------------
 # synthetic SMF-like data (SURVEY.md 8d) -- shared by tests, smoke() and bench.py
 # --------------------------------------------------------------------------------------

@@ -137,6 +137,28 @@ def case_annotate(H, name, K, decode, seed, N=10, L=70, prob=False, with_covered
     for nm in [merged, merged + "_lengths"] + created:
         out[f"merge__{nm}"] = np.asarray(ad.layers[nm])
     out["merge_names"] = np.array([merged, merged + "_lengths"] + created)
+    # the complete _apply_merges chain (tools/partitioned_hmm.py:78-108) for the default merge pairs
+    # (config/default.yaml hmm_merge_layer_features): merge -> size classes -> read-span NaN mask
+    chain = []
+    for core, dist in (("all_footprint_features", 10), ("all_accessible_features", 60)):
+        base = f"GpC_{core}"
+        if base not in ad.layers:
+            continue
+        mb = model.merge_intervals_to_new_layer(ad, base, distance_threshold=dist, suffix="_merged", overwrite=True)
+        masked = [mb, f"{mb}_lengths"]
+        ranges = {}
+        for gname, fs in fsets.items():
+            if core == f"all_{gname}_features":
+                ranges = fs.get("features", {}) or {}
+        if ranges:
+            masked.extend(model.write_size_class_layers_from_binary(
+                ad, mb, out_prefix="GpC", feature_ranges=ranges, suffix="_merged", overwrite=True))
+        H.mask_layers_outside_read_span(ad, masked, use_original_var_names=True)
+        chain.extend(masked)
+    for nm in chain:
+        out[f"chain__{nm}"] = np.asarray(ad.layers[nm])
+    out["chain_names"] = np.array(chain)
+    out["chain_appended"] = np.array(list(ad.uns["hmm_appended_layers"]))
     np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **out)
     print(name, len(appended), "layers", {str(np.asarray(ad.layers[a]).dtype) for a in appended})
 

@@ -37,6 +37,7 @@ EXPORTS = (
     "smf_hmm_estep",
     "smf_hmm_call_features",
     "smf_hmm_merge_runs",
+    "smf_hmm_merge_chain",
     "smf_hmm_span_mask",
 )
 
@@ -136,6 +137,10 @@ def load():
     lib.smf_hmm_merge_runs.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_int, c_int64, c_void_p,
                                        c_void_p, POINTER(c_double), POINTER(c_double), c_int, c_void_p,
                                        c_void_p, c_void_p]
+    lib.smf_hmm_merge_chain.restype = c_int
+    lib.smf_hmm_merge_chain.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_int, c_int64, POINTER(c_double),
+                                        POINTER(c_double), c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p]
     lib.smf_hmm_span_mask.restype = c_int
     lib.smf_hmm_span_mask.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p,
                                       c_void_p]

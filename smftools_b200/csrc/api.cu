@@ -802,8 +802,7 @@ int smf_hmm_merge_runs(const uint8_t* layer, int64_t n_reads, int64_t n_grid,
   DeviceInfo di;
   rc = get_device_info(&di);
   if (rc != SMF_OK) return rc;
-  const int maxruns = ((int)n_grid + 1) / 2 + 1;
-  const size_t smem = (size_t)maxruns * 16 + (2 * kFeatWarps + 2) * 4 + (size_t)align_up(maxruns, 16);
+  const size_t smem = (size_t)(((int)n_grid + 31) / 32) * 20;  // five word arrays (bit masks + word scans)
   if ((long long)smem > di.max_smem_optin) return SMF_ERR_TOO_LONG;
   if (cudaFuncSetAttribute(merge_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
       cudaSuccess)
@@ -813,6 +812,7 @@ int smf_hmm_merge_runs(const uint8_t* layer, int64_t n_reads, int64_t n_grid,
           cudaSuccess || occ < 1)
     return SMF_ERR_CUDA;
   MergeArgs a;
+  memset(&a, 0, sizeof(a));
   a.layer = layer;
   a.N = n_reads;
   a.V = (int)n_grid;
@@ -823,6 +823,53 @@ int smf_hmm_merge_runs(const uint8_t* layer, int64_t n_reads, int64_t n_grid,
   a.merged_len = merged_len;
   a.class_out = (n_classes > 0) ? class_out : nullptr;
   a.len_cls = (n_classes > 0) ? len_cls : nullptr;
+  long long cap = (long long)di.num_sms * occ;
+  const int nblocks = (int)(n_reads < cap ? n_reads : cap);
+  merge_runs_kernel<<<nblocks, kFeatThreads, smem, (cudaStream_t)stream>>>(ct, a);
+  return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
+}
+
+int smf_hmm_merge_chain(const uint8_t* layer, int64_t n_reads, int64_t n_grid, const int64_t* coords,
+                        int coords_are_ints, int64_t distance_threshold, const double* class_lo_host,
+                        const double* class_hi_host, int n_classes, const uint8_t* covered,
+                        const int64_t* span_coords, const double* read_start, const double* read_end,
+                        uint8_t* code_out, int32_t* run_len, void* stream) {
+  if (n_reads < 0 || n_grid < 0) return SMF_ERR_BAD_ARG;
+  if (n_reads == 0 || n_grid == 0) return SMF_OK;
+  if (!layer || !code_out || !run_len) return SMF_ERR_BAD_ARG;
+  if (coords_are_ints && !coords) return SMF_ERR_BAD_ARG;
+  if (!covered && (!span_coords || !read_start || !read_end)) return SMF_ERR_BAD_ARG;
+  if (n_classes > 15) return SMF_ERR_BAD_ARG;  // four code bits
+  if (n_grid > 0x3fffffff) return SMF_ERR_TOO_LONG;
+  ClassTable ct;
+  int rc = fill_class_table(class_lo_host, class_hi_host, n_classes, &ct);
+  if (rc != SMF_OK) return rc;
+  DeviceInfo di;
+  rc = get_device_info(&di);
+  if (rc != SMF_OK) return rc;
+  const size_t smem = (size_t)(((int)n_grid + 31) / 32) * 20;  // five word arrays (bit masks + word scans)
+  if ((long long)smem > di.max_smem_optin) return SMF_ERR_TOO_LONG;
+  if (cudaFuncSetAttribute(merge_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+      cudaSuccess)
+    return SMF_ERR_CUDA;
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, merge_runs_kernel, kFeatThreads, smem) !=
+          cudaSuccess || occ < 1)
+    return SMF_ERR_CUDA;
+  MergeArgs a;
+  memset(&a, 0, sizeof(a));
+  a.layer = layer;
+  a.N = n_reads;
+  a.V = (int)n_grid;
+  a.coords = reinterpret_cast<const long long*>(coords);
+  a.coords_are_ints = coords_are_ints;
+  a.dt = distance_threshold;
+  a.merged_len = run_len;
+  a.packed = code_out;
+  a.covered = covered;
+  a.span_coords = reinterpret_cast<const long long*>(span_coords);
+  a.read_start = read_start;
+  a.read_end = read_end;
   long long cap = (long long)di.num_sms * occ;
   const int nblocks = (int)(n_reads < cap ? n_reads : cap);
   merge_runs_kernel<<<nblocks, kFeatThreads, smem, (cudaStream_t)stream>>>(ct, a);

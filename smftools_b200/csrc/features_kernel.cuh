@@ -239,97 +239,230 @@ struct MergeArgs {
   int* merged_len;     // [N, V]
   uint8_t* class_out;  // [N, V] or nullptr
   int* len_cls;        // [N, V] or nullptr
+  // fused chain (smf_hmm_merge_chain): one packed code byte per cell instead of merged/class_out/len_cls
+  //   bits 0-3 size class + 1 (0 = none) | 0x40 member of a merged run | 0x80 inside the read span
+  uint8_t* packed;              // [N, V] or nullptr
+  const uint8_t* covered;       // [N, V] or nullptr: explicit coverage mask (HMM.py:193-204)
+  const long long* span_coords; // [V] coordinates compared against the read span (HMM.py:178-191)
+  const double* read_start;     // [N]
+  const double* read_end;       // [N]
 };
 
-// merge_intervals_to_new_layer + write_size_class_layers_from_binary (HMM.py:1006-1123).
+constexpr uint8_t kCodeMember = 0x40;
+constexpr uint8_t kCodeValid = 0x80;
+
+// ---------------------------------------------------------------------------------------
+// merge_intervals_to_new_layer + write_size_class_layers_from_binary (HMM.py:1006-1123), optionally
+// fused with mask_layers_outside_read_span (HMM.py:148-231): the chain of tools/partitioned_hmm.py:78-108.
+//
+// One CTA per read; the row lives on chip as BIT MASKS (V/32 words, a few KB for any realistic grid),
+// so the kernel streams: 1 byte in, 1 + 4 (packed) bytes out per cell, no per-run tables.
+//   A. membership words   mem[w]  (byte loads + ballot)
+//   B. nxt[w] = first non-empty word >= w        (one warp, ballot scan over the words)
+//   C. every falling edge (last cell p of a run) finds the next run start s with bit operations and
+//      bridges the gap [p+1, s) into mrg[] iff its coordinate width <= the threshold.  The decision
+//      only involves the two neighbouring runs, exactly as in the reference's chain merge where the
+//      growing merged run always ends with the last run appended (HMM.py:1045-1057).
+//   D. pz[w] / nz[w] = nearest word at or below / above w that has a clear bit in mrg
+//   E. per cell: start / end of its merged run from clz / ffs on mrg (+ pz / nz across full words),
+//      size class from the coordinates of the run's first and last cell, read-span validity; each lane
+//      writes 4 consecutive cells (32-bit code store, 128-bit length store) when the row allows it.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int mc_run_start(const uint32_t* mrg, const int* pz, int v) {
+  const int w = v >> 5, b = v & 31;
+  const uint32_t zeros = ~mrg[w] & ((1u << b) - 1u);  // clear bits below b
+  if (zeros) return (w << 5) + (32 - __clz(zeros));
+  const int w2 = (w > 0) ? pz[w - 1] : -1;
+  if (w2 < 0) return 0;
+  return (w2 << 5) + (32 - __clz(~mrg[w2]));
+}
+__device__ __forceinline__ int mc_run_end(const uint32_t* mrg, const int* nz, int v, int V, int W) {
+  const int w = v >> 5, b = v & 31;
+  const uint32_t zeros = ~mrg[w] & ~((2u << b) - 1u);  // clear bits above b (b == 31: none)
+  if (zeros) return min((w << 5) + __ffs(zeros) - 1, V);
+  const int w2 = (w + 1 < W) ? nz[w + 1] : W;
+  if (w2 >= W) return V;
+  return min((w2 << 5) + __ffs(~mrg[w2]) - 1, V);
+}
+
 __global__ void __launch_bounds__(kFeatThreads) merge_runs_kernel(const __grid_constant__ ClassTable ct,
                                                                    const __grid_constant__ MergeArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const int maxruns = (a.V + 1) / 2 + 1;
-  int* rs = reinterpret_cast<int*>(smem);
-  int* re = rs + maxruns;
-  int* sgs = re + maxruns;   // segment start (grid) per run
-  int* sge = sgs + maxruns;  // segment end per run
-  int* s_cnt = sge + maxruns;
-  int8_t* rcls = reinterpret_cast<int8_t*>(s_cnt + 2 * kFeatWarps + 2);
-  const int tid = threadIdx.x;
+  const int V = a.V;
+  const int W = (V + 31) >> 5;
+  uint32_t* mem = reinterpret_cast<uint32_t*>(smem);  // [W]
+  uint32_t* mrg = mem + W;                            // [W]
+  int* nxt = reinterpret_cast<int*>(mrg + W);         // [W]
+  int* pz = nxt + W;                                  // [W]
+  int* nz = pz + W;                                   // [W]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool want_cls = (a.class_out != nullptr) || (a.packed != nullptr && ct.n > 0);
+  const bool vec_ok = ((V & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.merged_len) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(a.packed) & 3) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(a.merged) & 3) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(a.class_out) & 3) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(a.len_cls) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(a.covered) & 3) == 0);
 
   for (long long n = blockIdx.x; n < a.N; n += gridDim.x) {
-    const uint8_t* row = a.layer + n * (long long)a.V;
-    auto pred = [&](int v) -> bool { return __ldg(row + v) != 0; };
-    const int R = enumerate_runs(pred, a.V, rs, re, s_cnt);
-    // Sequential chain merge (gap measured against the growing merged run, HMM.py:1045-1057).
-    // One warp walks the runs 32 at a time: a run starts a new segment iff its gap > dt.
-    if (tid < 32) {
-      int seg_first = 0;  // index of the first run of the open segment
-      for (int r0 = 0; r0 < R; r0 += 32) {
-        const int r = r0 + tid;
-        bool starts = false;
-        if (r < R) {
-          if (r == 0) {
-            starts = true;
-          } else {
-            const long long gap = a.coords_are_ints
-                                      ? (__ldg(a.coords + rs[r]) - __ldg(a.coords + re[r - 1] - 1) - 1)
-                                      : (long long)(rs[r] - re[r - 1]);
-            starts = gap > a.dt;
+    const uint8_t* row = a.layer + n * (long long)V;
+    // ---- A: membership bit masks
+    for (int w = warp; w < W; w += kFeatWarps) {
+      const int v = (w << 5) + lane;
+      const bool mbit = (v < V) && (__ldg(row + v) != 0);
+      const uint32_t word = __ballot_sync(0xffffffffu, mbit);
+      if (lane == 0) {
+        mem[w] = word;
+        mrg[w] = word;
+      }
+    }
+    __syncthreads();
+    // ---- B: next non-empty word (suffix scan by one warp)
+    if (warp == 0) {
+      int carry = W;
+      for (int base = ((W - 1) >> 5) << 5; base >= 0; base -= 32) {
+        const int w = base + lane;
+        const bool f = (w < W) && (mem[w] != 0u);
+        const uint32_t bal = __ballot_sync(0xffffffffu, f);
+        const uint32_t up = bal >> lane;
+        if (w < W) nxt[w] = up ? (w + __ffs(up) - 1) : carry;
+        if (bal) carry = base + __ffs(bal) - 1;
+      }
+    }
+    __syncthreads();
+    // ---- C: bridge the gaps that are narrow enough
+    for (int w = tid; w < W; w += kFeatThreads) {
+      const uint32_t m = mem[w];
+      if (m == 0u) continue;
+      const uint32_t nb0 = (w + 1 < W) ? (mem[w + 1] & 1u) : 0u;
+      uint32_t fall = m & ~((m >> 1) | (nb0 << 31));  // last cell of every run ending in this word
+      while (fall) {
+        const int b = __ffs(fall) - 1;
+        fall &= fall - 1u;
+        const int p = (w << 5) + b;
+        const uint32_t rest = (b == 31) ? 0u : (m & ~((2u << b) - 1u));
+        int s;
+        if (rest) {
+          s = (w << 5) + __ffs(rest) - 1;
+        } else {
+          const int w2 = (w + 1 < W) ? nxt[w + 1] : W;
+          if (w2 >= W) continue;  // trailing zeros: no later run
+          s = (w2 << 5) + __ffs(mem[w2]) - 1;
+        }
+        const long long gap = a.coords_are_ints ? (__ldg(a.coords + s) - __ldg(a.coords + p) - 1)
+                                                : (long long)(s - p - 1);
+        if (gap > a.dt) continue;
+        // set bits (p, s) in mrg
+        const int f0 = p + 1, l0 = s - 1;
+        if (f0 > l0) continue;
+        const int wf = f0 >> 5, wl = l0 >> 5;
+        for (int ww = wf; ww <= wl; ++ww) {
+          uint32_t bits = 0xffffffffu;
+          if (ww == wf) bits &= ~((1u << (f0 & 31)) - 1u);
+          if (ww == wl) bits &= ((l0 & 31) == 31) ? 0xffffffffu : ((2u << (l0 & 31)) - 1u);
+          atomicOr(&mrg[ww], bits);
+        }
+      }
+    }
+    __syncthreads();
+    // ---- D: nearest word with a clear bit, below (pz) and above (nz)
+    if (warp == 0) {
+      int carry = -1;
+      for (int base = 0; base < W; base += 32) {
+        const int w = base + lane;
+        const bool f = (w < W) && (mrg[w] != 0xffffffffu);
+        const uint32_t bal = __ballot_sync(0xffffffffu, f);
+        const uint32_t dn = bal & (0xffffffffu >> (31 - lane));
+        if (w < W) pz[w] = dn ? (base + 31 - __clz(dn)) : carry;
+        if (bal) carry = base + 31 - __clz(bal);
+      }
+    } else if (warp == 1) {
+      int carry = W;
+      for (int base = ((W - 1) >> 5) << 5; base >= 0; base -= 32) {
+        const int w = base + lane;
+        const bool f = (w < W) && (mrg[w] != 0xffffffffu);
+        const uint32_t bal = __ballot_sync(0xffffffffu, f);
+        const uint32_t up = bal >> lane;
+        if (w < W) nz[w] = up ? (w + __ffs(up) - 1) : carry;
+        if (bal) carry = base + __ffs(bal) - 1;
+      }
+    }
+    __syncthreads();
+    // ---- E: outputs
+    bool all_valid = false;
+    long long sp = 0, ep = 0;
+    if (a.packed != nullptr && a.covered == nullptr) {
+      const double ds = a.read_start[n], de = a.read_end[n];
+      if (!isfinite(ds) || !isfinite(de)) {
+        all_valid = true;
+      } else {
+        sp = (long long)ds;  // int(start): truncation toward zero (HMM.py:219-220)
+        ep = (long long)de;
+      }
+    }
+    const long long roff = n * (long long)V;
+    auto cell_valid = [&](int v) -> bool {
+      if (a.covered != nullptr) return __ldg(a.covered + roff + v) != 0;
+      if (all_valid) return true;
+      const long long c = __ldg(a.span_coords + v);
+      return !(c < sp || c > ep);
+    };
+    auto classify = [&](int S, int E) -> int {
+      if (!want_cls) return -1;
+      const double len_bp = a.coords_are_ints ? (double)(__ldg(a.coords + E - 1) - __ldg(a.coords + S) + 1)
+                                              : (double)(E - S);
+      return pick_class(ct, len_bp);
+    };
+    const int step = vec_ok ? 4 : 1;
+    for (int v0 = tid * step; v0 < V; v0 += kFeatThreads * step) {
+      const uint32_t bits = (mrg[v0 >> 5] >> (v0 & 31)) & (vec_ok ? 0xFu : 0x1u);
+      int curE = -1, curLen = 0, curCls = -1;
+      uint32_t code4 = 0, mem4 = 0, cls4 = 0;
+      int len4[4] = {0, 0, 0, 0};
+      int clen4[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k >= step) break;
+        const int v = v0 + k;
+        uint32_t code = 0;
+        if ((bits >> k) & 1u) {
+          if (v >= curE) {
+            const int S = mc_run_start(mrg, pz, v);
+            curE = mc_run_end(mrg, nz, v, V, W);
+            curLen = curE - S;
+            curCls = classify(S, curE);
+          }
+          len4[k] = curLen;
+          code = kCodeMember | (curCls >= 0 ? (uint32_t)(curCls + 1) : 0u);
+          mem4 |= 1u << (8 * k);
+          if (curCls >= 0) {
+            cls4 |= (uint32_t)(curCls + 1) << (8 * k);
+            clen4[k] = curLen;
           }
         }
-        const unsigned bsx = __ballot_sync(0xffffffffu, starts);
-        if (r < R) {
-          // first run of my segment: highest start flag at or below my lane, else carry-in
-          const unsigned le = bsx & (0xffffffffu >> (31 - tid));
-          const int f = le ? (r0 + 31 - __clz(le)) : seg_first;
-          sgs[r] = f;
+        if (a.packed != nullptr && cell_valid(v)) code |= kCodeValid;
+        code4 |= code << (8 * k);
+      }
+      if (vec_ok) {
+        *reinterpret_cast<int4*>(a.merged_len + roff + v0) = make_int4(len4[0], len4[1], len4[2], len4[3]);
+        if (a.packed != nullptr) {
+          *reinterpret_cast<uint32_t*>(a.packed + roff + v0) = code4;
+        } else {
+          *reinterpret_cast<uint32_t*>(a.merged + roff + v0) = mem4;
+          if (a.class_out) *reinterpret_cast<uint32_t*>(a.class_out + roff + v0) = cls4;
+          if (a.len_cls)
+            *reinterpret_cast<int4*>(a.len_cls + roff + v0) = make_int4(clen4[0], clen4[1], clen4[2], clen4[3]);
         }
-        if (bsx) seg_first = r0 + 31 - __clz(bsx);
+      } else {
+        a.merged_len[roff + v0] = len4[0];
+        if (a.packed != nullptr) {
+          a.packed[roff + v0] = (uint8_t)code4;
+        } else {
+          a.merged[roff + v0] = (uint8_t)mem4;
+          if (a.class_out) a.class_out[roff + v0] = (uint8_t)cls4;
+          if (a.len_cls) a.len_cls[roff + v0] = clen4[0];
+        }
       }
-    }
-    __syncthreads();
-    // sgs[r] = index of first run of r's segment.  Segment end: last run l with sgs[l] == sgs[r];
-    // found from the next segment's first run (scan forward over run indices in parallel).
-    for (int r = tid; r < R; r += kFeatThreads) {
-      // binary search the first run index whose segment-first exceeds mine
-      const int f = sgs[r];
-      int lo = r + 1, hi = R;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (sgs[mid] > f) hi = mid; else lo = mid + 1;
-      }
-      sge[r] = re[lo - 1];
-    }
-    __syncthreads();
-    for (int r = tid; r < R; r += kFeatThreads) {
-      const int S = rs[sgs[r]], E = sge[r];
-      int cls = -1;
-      if (a.class_out != nullptr) {
-        const double len_bp = a.coords_are_ints
-                                  ? (double)(__ldg(a.coords + E - 1) - __ldg(a.coords + S) + 1)
-                                  : (double)(E - S);
-        cls = pick_class(ct, len_bp);
-      }
-      rcls[r] = (int8_t)cls;
-    }
-    __syncthreads();
-    for (int r = tid; r < R; r += kFeatThreads) sgs[r] = rs[sgs[r]];  // now the grid start
-    __syncthreads();
-    uint8_t* mrow = a.merged + n * (long long)a.V;
-    int* lrow = a.merged_len + n * (long long)a.V;
-    uint8_t* crow = a.class_out ? a.class_out + n * (long long)a.V : nullptr;
-    int* clrow = a.len_cls ? a.len_cls + n * (long long)a.V : nullptr;
-    for (int v = tid; v < a.V; v += kFeatThreads) {
-      const int r = find_run(rs, R, v);
-      uint8_t m = 0, c = 0;
-      int len = 0;
-      if (r >= 0 && v < sge[r]) {  // inside r's merged segment (run cell or joined gap)
-        m = 1;
-        len = sge[r] - sgs[r];
-        if (rcls[r] >= 0) c = (uint8_t)(rcls[r] + 1);
-      }
-      mrow[v] = m;
-      lrow[v] = len;
-      if (crow) crow[v] = c;
-      if (clrow) clrow[v] = c ? len : 0;
     }
     __syncthreads();
   }

@@ -228,6 +228,10 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 2) estep_sweep_kernel(const 
     }
 #pragma unroll 2
     for (int j = len - 1; j >= 0; --j) {
+      // gamma only feeds the emission statistics here: fold the "observed" mask into its normaliser
+      const float o = obs_to_float<ObsT>(s_in[j]);
+      const bool m = (o == o);
+      const float om = m ? o : 0.0f;
       float gk[K];
       float gs = 0.0f;
 #pragma unroll
@@ -235,9 +239,13 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 2) estep_sweep_kernel(const 
         gk[k] = alc[k] * bv[k];
         gs += gk[k];
       }
-      const float gr = rcp_approx(gs);
+      const float gr = m ? rcp_approx(gs) : 0.0f;
 #pragma unroll
-      for (int k = 0; k < K; ++k) gk[k] *= gr;
+      for (int k = 0; k < K; ++k) {
+        const float g = gk[k] * gr;
+        acc_num[k] = fmaf(g, om, acc_num[k]);
+        acc_den[k] += g;
+      }
       float alp[K];
       if (j > 0) {
         if (K == 4) {
@@ -258,14 +266,12 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 2) estep_sweep_kernel(const 
 #pragma unroll
         for (int k = 0; k < K; ++k) alp[k] = v[k];
       }
-      const float o = obs_to_float<ObsT>(s_in[j]);
-      const bool m = (o == o);
       const bool at_start = first && j == 0;
+      if (at_start) {
+        // gamma_0 of the read (start statistics, counted whether or not position 0 is observed)
+        const float g0 = rcp_approx(gs);
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        acc_start[k] += at_start ? gk[k] : 0.0f;
-        acc_num[k] = fmaf(m ? gk[k] : 0.0f, m ? o : 0.0f, acc_num[k]);
-        acc_den[k] += m ? gk[k] : 0.0f;
+        for (int k = 0; k < K; ++k) acc_start[k] += gk[k] * g0;
       }
       float cr[K], cb[K], nb[K];
       ratios(o, cr);

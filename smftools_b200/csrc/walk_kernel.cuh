@@ -20,6 +20,10 @@
 
 namespace smf {
 
+constexpr int kWalkTile = 16;                 // positions per staged tile (one register per tile row and thread)
+constexpr int kWalkRowsPerLoad = 32 / kWalkTile;  // rows one warp-wide load covers
+constexpr int kWalkLoads = 32 / kWalkRowsPerLoad;  // loads per tile and thread
+
 struct WalkArgs {
   const void* obs;
   long long N;
@@ -32,13 +36,13 @@ struct WalkArgs {
 };
 
 template <int K, int OBSK>
-__global__ void __launch_bounds__(kVitReads, 6) walk_kernel(const __grid_constant__ FbTables<K> tab,
+__global__ void __launch_bounds__(kVitReads, (K >= 4 ? 7 : 8)) walk_kernel(const __grid_constant__ FbTables<K> tab,
                                                             const __grid_constant__ WalkArgs a) {
   using src_t = typename std::conditional<OBSK == SMF_OBS_F64, double,
                                           typename std::conditional<OBSK == SMF_OBS_U8, unsigned char, float>::type>::type;
   extern __shared__ __align__(16) unsigned char smem[];
   const int L = a.L;
-  constexpr int row_stride = kVitTile | 1;
+  constexpr int row_stride = kWalkTile | 1;
   float* tile = reinterpret_cast<float*>(smem);
 
   const int tid = threadIdx.x;
@@ -60,23 +64,27 @@ __global__ void __launch_bounds__(kVitReads, 6) walk_kernel(const __grid_constan
 #pragma unroll
     for (int j = 0; j < K; ++j) A[i][j] = tab.Ap[i][j];
 
-  float nxt[32];
+  float nxt[kWalkLoads];
   const src_t* wsrc = reinterpret_cast<const src_t*>(a.obs) + (n0 + wbase) * (long long)L;
+  const int lcol = lane % kWalkTile;  // column of the tile this lane fetches
+  const int lrow = lane / kWalkTile;  // row offset inside one warp-wide load
   auto fetch_tile = [&](int tile0) {
     if (rows_w == 0) return;
-    const int col = min(tile0 + lane, L - 1);  // clamped: columns past the end are never consumed
+    const int col = min(tile0 + lcol, L - 1);  // clamped: columns past the end are never consumed
     const src_t* p = wsrc + col;
     if (rows_w == 32) {
 #pragma unroll
-      for (int r = 0; r < 32; ++r) nxt[r] = obs_to_float<src_t>(__ldg(p + (size_t)r * L));
+      for (int r = 0; r < kWalkLoads; ++r)
+        nxt[r] = obs_to_float<src_t>(__ldg(p + (r * kWalkRowsPerLoad + lrow) * L));  // 32-bit offset: < 32 * 2^24
     } else {
 #pragma unroll
-      for (int r = 0; r < 32; ++r) nxt[r] = obs_to_float<src_t>(__ldg(p + (size_t)min(r, rows_w - 1) * L));
+      for (int r = 0; r < kWalkLoads; ++r)
+        nxt[r] = obs_to_float<src_t>(__ldg(p + min(r * kWalkRowsPerLoad + lrow, rows_w - 1) * L));
     }
   };
   auto commit_tile = [&]() {
 #pragma unroll
-    for (int r = 0; r < 32; ++r) tile[(wbase + r) * row_stride + lane] = nxt[r];
+    for (int r = 0; r < kWalkLoads; ++r) tile[(wbase + r * kWalkRowsPerLoad + lrow) * row_stride + lcol] = nxt[r];
   };
   auto ratios = [&](float o, float (&c)[K]) {
     const bool m = (o == o);
@@ -84,7 +92,7 @@ __global__ void __launch_bounds__(kVitReads, 6) walk_kernel(const __grid_constan
     for (int k = 1; k < K; ++k) c[k] = ex2_approx(m ? fmaf(o, tab.rdl[k][0], tab.rl0p[k]) : tab.rmiss[k]);
     return m;
   };
-  const int ntiles = (L + kVitTile - 1) / kVitTile;
+  const int ntiles = (L + kWalkTile - 1) / kWalkTile;
   const float* my = tile + tid * row_stride;
 
   if (!backward) {
@@ -106,12 +114,12 @@ __global__ void __launch_bounds__(kVitReads, 6) walk_kernel(const __grid_constan
     float* dstv = a.bnd_v + bstride + (size_t)n * K;
     fetch_tile(0);
     for (int ti = 0; ti < ntiles; ++ti) {
-      const int tile0 = ti * kVitTile;
-      const int tw = min(kVitTile, L - tile0);
+      const int tile0 = ti * kWalkTile;
+      const int tw = min(kWalkTile, L - tile0);
       __syncthreads();
       commit_tile();
       __syncthreads();
-      if (ti + 1 < ntiles) fetch_tile(tile0 + kVitTile);
+      if (ti + 1 < ntiles) fetch_tile(tile0 + kWalkTile);
       if (live) {
         float tsum = 0.0f;  // per-tile partial of sumo (<= 32 terms in fp32, then fp64)
 #pragma unroll 4
@@ -168,14 +176,14 @@ __global__ void __launch_bounds__(kVitReads, 6) walk_kernel(const __grid_constan
     int wi = a.Tact - 1;       // next boundary to record is w_{wi-1} ...
     int wpos = wi * a.CH - 1;  // ... = beta at the last position of chunk wi-1
     float* dstw = a.bnd_w + (size_t)(wi > 0 ? wi - 1 : 0) * bstride + (size_t)n * K;
-    fetch_tile((ntiles - 1) * kVitTile);
+    fetch_tile((ntiles - 1) * kWalkTile);
     for (int ti = ntiles - 1; ti >= 0; --ti) {
-      const int tile0 = ti * kVitTile;
-      const int tw = min(kVitTile, L - tile0);
+      const int tile0 = ti * kWalkTile;
+      const int tw = min(kWalkTile, L - tile0);
       __syncthreads();
       commit_tile();
       __syncthreads();
-      if (ti > 0) fetch_tile(tile0 - kVitTile);
+      if (ti > 0) fetch_tile(tile0 - kWalkTile);
       if (live) {
 #pragma unroll 4
         for (int j = tw - 1; j >= 0; --j) {

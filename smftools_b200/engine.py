@@ -258,6 +258,49 @@ def merge_runs(layer: torch.Tensor, coords: Optional[torch.Tensor], coords_are_i
     return merged, mlen, cls, clen
 
 
+def merge_chain(layer: torch.Tensor, coords: Optional[torch.Tensor], coords_are_ints: bool,
+                distance_threshold: int, ranges: Sequence[Tuple[float, float]] = (), *,
+                covered: Optional[torch.Tensor] = None, span_coords: Optional[torch.Tensor] = None,
+                start: Optional[torch.Tensor] = None, end: Optional[torch.Tensor] = None):
+    """Fused merge -> size classes -> read-span mask (``smf_hmm_merge_chain``).
+
+    Returns (code uint8, run_len int32), both [N, V]; see include/smf_hmm.h for the code bits.
+    """
+    lib = _lib.load()
+    _require_cuda(layer, "layer")
+    if layer.dtype != torch.uint8 or not layer.is_contiguous() or layer.dim() != 2:
+        raise ValueError("layer must be a contiguous uint8 [N, V] tensor")
+    N, V = layer.shape
+    dev = layer.device
+    if coords is not None:
+        _require_cuda(coords, "coords")
+        if coords.dtype != torch.int64 or coords.numel() != V or not coords.is_contiguous():
+            raise ValueError("coords must be contiguous int64 of length V")
+    if covered is not None:
+        _require_cuda(covered, "covered")
+        if covered.dtype != torch.uint8 or tuple(covered.shape) != (N, V) or not covered.is_contiguous():
+            raise ValueError("covered must be a contiguous uint8 [N, V] tensor")
+    else:
+        if span_coords is None or start is None or end is None:
+            raise ValueError("either covered or (span_coords, start, end) is required")
+        for t, nm, dt, n in ((span_coords, "span_coords", torch.int64, V), (start, "start", torch.float64, N),
+                             (end, "end", torch.float64, N)):
+            _require_cuda(t, nm)
+            if t.dtype != dt or t.numel() != n or not t.is_contiguous():
+                raise ValueError(f"{nm} has the wrong dtype / length")
+    lo, hi, plo, phi = _class_arrays(ranges)
+    if len(lo) > 15:
+        raise ValueError("at most 15 size classes fit the packed code")
+    code = torch.empty((N, V), dtype=torch.uint8, device=dev)
+    run_len = torch.empty((N, V), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.smf_hmm_merge_chain(_ptr(layer), N, V, _ptr(coords), int(bool(coords_are_ints)),
+                                     int(distance_threshold), plo, phi, len(lo), _ptr(covered), _ptr(span_coords),
+                                     _ptr(start), _ptr(end), _ptr(code), _ptr(run_len), _stream_ptr(dev))
+    _lib.check(rc, "smf_hmm_merge_chain")
+    return code, run_len
+
+
 def span_mask(n_reads: int, n_grid: int, device, *, covered: Optional[torch.Tensor] = None,
               coords: Optional[torch.Tensor] = None, start: Optional[torch.Tensor] = None,
               end: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -180,8 +180,9 @@ def _default_cuda_device() -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
-def _span_validity(adata, *, start_key: str, end_key: str, use_original_var_names: bool) -> np.ndarray:
-    """bool [n_obs, n_vars]: True where a layer value is kept (HMM.py:178-226)."""
+def _span_inputs(adata, *, start_key: str, end_key: str, use_original_var_names: bool, device):
+    """Device inputs of the read-span test (HMM.py:178-226): ``{"covered": u8 [N,V]}`` when the
+    coverage mask layer exists, else ``{"coords": i64 [V], "start": f64 [N], "end": f64 [N]}``."""
     coord_source = adata.var_names
     if use_original_var_names and "Original_var_names" in adata.var:
         orig = np.asarray(adata.var["Original_var_names"])
@@ -195,26 +196,29 @@ def _span_validity(adata, *, start_key: str, end_key: str, use_original_var_name
     coords, _ = _safe_int_coords(coord_source)
     if coords.shape[0] != adata.n_vars:
         raise ValueError("Coordinate source length does not match adata.n_vars.")
-
-    dev = _default_cuda_device()
     if COVERED_BASE_MASK in adata.layers:
         covered = np.asarray(adata.layers[COVERED_BASE_MASK], dtype=bool)
         if covered.shape != tuple(adata.shape):
             raise ValueError("covered_base_mask must match adata shape")
-        cov_d = torch.from_numpy(np.ascontiguousarray(covered).view(np.uint8)).to(dev)
-        valid = engine.span_mask(adata.n_obs, adata.n_vars, dev, covered=cov_d)
-    else:
-        try:
-            starts = np.asarray(adata.obs[start_key], dtype=float)
-            ends = np.asarray(adata.obs[end_key], dtype=float)
-        except (TypeError, ValueError) as exc:
-            raise ValueError("Start/end positions must be numeric.") from exc
-        valid = engine.span_mask(
-            adata.n_obs, adata.n_vars, dev,
-            coords=torch.from_numpy(np.array(coords, dtype=np.int64, copy=True)).to(dev),
-            start=torch.from_numpy(np.array(starts, dtype=np.float64, copy=True)).to(dev),
-            end=torch.from_numpy(np.array(ends, dtype=np.float64, copy=True)).to(dev),
-        )
+        return {"covered": torch.from_numpy(np.ascontiguousarray(covered).view(np.uint8)).to(device)}
+    try:
+        starts = np.asarray(adata.obs[start_key], dtype=float)
+        ends = np.asarray(adata.obs[end_key], dtype=float)
+    except (TypeError, ValueError) as exc:
+        raise ValueError("Start/end positions must be numeric.") from exc
+    return {
+        "coords": torch.from_numpy(np.array(coords, dtype=np.int64, copy=True)).to(device),
+        "start": torch.from_numpy(np.array(starts, dtype=np.float64, copy=True)).to(device),
+        "end": torch.from_numpy(np.array(ends, dtype=np.float64, copy=True)).to(device),
+    }
+
+
+def _span_validity(adata, *, start_key: str, end_key: str, use_original_var_names: bool) -> np.ndarray:
+    """bool [n_obs, n_vars]: True where a layer value is kept (HMM.py:178-226)."""
+    dev = _default_cuda_device()
+    inp = _span_inputs(adata, start_key=start_key, end_key=end_key,
+                       use_original_var_names=use_original_var_names, device=dev)
+    valid = engine.span_mask(adata.n_obs, adata.n_vars, dev, **inp)
     return valid.cpu().numpy().astype(bool)
 
 

@@ -117,6 +117,32 @@ def test_annotate_layers(name):
         np.testing.assert_array_equal(cll[ci], g[f"merge__GpC_{feat}_merged_lengths"])
 
 
+@pytest.mark.parametrize("name", golden_names("annotate"))
+def test_merge_chain_matches_reference_apply_merges(name):
+    """oracle merge_chain == merge -> size classes -> read-span mask as the reference runs them
+    (tools/partitioned_hmm.py:78-108) for both default merge pairs."""
+    g = load_golden(name)
+    full = g["full"]
+    valid = O.span_valid(full, g["starts"], g["ends"], covered=g["covered"] if "covered" in g else None)
+    groups = annotate_groups(g)
+    names = [str(n) for n in g["chain_names"]]
+    got = {}
+    for core, dist in (("all_footprint_features", 10), ("all_accessible_features", 60)):
+        base = g[f"layer__GpC_{core}"]
+        grp = core[len("all_"):-len("_features")]
+        feats = groups[grp][1]
+        arrs = O.merge_chain(base, full, dist, list(feats.values()), valid)
+        order = [f"GpC_{core}_merged", f"GpC_{core}_merged_lengths"]
+        for feat in feats:
+            order += [f"GpC_{feat}_merged", f"GpC_{feat}_merged_lengths"]
+        got.update(dict(zip(order, arrs)))
+    assert list(got) == names
+    for nm in names:
+        ref = g[f"chain__{nm}"]
+        assert ref.dtype == np.float64
+        np.testing.assert_array_equal(got[nm], ref, err_msg=nm)
+
+
 def test_known_answer_merge_from_reference_test():
     # tests/unit/test_hmm_partitioned_cli.py:217-248: two runs 10 bp apart on a 14-wide row merge
     row = np.zeros((1, 14), dtype=np.uint8)
