@@ -2,6 +2,7 @@
 // dispatch to the per-K launchers.  No torch, no allocation, no global state other than cached
 // device attributes.
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -421,6 +422,26 @@ static int stats_len(const smf_hmm_tables* t) {
   return K + t->n_bins * K * K + 2 * K * C + 1;
 }
 
+// Integer form of the size classes for integer lengths: lo <= len < hi  <=>  ceil(lo) <= len < ceil(hi).
+static void to_int_classes(const ClassTable& ct, IntClassTable* it) {
+  memset(it, 0, sizeof(*it));
+  it->n = ct.n;
+  auto cl = [](double x) -> long long {
+    if (x != x) return LLONG_MAX;  // NaN bound: never matches (lo) / never bounds (hi) like the comparison
+    if (x >= 9.2e18) return LLONG_MAX;
+    if (x <= -9.2e18) return LLONG_MIN;
+    return (long long)ceil(x);
+  };
+  for (int i = 0; i < ct.n; ++i) {
+    it->lo[i] = cl(ct.lo[i]);
+    it->hi[i] = cl(ct.hi[i]);
+    if (ct.lo[i] != ct.lo[i] || ct.hi[i] != ct.hi[i]) {  // NaN bounds compare false: class never matches
+      it->lo[i] = LLONG_MAX;
+      it->hi[i] = LLONG_MIN;
+    }
+  }
+}
+
 static int fill_class_table(const double* lo, const double* hi, int n, ClassTable* ct) {
   if (n < 0 || n > kMaxClasses) return SMF_ERR_BAD_ARG;
   if (n > 0 && (!lo || !hi)) return SMF_ERR_BAD_ARG;
@@ -802,13 +823,14 @@ int smf_hmm_merge_runs(const uint8_t* layer, int64_t n_reads, int64_t n_grid,
   DeviceInfo di;
   rc = get_device_info(&di);
   if (rc != SMF_OK) return rc;
-  const size_t smem = (size_t)(((int)n_grid + 31) / 32) * 20;  // five word arrays (bit masks + word scans)
+  // five word arrays (bit masks + word scans) + one staging tile per warp
+  const size_t smem = (size_t)(((((int)n_grid + 31) / 32) + 3) & ~3) * 20 + (size_t)kMcWarps * kMcTileBytes;
   if ((long long)smem > di.max_smem_optin) return SMF_ERR_TOO_LONG;
   if (cudaFuncSetAttribute(merge_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
       cudaSuccess)
     return SMF_ERR_CUDA;
   int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, merge_runs_kernel, kFeatThreads, smem) !=
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, merge_runs_kernel, kMcThreads, smem) !=
           cudaSuccess || occ < 1)
     return SMF_ERR_CUDA;
   MergeArgs a;
@@ -825,7 +847,9 @@ int smf_hmm_merge_runs(const uint8_t* layer, int64_t n_reads, int64_t n_grid,
   a.len_cls = (n_classes > 0) ? len_cls : nullptr;
   long long cap = (long long)di.num_sms * occ;
   const int nblocks = (int)(n_reads < cap ? n_reads : cap);
-  merge_runs_kernel<<<nblocks, kFeatThreads, smem, (cudaStream_t)stream>>>(ct, a);
+  IntClassTable ict;
+  to_int_classes(ct, &ict);
+  merge_runs_kernel<<<nblocks, kMcThreads, smem, (cudaStream_t)stream>>>(ict, a);
   return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
 }
 
@@ -847,13 +871,14 @@ int smf_hmm_merge_chain(const uint8_t* layer, int64_t n_reads, int64_t n_grid, c
   DeviceInfo di;
   rc = get_device_info(&di);
   if (rc != SMF_OK) return rc;
-  const size_t smem = (size_t)(((int)n_grid + 31) / 32) * 20;  // five word arrays (bit masks + word scans)
+  // five word arrays (bit masks + word scans) + one staging tile per warp
+  const size_t smem = (size_t)(((((int)n_grid + 31) / 32) + 3) & ~3) * 20 + (size_t)kMcWarps * kMcTileBytes;
   if ((long long)smem > di.max_smem_optin) return SMF_ERR_TOO_LONG;
   if (cudaFuncSetAttribute(merge_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
       cudaSuccess)
     return SMF_ERR_CUDA;
   int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, merge_runs_kernel, kFeatThreads, smem) !=
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, merge_runs_kernel, kMcThreads, smem) !=
           cudaSuccess || occ < 1)
     return SMF_ERR_CUDA;
   MergeArgs a;
@@ -872,7 +897,9 @@ int smf_hmm_merge_chain(const uint8_t* layer, int64_t n_reads, int64_t n_grid, c
   a.read_end = read_end;
   long long cap = (long long)di.num_sms * occ;
   const int nblocks = (int)(n_reads < cap ? n_reads : cap);
-  merge_runs_kernel<<<nblocks, kFeatThreads, smem, (cudaStream_t)stream>>>(ct, a);
+  IntClassTable ict;
+  to_int_classes(ct, &ict);
+  merge_runs_kernel<<<nblocks, kMcThreads, smem, (cudaStream_t)stream>>>(ict, a);
   return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
 }
 

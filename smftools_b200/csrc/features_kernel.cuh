@@ -257,17 +257,37 @@ constexpr uint8_t kCodeValid = 0x80;
 //
 // One CTA per read; the row lives on chip as BIT MASKS (V/32 words, a few KB for any realistic grid),
 // so the kernel streams: 1 byte in, 1 + 4 (packed) bytes out per cell, no per-run tables.
-//   A. membership words   mem[w]  (byte loads + ballot)
+//   A. membership words   mem[w]  (32-bit loads of 4 cells, nibbles OR-reduced over 8 lanes)
 //   B. nxt[w] = first non-empty word >= w        (one warp, ballot scan over the words)
 //   C. every falling edge (last cell p of a run) finds the next run start s with bit operations and
 //      bridges the gap [p+1, s) into mrg[] iff its coordinate width <= the threshold.  The decision
 //      only involves the two neighbouring runs, exactly as in the reference's chain merge where the
 //      growing merged run always ends with the last run appended (HMM.py:1045-1057).
 //   D. pz[w] / nz[w] = nearest word at or below / above w that has a clear bit in mrg
-//   E. per cell: start / end of its merged run from clz / ffs on mrg (+ pz / nz across full words),
-//      size class from the coordinates of the run's first and last cell, read-span validity; each lane
-//      writes 4 consecutive cells (32-bit code store, 128-bit length store) when the row allows it.
+//   E. ONE LANE PER WORD: the lane walks the (few) sub-runs of its 32 cells, gets the start / end of
+//      a run that crosses the word boundary from clz / ffs on mrg (+ pz / nz across full words), the
+//      size class from the coordinates of the run's first and last cell, the read-span validity as
+//      a 32-bit mask, and writes code bytes + run lengths into a per-warp staging tile (padded,
+//      conflict free); the warp then copies the tile out with coalesced 128-bit stores.
 // ---------------------------------------------------------------------------------------
+constexpr int kMcThreads = 128;  // threads per CTA of merge_runs_kernel
+constexpr int kMcWarps = kMcThreads / 32;
+constexpr int kMcCodeStride = 48;   // bytes per lane in the code tile (32 used)
+constexpr int kMcLenStride = 144;   // bytes per lane in the length tile (128 used)
+constexpr int kMcTileBytes = 32 * (kMcCodeStride + kMcLenStride);
+
+struct IntClassTable {
+  long long lo[kMaxClasses];  // ceil(lo): len >= lo  <=>  len >= ceil(lo) for integer len
+  long long hi[kMaxClasses];  // ceil(hi): len <  hi  <=>  len <  ceil(hi)
+  int n;
+};
+__device__ __forceinline__ int pick_class_int(const IntClassTable& ct, long long len) {
+  int cls = -1;
+  for (int c = ct.n - 1; c >= 0; --c)
+    if (ct.lo[c] <= len && len < ct.hi[c]) cls = c;
+  return cls;
+}
+
 __device__ __forceinline__ int mc_run_start(const uint32_t* mrg, const int* pz, int v) {
   const int w = v >> 5, b = v & 31;
   const uint32_t zeros = ~mrg[w] & ((1u << b) - 1u);  // clear bits below b
@@ -284,36 +304,119 @@ __device__ __forceinline__ int mc_run_end(const uint32_t* mrg, const int* nz, in
   if (w2 >= W) return V;
   return min((w2 << 5) + __ffs(~mrg[w2]) - 1, V);
 }
+// bits [lo, hi) of a 32-bit word, for any integers lo <= hi (clamped to the word)
+__device__ __forceinline__ uint32_t mc_range_mask(int lo, int hi) {
+  lo = max(lo, 0);
+  hi = min(hi, 32);
+  if (lo >= hi) return 0u;
+  const uint32_t upto_hi = (hi == 32) ? 0xffffffffu : ((1u << hi) - 1u);
+  return upto_hi & ~((1u << lo) - 1u);
+}
+// the four low bits of x spread to the low bit of four bytes
+__device__ __forceinline__ uint32_t mc_spread4(uint32_t x) { return ((x & 0xFu) * 0x00204081u) & 0x01010101u; }
 
-__global__ void __launch_bounds__(kFeatThreads) merge_runs_kernel(const __grid_constant__ ClassTable ct,
+__global__ void __launch_bounds__(kMcThreads) merge_runs_kernel(const __grid_constant__ IntClassTable ct,
                                                                    const __grid_constant__ MergeArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int V = a.V;
   const int W = (V + 31) >> 5;
-  uint32_t* mem = reinterpret_cast<uint32_t*>(smem);  // [W]
-  uint32_t* mrg = mem + W;                            // [W]
-  int* nxt = reinterpret_cast<int*>(mrg + W);         // [W]
-  int* pz = nxt + W;                                  // [W]
-  int* nz = pz + W;                                   // [W]
+  const int Wpad = (W + 3) & ~3;
+  uint32_t* mem = reinterpret_cast<uint32_t*>(smem);  // [Wpad]
+  uint32_t* mrg = mem + Wpad;                         // [Wpad]
+  int* nxt = reinterpret_cast<int*>(mrg + Wpad);      // [Wpad]
+  int* pz = nxt + Wpad;                               // [Wpad]
+  int* nz = pz + Wpad;                                // [Wpad]
+  __shared__ int s_cnt[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool want_cls = (a.class_out != nullptr) || (a.packed != nullptr && ct.n > 0);
-  const bool vec_ok = ((V & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.merged_len) & 15) == 0) &&
-                      ((reinterpret_cast<uintptr_t>(a.packed) & 3) == 0) &&
-                      ((reinterpret_cast<uintptr_t>(a.merged) & 3) == 0) &&
-                      ((reinterpret_cast<uintptr_t>(a.class_out) & 3) == 0) &&
-                      ((reinterpret_cast<uintptr_t>(a.len_cls) & 15) == 0) &&
-                      ((reinterpret_cast<uintptr_t>(a.covered) & 3) == 0);
+  unsigned char* tile = smem + (size_t)Wpad * 20 + (size_t)warp * kMcTileBytes;
+  unsigned char* tcode = tile;
+  unsigned char* tlen = tile + 32 * kMcCodeStride;
+  const bool want_cls = (ct.n > 0) && ((a.class_out != nullptr) || (a.packed != nullptr));
+  const bool packed = (a.packed != nullptr);
+  const bool in_vec = ((V & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.layer) & 3) == 0);
+  const bool out_vec = ((V & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.merged_len) & 15) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(a.packed) & 3) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(a.merged) & 3) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(a.class_out) & 3) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(a.len_cls) & 15) == 0);
+  const bool cov_vec = ((V & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.covered) & 3) == 0);
+
+  // Non-decreasing span coordinates (the normal case: genomic positions) turn the read-span test
+  // of a row into one column range; otherwise every cell is tested against its coordinate.
+  bool span_sorted = false;
+  if (packed && a.covered == nullptr) {
+    bool ok = true;
+    for (int v = tid + 1; v < V; v += kMcThreads) ok = ok && (__ldg(a.span_coords + v) >= __ldg(a.span_coords + v - 1));
+    span_sorted = __syncthreads_and(ok) != 0;
+  }
 
   for (long long n = blockIdx.x; n < a.N; n += gridDim.x) {
-    const uint8_t* row = a.layer + n * (long long)V;
+    const long long roff = n * (long long)V;
+    const uint8_t* row = a.layer + roff;
     // ---- A: membership bit masks
-    for (int w = warp; w < W; w += kFeatWarps) {
-      const int v = (w << 5) + lane;
-      const bool mbit = (v < V) && (__ldg(row + v) != 0);
-      const uint32_t word = __ballot_sync(0xffffffffu, mbit);
-      if (lane == 0) {
-        mem[w] = word;
-        mrg[w] = word;
+    if (in_vec) {
+      for (int base = warp * 128; base < V; base += kMcWarps * 128) {
+        const int v = base + lane * 4;
+        const uint32_t x = (v < V) ? __ldg(reinterpret_cast<const uint32_t*>(row + v)) : 0u;
+        const uint32_t ne = __vcmpne4(x, 0u);  // 0xff per non-zero byte
+        uint32_t word = ((ne & 0x01010101u) * 0x01020408u) >> 24;  // 4 cells -> nibble
+        word <<= 4 * (lane & 7);
+        word |= __shfl_xor_sync(0xffffffffu, word, 1);
+        word |= __shfl_xor_sync(0xffffffffu, word, 2);
+        word |= __shfl_xor_sync(0xffffffffu, word, 4);
+        const int w = (base >> 5) + (lane >> 3);
+        if ((lane & 7) == 0 && w < W) {
+          mem[w] = word;
+          mrg[w] = word;
+        }
+      }
+    } else {
+      for (int w = warp; w < W; w += kMcWarps) {
+        const int v = (w << 5) + lane;
+        const bool mbit = (v < V) && (__ldg(row + v) != 0);
+        const uint32_t word = __ballot_sync(0xffffffffu, mbit);
+        if (lane == 0) {
+          mem[w] = word;
+          mrg[w] = word;
+        }
+      }
+    }
+    // read-span column range of this row (sorted coordinates): two-level counting search
+    int vlo = 0, vhi = V;
+    bool all_valid = false;
+    long long sp = 0, ep = 0;
+    if (packed && a.covered == nullptr) {
+      const double ds = a.read_start[n], de = a.read_end[n];
+      if (!isfinite(ds) || !isfinite(de)) {
+        all_valid = true;
+      } else {
+        sp = (long long)ds;  // int(start): truncation toward zero (HMM.py:219-220)
+        ep = (long long)de;
+      }
+      if (span_sorted && !all_valid) {
+        // vlo = #cells with c < sp, vhi = #cells with c <= ep
+        const int seg = (V + kMcThreads - 1) / kMcThreads;
+        const int pos = min(tid * seg, V - 1);
+        const long long c0 = __ldg(a.span_coords + pos);
+        const int segs_lo = __syncthreads_count(tid * seg < V && c0 < sp);   // segments starting below sp
+        const int segs_hi = __syncthreads_count(tid * seg < V && c0 <= ep);
+        // the boundary lies inside segment segs-1 (if any): count inside it
+        const int blo = max(segs_lo - 1, 0) * seg, bhi = max(segs_hi - 1, 0) * seg;
+        int cl = 0, ch = 0;
+        for (int i = tid; i < seg; i += kMcThreads) {
+          if (blo + i < V && __ldg(a.span_coords + blo + i) < sp) ++cl;
+          if (bhi + i < V && __ldg(a.span_coords + bhi + i) <= ep) ++ch;
+        }
+        if (tid == 0) {
+          s_cnt[0] = 0;
+          s_cnt[1] = 0;
+        }
+        __syncthreads();
+        if (cl) atomicAdd(&s_cnt[0], cl);
+        if (ch) atomicAdd(&s_cnt[1], ch);
+        __syncthreads();
+        vlo = (segs_lo > 0) ? blo + s_cnt[0] : 0;
+        vhi = (segs_hi > 0) ? bhi + s_cnt[1] : 0;
       }
     }
     __syncthreads();
@@ -331,7 +434,7 @@ __global__ void __launch_bounds__(kFeatThreads) merge_runs_kernel(const __grid_c
     }
     __syncthreads();
     // ---- C: bridge the gaps that are narrow enough
-    for (int w = tid; w < W; w += kFeatThreads) {
+    for (int w = tid; w < W; w += kMcThreads) {
       const uint32_t m = mem[w];
       if (m == 0u) continue;
       const uint32_t nb0 = (w + 1 < W) ? (mem[w + 1] & 1u) : 0u;
@@ -352,16 +455,11 @@ __global__ void __launch_bounds__(kFeatThreads) merge_runs_kernel(const __grid_c
         const long long gap = a.coords_are_ints ? (__ldg(a.coords + s) - __ldg(a.coords + p) - 1)
                                                 : (long long)(s - p - 1);
         if (gap > a.dt) continue;
-        // set bits (p, s) in mrg
-        const int f0 = p + 1, l0 = s - 1;
+        const int f0 = p + 1, l0 = s - 1;  // set bits (p, s) in mrg
         if (f0 > l0) continue;
         const int wf = f0 >> 5, wl = l0 >> 5;
-        for (int ww = wf; ww <= wl; ++ww) {
-          uint32_t bits = 0xffffffffu;
-          if (ww == wf) bits &= ~((1u << (f0 & 31)) - 1u);
-          if (ww == wl) bits &= ((l0 & 31) == 31) ? 0xffffffffu : ((2u << (l0 & 31)) - 1u);
-          atomicOr(&mrg[ww], bits);
-        }
+        for (int ww = wf; ww <= wl; ++ww)
+          atomicOr(&mrg[ww], mc_range_mask(f0 - (ww << 5), l0 + 1 - (ww << 5)));
       }
     }
     __syncthreads();
@@ -388,81 +486,129 @@ __global__ void __launch_bounds__(kFeatThreads) merge_runs_kernel(const __grid_c
       }
     }
     __syncthreads();
-    // ---- E: outputs
-    bool all_valid = false;
-    long long sp = 0, ep = 0;
-    if (a.packed != nullptr && a.covered == nullptr) {
-      const double ds = a.read_start[n], de = a.read_end[n];
-      if (!isfinite(ds) || !isfinite(de)) {
-        all_valid = true;
-      } else {
-        sp = (long long)ds;  // int(start): truncation toward zero (HMM.py:219-220)
-        ep = (long long)de;
-      }
-    }
-    const long long roff = n * (long long)V;
-    auto cell_valid = [&](int v) -> bool {
-      if (a.covered != nullptr) return __ldg(a.covered + roff + v) != 0;
-      if (all_valid) return true;
-      const long long c = __ldg(a.span_coords + v);
-      return !(c < sp || c > ep);
-    };
-    auto classify = [&](int S, int E) -> int {
-      if (!want_cls) return -1;
-      const double len_bp = a.coords_are_ints ? (double)(__ldg(a.coords + E - 1) - __ldg(a.coords + S) + 1)
-                                              : (double)(E - S);
-      return pick_class(ct, len_bp);
-    };
-    const int step = vec_ok ? 4 : 1;
-    for (int v0 = tid * step; v0 < V; v0 += kFeatThreads * step) {
-      const uint32_t bits = (mrg[v0 >> 5] >> (v0 & 31)) & (vec_ok ? 0xFu : 0x1u);
-      int curE = -1, curLen = 0, curCls = -1;
-      uint32_t code4 = 0, mem4 = 0, cls4 = 0;
-      int len4[4] = {0, 0, 0, 0};
-      int clen4[4] = {0, 0, 0, 0};
+    // ---- E: one lane per word -> staging tile -> coalesced copy-out
+    for (int blk = warp; blk * 32 < W; blk += kMcWarps) {
+      const int w = blk * 32 + lane;
+      const int c0 = w << 5;  // first cell of my word
+      uint32_t m = (w < W) ? mrg[w] : 0u;
+      // validity bits of my 32 cells
+      uint32_t vb = 0u;
+      if (packed && w < W) {
+        if (a.covered != nullptr) {
+          if (cov_vec) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (k >= step) break;
-        const int v = v0 + k;
-        uint32_t code = 0;
-        if ((bits >> k) & 1u) {
-          if (v >= curE) {
-            const int S = mc_run_start(mrg, pz, v);
-            curE = mc_run_end(mrg, nz, v, V, W);
-            curLen = curE - S;
-            curCls = classify(S, curE);
+            for (int g = 0; g < 8; ++g) {
+              const int v = c0 + 4 * g;
+              const uint32_t x = (v < V) ? __ldg(reinterpret_cast<const uint32_t*>(a.covered + roff + v)) : 0u;
+              vb |= ((((__vcmpne4(x, 0u)) & 0x01010101u) * 0x01020408u) >> 24) << (4 * g);
+            }
+          } else {
+            for (int i = 0; i < 32 && c0 + i < V; ++i) vb |= (__ldg(a.covered + roff + c0 + i) != 0 ? 1u : 0u) << i;
           }
-          len4[k] = curLen;
-          code = kCodeMember | (curCls >= 0 ? (uint32_t)(curCls + 1) : 0u);
-          mem4 |= 1u << (8 * k);
-          if (curCls >= 0) {
-            cls4 |= (uint32_t)(curCls + 1) << (8 * k);
-            clen4[k] = curLen;
+        } else if (all_valid) {
+          vb = 0xffffffffu;
+        } else if (span_sorted) {
+          vb = mc_range_mask(vlo - c0, vhi - c0);
+        } else {
+          for (int i = 0; i < 32 && c0 + i < V; ++i) {
+            const long long c = __ldg(a.span_coords + c0 + i);
+            vb |= (!(c < sp || c > ep) ? 1u : 0u) << i;
           }
         }
-        if (a.packed != nullptr && cell_valid(v)) code |= kCodeValid;
-        code4 |= code << (8 * k);
       }
-      if (vec_ok) {
-        *reinterpret_cast<int4*>(a.merged_len + roff + v0) = make_int4(len4[0], len4[1], len4[2], len4[3]);
-        if (a.packed != nullptr) {
-          *reinterpret_cast<uint32_t*>(a.packed + roff + v0) = code4;
-        } else {
-          *reinterpret_cast<uint32_t*>(a.merged + roff + v0) = mem4;
-          if (a.class_out) *reinterpret_cast<uint32_t*>(a.class_out + roff + v0) = cls4;
-          if (a.len_cls)
-            *reinterpret_cast<int4*>(a.len_cls + roff + v0) = make_int4(clen4[0], clen4[1], clen4[2], clen4[3]);
+      // default fill: no run -> length 0, code = validity bit
+      uint4* lrow = reinterpret_cast<uint4*>(tlen + lane * kMcLenStride);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) lrow[g] = make_uint4(0u, 0u, 0u, 0u);
+      uint32_t cw[8];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) cw[g] = mc_spread4(vb >> (4 * g)) * (uint32_t)kCodeValid;
+      uint4* crow = reinterpret_cast<uint4*>(tcode + lane * kMcCodeStride);
+      crow[0] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+      crow[1] = make_uint4(cw[4], cw[5], cw[6], cw[7]);
+      // sub-runs of the word
+      int* lcell = reinterpret_cast<int*>(tlen + lane * kMcLenStride);
+      unsigned char* ccell = tcode + lane * kMcCodeStride;
+      while (m) {
+        const int b0 = __ffs(m) - 1;
+        const uint32_t above = ~m & ~((1u << b0) - 1u);  // clear bits at or above b0
+        const int b1 = above ? (__ffs(above) - 2) : 31;  // last cell of the sub-run
+        m &= ~mc_range_mask(b0, b1 + 1);
+        int S = c0 + b0, E = c0 + b1 + 1;
+        if (b0 == 0 && w > 0 && (mrg[w - 1] >> 31)) S = mc_run_start(mrg, pz, c0);
+        if (b1 == 31 && w + 1 < W && (mrg[w + 1] & 1u)) E = mc_run_end(mrg, nz, c0 + 31, V, W);
+        E = min(E, V);
+        const int len = E - S;
+        int cls = -1;
+        if (want_cls) {
+          const long long len_bp =
+              a.coords_are_ints ? (__ldg(a.coords + E - 1) - __ldg(a.coords + S) + 1) : (long long)(E - S);
+          cls = pick_class_int(ct, len_bp);
+        }
+        const unsigned char cd = (unsigned char)(kCodeMember | (cls >= 0 ? (cls + 1) : 0));
+        // fully covered groups of 4 cells get vector stores, the ragged ends cell stores
+        const int gs = (b0 + 3) >> 2, ge = ((b1 + 1) >> 2) - 1;
+        const int head_end = (gs <= ge) ? 4 * gs : b1 + 1;
+        for (int i = b0; i < head_end; ++i) {
+          lcell[i] = len;
+          ccell[i] = cd | (((vb >> i) & 1u) ? kCodeValid : 0);
+        }
+        if (gs <= ge) {
+          const uint4 len4 = make_uint4((uint32_t)len, (uint32_t)len, (uint32_t)len, (uint32_t)len);
+          const uint32_t cd4 = (uint32_t)cd * 0x01010101u;
+          for (int g = gs; g <= ge; ++g) {
+            lrow[g] = len4;
+            *reinterpret_cast<uint32_t*>(ccell + 4 * g) = cd4 | (mc_spread4(vb >> (4 * g)) * (uint32_t)kCodeValid);
+          }
+          for (int i = 4 * (ge + 1); i <= b1; ++i) {
+            lcell[i] = len;
+            ccell[i] = cd | (((vb >> i) & 1u) ? kCodeValid : 0);
+          }
+        }
+      }
+      __syncwarp();
+      // copy-out: 1024 cells of this block, coalesced
+      const int cbase = blk * 1024;
+      if (out_vec) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int o = 4 * lane + 128 * k;  // cell offset inside the block (4 cells per lane)
+          const int v = cbase + o;
+          if (v < V) {
+            const uint32_t c4 =
+                *reinterpret_cast<const uint32_t*>(tcode + (o >> 5) * kMcCodeStride + (o & 31));
+            const uint4 l4 = *reinterpret_cast<const uint4*>(tlen + (o >> 5) * kMcLenStride + (o & 31) * 4);
+            *reinterpret_cast<uint4*>(a.merged_len + roff + v) = l4;
+            if (packed) {
+              *reinterpret_cast<uint32_t*>(a.packed + roff + v) = c4;
+            } else {
+              *reinterpret_cast<uint32_t*>(a.merged + roff + v) = (c4 >> 6) & 0x01010101u;
+              const uint32_t k4 = c4 & 0x0f0f0f0fu;
+              if (a.class_out) *reinterpret_cast<uint32_t*>(a.class_out + roff + v) = k4;
+              if (a.len_cls)
+                *reinterpret_cast<uint4*>(a.len_cls + roff + v) =
+                    make_uint4((k4 & 0xffu) ? l4.x : 0u, (k4 & 0xff00u) ? l4.y : 0u, (k4 & 0xff0000u) ? l4.z : 0u,
+                               (k4 & 0xff000000u) ? l4.w : 0u);
+            }
+          }
         }
       } else {
-        a.merged_len[roff + v0] = len4[0];
-        if (a.packed != nullptr) {
-          a.packed[roff + v0] = (uint8_t)code4;
-        } else {
-          a.merged[roff + v0] = (uint8_t)mem4;
-          if (a.class_out) a.class_out[roff + v0] = (uint8_t)cls4;
-          if (a.len_cls) a.len_cls[roff + v0] = clen4[0];
+        for (int o = lane; o < 1024; o += 32) {
+          const int v = cbase + o;
+          if (v >= V) break;
+          const unsigned char c1 = tcode[(o >> 5) * kMcCodeStride + (o & 31)];
+          const int l1 = *reinterpret_cast<const int*>(tlen + (o >> 5) * kMcLenStride + (o & 31) * 4);
+          a.merged_len[roff + v] = l1;
+          if (packed) {
+            a.packed[roff + v] = c1;
+          } else {
+            a.merged[roff + v] = (c1 >> 6) & 1u;
+            if (a.class_out) a.class_out[roff + v] = c1 & 15u;
+            if (a.len_cls) a.len_cls[roff + v] = (c1 & 15u) ? l1 : 0;
+          }
         }
       }
+      __syncwarp();
     }
     __syncthreads();
   }
