@@ -1,0 +1,370 @@
+// Posterior decode of SHORT reads: several reads per warp.
+//
+// fb2_kernel gives every read whole warps; a read of 170 positions (the reference's amplicon case)
+// then occupies 10 of 32 lanes.  Here a warp owns a BUNDLE of R = floor(32 / Tg) consecutive reads,
+// read r on lanes [r*Tg, (r+1)*Tg) with Tg = ceil(L / CH) chunks of CH positions, and everything is
+// warp-local (no CTA barrier):
+//   * consecutive reads are contiguous in HBM, so a bundle's observations arrive with ONE bulk
+//     asynchronous copy into the warp's private double buffer (mbarrier completion, next bundle
+//     prefetched), and its posteriors / states leave with ONE bulk store each from a staging tile laid
+//     out exactly like the global rows;
+//   * phase 1 (chunk transfer-matrix product), phase 2 (Kogge-Stone prefix + suffix scans, SEGMENTED:
+//     a lane only combines with lanes of its own read) and phase 3 (forward sweep stacking alpha in
+//     a private shared-memory column, backward sweep writing gamma / arg-max to the staging tile) use
+//     the same scaled fp32 arithmetic and column-normalised tables as fb2_kernel;
+//   * position loops are rolled: the chunk length is a run-time odd number chosen by the planner to
+//     keep the lanes busy (e.g. L = 170: CH = 17, Tg = 10, R = 3 -> 94 % of the lanes), and the ragged
+//     last chunk of a read simply runs fewer iterations (no padding, nothing to clobber).
+#pragma once
+#include "fb2_kernel.cuh"
+
+namespace smf {
+
+constexpr int kShortWarps = 8;
+
+struct ShortArgs {
+  const void* obs;
+  long long N;
+  int L;
+  int CH;   // chunk length (odd)
+  int Tg;   // lanes (chunks) per read
+  int R;    // reads per warp
+  float* gamma;     // [N,L,K] / [N,L] / nullptr
+  int gamma_state;  // < 0: all states
+  int8_t* states;   // [N,L] / nullptr
+  double* loglik;   // [N] / nullptr
+  int in_bytes;     // one observation buffer
+  int stack_off;    // byte offsets inside a warp's region
+  int gam_off, st_off;
+  int warp_bytes;
+};
+
+template <int K, typename ObsT>
+__global__ void __launch_bounds__(kShortWarps * 32, 2) short_kernel(const __grid_constant__ FbTables<K> tab,
+                                                                   const __grid_constant__ ShortArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr unsigned kFull = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int L = a.L, CH = a.CH, Tg = a.Tg, R = a.R;
+  const int seg = lane / Tg;         // read of the bundle this lane works for
+  const int li = lane - seg * Tg;    // chunk index inside the read
+  const int t0 = li * CH;
+  const bool first = (li == 0);
+  const bool last = (li == Tg - 1);
+  const int len = (seg < R) ? max(0, min(CH, L - t0)) : 0;
+
+  unsigned char* wbase = smem + (size_t)warp * a.warp_bytes;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(wbase);  // [2]
+  unsigned char* in_raw = wbase + 16;
+  float* stack = reinterpret_cast<float*>(wbase + a.stack_off) + (size_t)lane * CH * K;
+  float* s_gam_base = reinterpret_cast<float*>(wbase + a.gam_off);
+  int8_t* s_st_base = reinterpret_cast<int8_t*>(wbase + a.st_off);
+
+  if (lane == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+
+  float A[K][K];
+#pragma unroll
+  for (int i = 0; i < K; ++i)
+#pragma unroll
+    for (int j = 0; j < K; ++j) A[i][j] = tab.Ap[i][j];
+  auto vecA = [&](const float (&x)[K], float (&y)[K]) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      float s = x[j];
+#pragma unroll
+      for (int i = 0; i < K; ++i)
+        if (i != j) s = fmaf(x[i], A[i][j], s);
+      y[j] = s;
+    }
+  };
+  auto ratios = [&](float o, float (&c)[K]) {
+    const bool m = (o == o);
+    c[0] = 1.0f;
+#pragma unroll
+    for (int k = 1; k < K; ++k) c[k] = ex2_approx(m ? fmaf(o, tab.rdl[k][0], tab.rl0p[k]) : tab.rmiss[k]);
+    return m;
+  };
+
+  const bool want_ll = (a.loglik != nullptr);
+  const int gs = a.gamma_state;
+  const bool w_gamma_all = (a.gamma != nullptr && gs < 0);
+  const bool w_gamma_one = (a.gamma != nullptr && gs >= 0);
+  const bool w_states = (a.states != nullptr);
+  const char* obs_base = static_cast<const char*>(a.obs);
+  const long long nbundles = (a.N + R - 1) / R;
+  const long long wstride = (long long)gridDim.x * kShortWarps;
+
+  auto issue_load = [&](long long b, int buf) {
+    const long long n0 = b * R;
+    const int nr = (int)min((long long)R, a.N - n0);
+    const char* src = obs_base + (size_t)n0 * L * sizeof(ObsT);
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
+    const uint32_t bytes = (mis + (uint32_t)(nr * L) * (uint32_t)sizeof(ObsT) + 15u) & ~15u;
+    mbar_expect_tx(&mbar[buf], bytes);
+    bulk_load(in_raw + (size_t)buf * a.in_bytes, src - mis, bytes, &mbar[buf]);
+  };
+
+  long long b = (long long)blockIdx.x * kShortWarps + warp;
+  if (lane == 0 && b < nbundles) issue_load(b, 0);
+
+  int it = 0;
+  for (; b < nbundles; b += wstride, ++it) {
+    const int buf = it & 1;
+    if (lane == 0 && b + wstride < nbundles) issue_load(b + wstride, buf ^ 1);
+    const long long n0 = b * R;
+    const int nr = (int)min((long long)R, a.N - n0);
+    const bool active = (seg < nr) && (len > 0);
+    const int mylen = active ? len : 0;
+    const uint32_t mis =
+        (uint32_t)(reinterpret_cast<uintptr_t>(obs_base + (size_t)n0 * L * sizeof(ObsT)) & 15u);
+    const ObsT* s_in = reinterpret_cast<const ObsT*>(in_raw + (size_t)buf * a.in_bytes + mis) + (size_t)seg * L + t0;
+
+    mbar_wait(&mbar[buf], (uint32_t)((it >> 1) & 1));
+
+    // ---------------- phase 1: chunk transfer matrix ----------------
+    float P[K][K];
+    mat_set_identity<K>(P);
+    float ll_sumo = 0.0f;
+    int ll_cnt = 0;
+    for (int j = 0; j < mylen; ++j) {
+      const float o = obs_to_float<ObsT>(s_in[j]);
+      float c[K];
+      const bool m = ratios(o, c);
+      if (want_ll && m) {
+        ll_sumo += o;
+        ++ll_cnt;
+      }
+      const bool no_trans = first && j == 0;  // P <- diag(c) for the first position of a read
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        float q[K];
+        vecA(P[i], q);
+#pragma unroll
+        for (int jj = 0; jj < K; ++jj) {
+          const float x = no_trans ? P[i][jj] : q[jj];
+          P[i][jj] = (jj == 0) ? x : x * c[jj];
+        }
+      }
+      if ((j & 3) == 3 || j == mylen - 1) mat_scale<K>(P, pow2_rescale_noexp(mat_max<K>(P)));
+    }
+
+    // ---------------- phase 2: segmented warp-shuffle scans ----------------
+    float pre[K][K], suf[K][K];
+#pragma unroll
+    for (int i = 0; i < K; ++i)
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        pre[i][j] = P[i][j];
+        suf[i][j] = P[i][j];
+      }
+    int lvl = 0;
+    for (int d = 1; d < Tg; d <<= 1, ++lvl) {
+      float q[K][K], r[K][K];
+#pragma unroll
+      for (int i = 0; i < K; ++i)
+#pragma unroll
+        for (int j = 0; j < K; ++j) q[i][j] = __shfl_up_sync(kFull, pre[i][j], d);
+      mat_mul<K>(q, pre, r);
+      const bool up_ok = li >= d;
+#pragma unroll
+      for (int i = 0; i < K; ++i)
+#pragma unroll
+        for (int j = 0; j < K; ++j) pre[i][j] = up_ok ? r[i][j] : pre[i][j];
+#pragma unroll
+      for (int i = 0; i < K; ++i)
+#pragma unroll
+        for (int j = 0; j < K; ++j) q[i][j] = __shfl_down_sync(kFull, suf[i][j], d);
+      mat_mul<K>(suf, q, r);
+      const bool dn_ok = li + d < Tg;
+#pragma unroll
+      for (int i = 0; i < K; ++i)
+#pragma unroll
+        for (int j = 0; j < K; ++j) suf[i][j] = dn_ok ? r[i][j] : suf[i][j];
+      if (lvl & 1) {
+        mat_scale<K>(pre, pow2_rescale_noexp(mat_max<K>(pre)));
+        mat_scale<K>(suf, pow2_rescale_noexp(mat_max<K>(suf)));
+      }
+    }
+    float v[K], w[K];
+    {
+      float vo[K], wo[K];
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        float s = tab.pi2[0] * pre[0][j];
+#pragma unroll
+        for (int i = 1; i < K; ++i) s = fmaf(tab.pi2[i], pre[i][j], s);
+        vo[j] = s;
+      }
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        float s = suf[i][0];
+#pragma unroll
+        for (int j = 1; j < K; ++j) s += suf[i][j];
+        wo[i] = s;
+      }
+      float sv = 0.0f, sw = 0.0f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        v[k] = __shfl_up_sync(kFull, vo[k], 1);
+        w[k] = __shfl_down_sync(kFull, wo[k], 1);
+        if (first) v[k] = tab.pi2[k];
+        if (last) w[k] = 1.0f;
+        sv += v[k];
+        sw += w[k];
+      }
+      const float rv = want_ll ? (1.0f / sv) : rcp_approx(sv);
+      const float rw = rcp_approx(sw);
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        v[k] *= rv;
+        w[k] *= rw;
+      }
+    }
+
+    // the previous bundle's bulk stores have finished reading the staging tile
+    if (lane == 0) bulk_wait_read_all();
+    __syncwarp();
+
+    // where the bundle's rows sit relative to 16-byte granules (keeps smem and global congruent)
+    float* s_gam = s_gam_base;
+    int8_t* s_st = s_st_base;
+    if (w_gamma_all) s_gam += (reinterpret_cast<uintptr_t>(a.gamma + (size_t)n0 * L * K) & 15u) >> 2;
+    if (w_gamma_one) s_gam += (reinterpret_cast<uintptr_t>(a.gamma + (size_t)n0 * L) & 15u) >> 2;
+    if (w_states) s_st += reinterpret_cast<uintptr_t>(a.states + (size_t)n0 * L) & 15u;
+    const int pos0 = seg * L + t0;  // my first position inside the bundle
+
+    // ---------------- phase 3: forward sweep (alpha column), backward sweep (gamma, states) ----------------
+    double ll_thread = 0.0;
+    {
+      float al[K];
+      int e = 0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) al[k] = v[k];
+      for (int j = 0; j < mylen; ++j) {
+        const float o = obs_to_float<ObsT>(s_in[j]);
+        float cf[K], y[K];
+        ratios(o, cf);
+        vecA(al, y);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const float x = (first && j == 0) ? al[k] : y[k];
+          y[k] = (k == 0) ? x : x * cf[k];
+        }
+        if ((j & 3) == 3) {
+          const float sc = want_ll ? pow2_rescale(vec_max<K>(y), e) : pow2_rescale_noexp(vec_max<K>(y));
+#pragma unroll
+          for (int k = 0; k < K; ++k) y[k] *= sc;
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          al[k] = y[k];
+          stack[j * K + k] = y[k];
+        }
+      }
+      if (want_ll && active) {
+        float s = al[0];
+#pragma unroll
+        for (int k = 1; k < K; ++k) s += al[k];
+        ll_thread = (double)logf(s) + (double)e * 0.6931471805599453094 + (double)ll_cnt * tab.l00[0] +
+                    (double)ll_sumo * tab.dl0[0] + (double)(first ? mylen - 1 : mylen) * tab.log_s0;
+        if (first) ll_thread += tab.log_pi2_sum;
+      }
+      float bv[K], alc[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        bv[k] = w[k];
+        alc[k] = al[k];
+      }
+      for (int j = mylen - 1; j >= 0; --j) {
+        float gk[K];
+        float gsum = 0.0f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          gk[k] = alc[k] * bv[k];
+          gsum += gk[k];
+        }
+        const float gr = rcp_approx(gsum);
+#pragma unroll
+        for (int k = 0; k < K; ++k) gk[k] *= gr;
+        if (w_gamma_all) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) s_gam[(size_t)(pos0 + j) * K + k] = gk[k];
+        } else if (w_gamma_one) {
+          float gsel = gk[0];
+#pragma unroll
+          for (int k = 1; k < K; ++k)
+            if (gs == k) gsel = gk[k];
+          s_gam[pos0 + j] = gsel;
+        }
+        if (w_states) {
+          int best = 0;
+          float gbest = gk[0];
+#pragma unroll
+          for (int k = 1; k < K; ++k)
+            if (gk[k] > gbest) {
+              gbest = gk[k];
+              best = k;
+            }
+          s_st[pos0 + j] = (int8_t)best;
+        }
+        if (j > 0) {
+          const float o = obs_to_float<ObsT>(s_in[j]);
+          float cr[K], cb[K], nb[K];
+          ratios(o, cr);
+          cb[0] = bv[0];
+#pragma unroll
+          for (int k = 1; k < K; ++k) cb[k] = cr[k] * bv[k];
+#pragma unroll
+          for (int i = 0; i < K; ++i) {
+            float s = cb[i];
+#pragma unroll
+            for (int jj = 0; jj < K; ++jj)
+              if (jj != i) s = fmaf(A[i][jj], cb[jj], s);
+            nb[i] = s;
+          }
+          if (((mylen - 1 - j) & 3) == 3) {
+            const float sc = pow2_rescale_noexp(vec_max<K>(nb));
+#pragma unroll
+            for (int k = 0; k < K; ++k) nb[k] *= sc;
+          }
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            bv[k] = nb[k];
+            alc[k] = stack[(j - 1) * K + k];
+          }
+        }
+      }
+    }
+
+    // ---------------- store: one bulk store per output for the whole bundle ----------------
+    fence_proxy_async();
+    __syncwarp();
+    {
+      const uint32_t npos = (uint32_t)(nr * L);
+      if (w_gamma_all) store_row_bulk<float>(a.gamma + (size_t)n0 * L * K, s_gam, npos * K * 4u, lane);
+      if (w_gamma_one) store_row_bulk<float>(a.gamma + (size_t)n0 * L, s_gam, npos * 4u, lane);
+      if (w_states) store_row_bulk<int8_t>(a.states + (size_t)n0 * L, s_st, npos, lane);
+      if (lane == 0) bulk_commit();
+    }
+    if (want_ll) {
+      // segmented sum over the lanes of a read
+      double s = ll_thread;
+      for (int d = 1; d < Tg; d <<= 1) {
+        const double o = __shfl_down_sync(kFull, s, d);
+        if (li + d < Tg) s += o;
+      }
+      // after a power-of-two ladder lane li = 0 holds the sum of lanes [0, 2^ceil(log2 Tg)) restricted by the guard
+      if (first && seg < nr) a.loglik[n0 + seg] = s;
+    }
+    __syncwarp();  // every lane is done with this observation buffer before it is refilled
+  }
+  if (lane == 0) bulk_wait_all();
+}
+
+}  // namespace smf
