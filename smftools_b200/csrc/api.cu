@@ -11,6 +11,7 @@
 #include "features_kernel.cuh"
 #include "launch.h"
 #include "smf_hmm.h"
+#include "short_kernel.cuh"
 #include "sweep_kernel.cuh"
 #include "walk_kernel.cuh"
 
@@ -338,6 +339,66 @@ static int launch_walk_path(bool stats, const smf_hmm_tables* t, int obs_dtype, 
                   : launch_fb2w_k4(plan.chunk, stats, obs_dtype, out, t, a, plan, di, nblocks, stream);
 }
 
+// ---------------------------------------------------------------------------------------
+// short reads (short_kernel): several reads per warp
+// ---------------------------------------------------------------------------------------
+// -1 = measured policy, 0 = never, 1 = whenever it fits.  SMF_SHORT / smf_hmm_set_option("short", v).
+static int g_short_mode = [] { const char* e = getenv("SMF_SHORT"); return e ? atoi(e) : -1; }();
+// measured (profiles/r01_short.txt): faster than one read per warp up to ~200 positions (K = 4: ~100)
+static int short_max_len(int K) { return K >= 4 ? 100 : 200; }
+
+// Picks the odd chunk length that keeps the most lanes busy (weighted by how well it amortises the
+// scan) with at least two reads per warp, and lays out the warp's shared-memory region.
+static int plan_short(int K, int64_t L64, int es, bool gamma_all, bool gamma_one, bool want_states, int max_smem,
+                      ShortArgs* a) {
+  if (L64 < 1 || L64 > 16 * 33) return SMF_ERR_TOO_LONG;
+  const int L = (int)L64;
+  double best = -1.0;
+  int bch = 0;
+  static const int env_ch = [] { const char* e = getenv("SMF_SHORT_CHUNK"); return e ? atoi(e) : 0; }();
+  for (int ch = 5; ch <= 33; ch += 2) {
+    if (env_ch && ch != env_ch) continue;
+    const int tg = (L + ch - 1) / ch;
+    if (tg > 16) continue;
+    const int r = 32 / tg;
+    const double eff = (double)(r * L) / (32.0 * ch);
+    // shared memory per warp decides how many warps hide each other's recurrence latency
+    const int kout_c = gamma_all ? K : (gamma_one ? 1 : 0);
+    const double wb = 16.0 + 2.0 * (r * L * es + 32) + 32.0 * ch * K * 4 + r * L * kout_c * 4.0 + (want_states ? r * L : 0) + 64;
+    const double warps = 227.0 * 1024.0 / wb;
+    if (kShortWarps * wb > max_smem) continue;
+    const double score = eff * ch / (ch + 6.0) * (warps >= 16.0 ? 1.0 : warps / 16.0);
+    if (score > best) {
+      best = score;
+      bch = ch;
+    }
+  }
+  if (bch == 0) return SMF_ERR_TOO_LONG;
+  const int Tg = (L + bch - 1) / bch, R = 32 / Tg;
+  const int kout = gamma_all ? K : (gamma_one ? 1 : 0);
+  a->L = L;
+  a->CH = bch;
+  a->Tg = Tg;
+  a->R = R;
+  a->in_bytes = align_up(R * L * es + 32, 16);
+  a->stack_off = 16 + 2 * a->in_bytes;
+  a->gam_off = a->stack_off + align_up(32 * bch * K * 4, 16);
+  a->st_off = a->gam_off + (kout ? align_up(R * L * kout * 4 + 16, 16) : 0);
+  a->warp_bytes = a->st_off + (want_states ? align_up(R * L + 32, 16) : 0);
+  if (kShortWarps * a->warp_bytes > max_smem) return SMF_ERR_TOO_LONG;
+  return SMF_OK;
+}
+
+static int launch_short(const smf_hmm_tables* t, int obs_dtype, const ShortArgs& a, const DeviceInfo& di,
+                        cudaStream_t s) {
+  switch (t->n_states) {
+    case 2: return launch_short_k2(obs_dtype, t, a, di, s);
+    case 3: return launch_short_k3(obs_dtype, t, a, di, s);
+    case 4: return launch_short_k4(obs_dtype, t, a, di, s);
+  }
+  return SMF_ERR_BAD_ARG;
+}
+
 static int launch_fb2(bool stats, const smf_hmm_tables* t, int obs_dtype, Fb2Args& a, const Fb2Plan& plan,
                       const DeviceInfo& di, int* nblocks, cudaStream_t stream) {
   // output-set specialisations exist for float observations; everything else decides at run time
@@ -481,6 +542,11 @@ int smf_hmm_set_option(const char* key, int value) {
     g_walk_mode = value;
     return SMF_OK;
   }
+  if (strcmp(key, "short") == 0) {
+    if (value < -1 || value > 1) return SMF_ERR_BAD_ARG;
+    g_short_mode = value;
+    return SMF_OK;
+  }
   return SMF_ERR_BAD_ARG;
 }
 
@@ -543,6 +609,21 @@ int smf_hmm_posterior(const smf_hmm_tables* tab, const void* obs, int obs_dtype,
   const int cadence = rescale_cadence(tab);
   if (tab->n_channels == 1 && tab->n_bins == 1 && !g_force_generic && cadence == 4 &&
       fb2_aligned(obs, obs_dtype, gamma, tab->n_states, gamma_state)) {
+    // short reads: several reads per warp
+    if (g_short_mode != 0 && (g_short_mode == 1 || n_pos <= short_max_len(tab->n_states))) {
+      ShortArgs sa;
+      memset(&sa, 0, sizeof(sa));
+      if (plan_short(tab->n_states, n_pos, obs_elem_size(obs_dtype), gamma != nullptr && gamma_state < 0,
+                     gamma != nullptr && gamma_state >= 0, states != nullptr, di.max_smem_optin, &sa) == SMF_OK) {
+        sa.obs = obs;
+        sa.N = n_reads;
+        sa.gamma = gamma;
+        sa.gamma_state = gamma_state;
+        sa.states = states;
+        sa.loglik = loglik;
+        return launch_short(tab, obs_dtype, sa, di, (cudaStream_t)stream);
+      }
+    }
     Fb2Args b;
     memset(&b, 0, sizeof(b));
     Fb2Plan p2;

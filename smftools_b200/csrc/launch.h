@@ -120,6 +120,10 @@ SMF_DECLARE_K(4)
 #undef SMF_DECLARE_K
 struct WalkArgs;
 struct SweepArgs;
+struct ShortArgs;
+int launch_short_k2(int obs_dtype, const smf_hmm_tables* t, const ShortArgs& a, const DeviceInfo& di, cudaStream_t s);
+int launch_short_k3(int obs_dtype, const smf_hmm_tables* t, const ShortArgs& a, const DeviceInfo& di, cudaStream_t s);
+int launch_short_k4(int obs_dtype, const smf_hmm_tables* t, const ShortArgs& a, const DeviceInfo& di, cudaStream_t s);
 #define SMF_DECLARE_WK(KV)                                                                                   \
   int launch_walk_k##KV(int obs_dtype, const smf_hmm_tables* t, const WalkArgs& a, cudaStream_t s);         \
   int launch_sweep_k##KV(int obs_dtype, const smf_hmm_tables* t, SweepArgs& a, const DeviceInfo& di,        \

@@ -132,10 +132,21 @@ __global__ void __launch_bounds__(kShortWarps * 32, 2) short_kernel(const __grid
     mat_set_identity<K>(P);
     float ll_sumo = 0.0f;
     int ll_cnt = 0;
+    // The emission ratios of position j+1 are formed while position j is folded in: the loop-carried
+    // dependency is then only the K(K-1) FMA chain, not load -> ex2 -> multiply.
+    float cn[K];
+    float on = (mylen > 0) ? obs_to_float<ObsT>(s_in[0]) : 0.0f;
+    bool mn = ratios(on, cn);
     for (int j = 0; j < mylen; ++j) {
-      const float o = obs_to_float<ObsT>(s_in[j]);
       float c[K];
-      const bool m = ratios(o, c);
+#pragma unroll
+      for (int k = 0; k < K; ++k) c[k] = cn[k];
+      const float o = on;
+      const bool m = mn;
+      if (j + 1 < mylen) {
+        on = obs_to_float<ObsT>(s_in[j + 1]);
+        mn = ratios(on, cn);
+      }
       if (want_ll && m) {
         ll_sumo += o;
         ++ll_cnt;
@@ -246,10 +257,13 @@ __global__ void __launch_bounds__(kShortWarps * 32, 2) short_kernel(const __grid
       int e = 0;
 #pragma unroll
       for (int k = 0; k < K; ++k) al[k] = v[k];
+      float fn[K];
+      ratios((mylen > 0) ? obs_to_float<ObsT>(s_in[0]) : 0.0f, fn);
       for (int j = 0; j < mylen; ++j) {
-        const float o = obs_to_float<ObsT>(s_in[j]);
         float cf[K], y[K];
-        ratios(o, cf);
+#pragma unroll
+        for (int k = 0; k < K; ++k) cf[k] = fn[k];
+        if (j + 1 < mylen) ratios(obs_to_float<ObsT>(s_in[j + 1]), fn);
         vecA(al, y);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -281,7 +295,24 @@ __global__ void __launch_bounds__(kShortWarps * 32, 2) short_kernel(const __grid
         bv[k] = w[k];
         alc[k] = al[k];
       }
+      float rn[K], an[K];  // ratios of position j, alpha of position j-1: fetched one step ahead
+      ratios((mylen > 0) ? obs_to_float<ObsT>(s_in[mylen - 1]) : 0.0f, rn);
+#pragma unroll
+      for (int k = 0; k < K; ++k) an[k] = (mylen > 1) ? stack[(mylen - 2) * K + k] : 0.0f;
       for (int j = mylen - 1; j >= 0; --j) {
+        float cr[K], alp[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          cr[k] = rn[k];
+          alp[k] = an[k];
+        }
+        if (j > 0) {
+          ratios(obs_to_float<ObsT>(s_in[j - 1]), rn);
+          if (j > 1) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) an[k] = stack[(j - 2) * K + k];
+          }
+        }
         float gk[K];
         float gsum = 0.0f;
 #pragma unroll
@@ -314,9 +345,7 @@ __global__ void __launch_bounds__(kShortWarps * 32, 2) short_kernel(const __grid
           s_st[pos0 + j] = (int8_t)best;
         }
         if (j > 0) {
-          const float o = obs_to_float<ObsT>(s_in[j]);
-          float cr[K], cb[K], nb[K];
-          ratios(o, cr);
+          float cb[K], nb[K];
           cb[0] = bv[0];
 #pragma unroll
           for (int k = 1; k < K; ++k) cb[k] = cr[k] * bv[k];
@@ -336,7 +365,7 @@ __global__ void __launch_bounds__(kShortWarps * 32, 2) short_kernel(const __grid
 #pragma unroll
           for (int k = 0; k < K; ++k) {
             bv[k] = nb[k];
-            alc[k] = stack[(j - 1) * K + k];
+            alc[k] = alp[k];
           }
         }
       }
