@@ -339,18 +339,21 @@ static int launch_walk_path(bool stats, const smf_hmm_tables* t, int obs_dtype, 
                   : launch_fb2w_k4(plan.chunk, stats, obs_dtype, out, t, a, plan, di, nblocks, stream);
 }
 
+static inline int obs_elem_size(int dt) { return dt == SMF_OBS_F32 ? 4 : (dt == SMF_OBS_F64 ? 8 : 1); }
+
 // ---------------------------------------------------------------------------------------
 // short reads (short_kernel): several reads per warp
 // ---------------------------------------------------------------------------------------
 // -1 = measured policy, 0 = never, 1 = whenever it fits.  SMF_SHORT / smf_hmm_set_option("short", v).
 static int g_short_mode = [] { const char* e = getenv("SMF_SHORT"); return e ? atoi(e) : -1; }();
-// measured (profiles/r01_short.txt): faster than one read per warp up to ~200 positions (K = 4: ~100)
-static int short_max_len(int K) { return K >= 4 ? 100 : 200; }
+// measured (profiles/r01_short.txt): faster than one read per warp up to ~270 positions (K = 4: ~100)
+static int short_max_len(int K) { return K >= 4 ? 100 : 270; }
 
 // Picks the odd chunk length that keeps the most lanes busy (weighted by how well it amortises the
 // scan) with at least two reads per warp, and lays out the warp's shared-memory region.
-static int plan_short(int K, int64_t L64, int es, bool gamma_all, bool gamma_one, bool want_states, int max_smem,
-                      ShortArgs* a) {
+static int plan_short(int K, int64_t L64, int obs_dtype, bool gamma_all, bool gamma_one, bool want_states,
+                      int max_smem, ShortArgs* a) {
+  const int es = obs_elem_size(obs_dtype);
   if (L64 < 1 || L64 > 16 * 33) return SMF_ERR_TOO_LONG;
   const int L = (int)L64;
   double best = -1.0;
@@ -367,7 +370,9 @@ static int plan_short(int K, int64_t L64, int es, bool gamma_all, bool gamma_one
     const double wb = 16.0 + 2.0 * (r * L * es + 32) + 32.0 * ch * K * 4 + r * L * kout_c * 4.0 + (want_states ? r * L : 0) + 64;
     const double warps = 227.0 * 1024.0 / wb;
     if (kShortWarps * wb > max_smem) continue;
-    const double score = eff * ch / (ch + 6.0) * (warps >= 16.0 ? 1.0 : warps / 16.0);
+    double score = eff * ch / (ch + 6.0) * (warps >= 16.0 ? 1.0 : warps / 16.0);
+    // fully unrolled instantiations run ~2.5x fewer instructions per position than the rolled variant
+    if (short_chunk_compiled(K, obs_dtype, ch)) score *= 2.5;
     if (score > best) {
       best = score;
       bch = ch;
@@ -425,7 +430,6 @@ static int launch_fb(bool stats, const smf_hmm_tables* t, FbArgs& a, const FbPla
   return SMF_ERR_BAD_ARG;
 }
 
-static inline int obs_elem_size(int dt) { return dt == SMF_OBS_F32 ? 4 : (dt == SMF_OBS_F64 ? 8 : 1); }
 
 // The fast path needs natural alignment of the row pointers it vectorises.
 static bool fb2_aligned(const void* obs, int obs_dtype, const float* gamma, int K, int gamma_state) {
@@ -613,7 +617,7 @@ int smf_hmm_posterior(const smf_hmm_tables* tab, const void* obs, int obs_dtype,
     if (g_short_mode != 0 && (g_short_mode == 1 || n_pos <= short_max_len(tab->n_states))) {
       ShortArgs sa;
       memset(&sa, 0, sizeof(sa));
-      if (plan_short(tab->n_states, n_pos, obs_elem_size(obs_dtype), gamma != nullptr && gamma_state < 0,
+      if (plan_short(tab->n_states, n_pos, obs_dtype, gamma != nullptr && gamma_state < 0,
                      gamma != nullptr && gamma_state >= 0, states != nullptr, di.max_smem_optin, &sa) == SMF_OK) {
         sa.obs = obs;
         sa.N = n_reads;

@@ -121,6 +121,12 @@ SMF_DECLARE_K(4)
 struct WalkArgs;
 struct SweepArgs;
 struct ShortArgs;
+// chunk lengths short_kernel is instantiated for with fully unrolled loops (short_launch.inc)
+static inline bool short_chunk_compiled(int K, int obs_dtype, int ch) {
+  if (K > 3 || obs_dtype == SMF_OBS_F64) return false;
+  if (ch == 9 || ch == 17) return true;
+  return K == 2 && (ch == 25 || ch == 33);
+}
 int launch_short_k2(int obs_dtype, const smf_hmm_tables* t, const ShortArgs& a, const DeviceInfo& di, cudaStream_t s);
 int launch_short_k3(int obs_dtype, const smf_hmm_tables* t, const ShortArgs& a, const DeviceInfo& di, cudaStream_t s);
 int launch_short_k4(int obs_dtype, const smf_hmm_tables* t, const ShortArgs& a, const DeviceInfo& di, cudaStream_t s);

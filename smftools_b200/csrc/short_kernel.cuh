@@ -39,14 +39,19 @@ struct ShortArgs {
   int warp_bytes;
 };
 
-template <int K, typename ObsT>
+// CHT > 0: the chunk length is the compile-time constant CHT -- the position loops are fully unrolled
+// (no loop / address / predicate arithmetic, emission ratios cached in registers) and a lane simply
+// skips the copies beyond its chunk; CHT == 0: run-time chunk length a.CH with rolled, software-
+// pipelined loops (any odd length, any observation type).
+template <int K, typename ObsT, int CHT>
 __global__ void __launch_bounds__(kShortWarps * 32, 2) short_kernel(const __grid_constant__ FbTables<K> tab,
                                                                    const __grid_constant__ ShortArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr unsigned kFull = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int L = a.L, CH = a.CH, Tg = a.Tg, R = a.R;
+  const int L = a.L, CH = (CHT > 0) ? CHT : a.CH, Tg = a.Tg, R = a.R;
+  constexpr int NRT = (CHT > 0) ? CHT : 1;
   const int seg = lane / Tg;         // read of the bundle this lane works for
   const int li = lane - seg * Tg;    // chunk index inside the read
   const int t0 = li * CH;
@@ -132,37 +137,68 @@ __global__ void __launch_bounds__(kShortWarps * 32, 2) short_kernel(const __grid
     mat_set_identity<K>(P);
     float ll_sumo = 0.0f;
     int ll_cnt = 0;
-    // The emission ratios of position j+1 are formed while position j is folded in: the loop-carried
-    // dependency is then only the K(K-1) FMA chain, not load -> ex2 -> multiply.
-    float cn[K];
-    float on = (mylen > 0) ? obs_to_float<ObsT>(s_in[0]) : 0.0f;
-    bool mn = ratios(on, cn);
-    for (int j = 0; j < mylen; ++j) {
-      float c[K];
+    float rt[NRT][K];  // cached emission ratios (compile-time chunk only)
+    if constexpr (CHT > 0) {
+      // Positions past the end of the chunk (ragged last chunk of a read, idle lanes) are treated as
+      // missing observations: they leave the posteriors of the real positions unchanged (beta of the
+      // last real position stays uniform), so nothing but the loads and the output stores is predicated.
+      const float kMissing = __int_as_float(0x7fc00000);
 #pragma unroll
-      for (int k = 0; k < K; ++k) c[k] = cn[k];
-      const float o = on;
-      const bool m = mn;
-      if (j + 1 < mylen) {
-        on = obs_to_float<ObsT>(s_in[j + 1]);
-        mn = ratios(on, cn);
-      }
-      if (want_ll && m) {
-        ll_sumo += o;
-        ++ll_cnt;
-      }
-      const bool no_trans = first && j == 0;  // P <- diag(c) for the first position of a read
+      for (int j = 0; j < CHT; ++j) {
+        const float o = (j < mylen) ? obs_to_float<ObsT>(s_in[j]) : kMissing;
+        float c[K];
+        const bool m = ratios(o, c);
 #pragma unroll
-      for (int i = 0; i < K; ++i) {
-        float q[K];
-        vecA(P[i], q);
-#pragma unroll
-        for (int jj = 0; jj < K; ++jj) {
-          const float x = no_trans ? P[i][jj] : q[jj];
-          P[i][jj] = (jj == 0) ? x : x * c[jj];
+        for (int k = 0; k < K; ++k) rt[j][k] = c[k];
+        if (want_ll && m) {
+          ll_sumo += o;
+          ++ll_cnt;
         }
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+          float q[K];
+          vecA(P[i], q);
+#pragma unroll
+          for (int jj = 0; jj < K; ++jj) {
+            const float x = (j == 0 && first) ? P[i][jj] : q[jj];  // P <- diag(c) at the start of a read
+            P[i][jj] = (jj == 0) ? x : x * c[jj];
+          }
+        }
+        if ((j & 3) == 3 || j == CHT - 1) mat_scale<K>(P, pow2_rescale_noexp(mat_max<K>(P)));
       }
-      if ((j & 3) == 3 || j == mylen - 1) mat_scale<K>(P, pow2_rescale_noexp(mat_max<K>(P)));
+    } else {
+    // The emission ratios of position j+1 are formed while position j is folded in: the loop-carried
+      // dependency is then only the K(K-1) FMA chain, not load -> ex2 -> multiply.
+      float cn[K];
+      float on = (mylen > 0) ? obs_to_float<ObsT>(s_in[0]) : 0.0f;
+      bool mn = ratios(on, cn);
+      for (int j = 0; j < mylen; ++j) {
+        float c[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) c[k] = cn[k];
+        const float o = on;
+        const bool m = mn;
+        if (j + 1 < mylen) {
+          on = obs_to_float<ObsT>(s_in[j + 1]);
+          mn = ratios(on, cn);
+        }
+        if (want_ll && m) {
+          ll_sumo += o;
+          ++ll_cnt;
+        }
+        const bool no_trans = first && j == 0;  // P <- diag(c) for the first position of a read
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+          float q[K];
+          vecA(P[i], q);
+#pragma unroll
+          for (int jj = 0; jj < K; ++jj) {
+            const float x = no_trans ? P[i][jj] : q[jj];
+            P[i][jj] = (jj == 0) ? x : x * c[jj];
+          }
+        }
+        if ((j & 3) == 3 || j == mylen - 1) mat_scale<K>(P, pow2_rescale_noexp(mat_max<K>(P)));
+      }
     }
 
     // ---------------- phase 2: segmented warp-shuffle scans ----------------
@@ -252,6 +288,130 @@ __global__ void __launch_bounds__(kShortWarps * 32, 2) short_kernel(const __grid
 
     // ---------------- phase 3: forward sweep (alpha column), backward sweep (gamma, states) ----------------
     double ll_thread = 0.0;
+    if constexpr (CHT > 0) {
+      float al[K];
+      int e = 0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) al[k] = v[k];
+      float* gout = s_gam + (size_t)pos0 * (w_gamma_all ? K : 1);
+      int8_t* sout = s_st + pos0;
+#pragma unroll
+      for (int j = 0; j < CHT; ++j) {
+        float y[K];
+        vecA(al, y);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const float x = (j == 0 && first) ? al[k] : y[k];
+          y[k] = (k == 0) ? x : x * rt[j][k];
+        }
+        if ((j & 3) == 3) {
+          const float sc = want_ll ? pow2_rescale(vec_max<K>(y), e) : pow2_rescale_noexp(vec_max<K>(y));
+#pragma unroll
+          for (int k = 0; k < K; ++k) y[k] *= sc;
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) al[k] = y[k];
+        if (K == 2) {
+          *reinterpret_cast<float2*>(stack + j * 2) = make_float2(y[0], y[1 % K]);
+        } else if (K == 4) {
+          *reinterpret_cast<float4*>(stack + j * 4) = make_float4(y[0], y[1 % K], y[2 % K], y[3 % K]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < K; ++k) stack[j * K + k] = y[k];
+        }
+      }
+      if (want_ll && active) {
+        float s = al[0];
+#pragma unroll
+        for (int k = 1; k < K; ++k) s += al[k];
+        // every one of the CHT steps (pads included) dropped the scalar s_0
+        ll_thread = (double)logf(s) + (double)e * 0.6931471805599453094 + (double)ll_cnt * tab.l00[0] +
+                    (double)ll_sumo * tab.dl0[0] + (double)(first ? CHT - 1 : CHT) * tab.log_s0;
+        if (first) ll_thread += tab.log_pi2_sum;
+      }
+      float bv[K], alc[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        bv[k] = w[k];
+        alc[k] = al[k];
+      }
+#pragma unroll
+      for (int j = CHT - 1; j >= 0; --j) {
+        const bool real = j < mylen;
+        float gk[K];
+        float gsum = 0.0f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          gk[k] = alc[k] * bv[k];
+          gsum += gk[k];
+        }
+        const float gr = rcp_approx(gsum);
+#pragma unroll
+        for (int k = 0; k < K; ++k) gk[k] *= gr;
+        if (real) {
+          if (w_gamma_all) {
+            if (K == 2) {
+              *reinterpret_cast<float2*>(gout + j * 2) = make_float2(gk[0], gk[1 % K]);  // 8-byte aligned (fb2_aligned)
+            } else {
+#pragma unroll
+              for (int k = 0; k < K; ++k) gout[j * K + k] = gk[k];
+            }
+          } else if (w_gamma_one) {
+            float gsel = gk[0];
+#pragma unroll
+            for (int k = 1; k < K; ++k)
+              if (gs == k) gsel = gk[k];
+            gout[j] = gsel;
+          }
+          if (w_states) {
+            int best = 0;
+            float gbest = gk[0];
+#pragma unroll
+            for (int k = 1; k < K; ++k)
+              if (gk[k] > gbest) {
+                gbest = gk[k];
+                best = k;
+              }
+            sout[j] = (int8_t)best;
+          }
+        }
+        if (j > 0) {
+          float cb[K], nb[K];
+          cb[0] = bv[0];
+#pragma unroll
+          for (int k = 1; k < K; ++k) cb[k] = rt[j][k] * bv[k];
+#pragma unroll
+          for (int i = 0; i < K; ++i) {
+            float s = cb[i];
+#pragma unroll
+            for (int jj = 0; jj < K; ++jj)
+              if (jj != i) s = fmaf(A[i][jj], cb[jj], s);
+            nb[i] = s;
+          }
+          if (((CHT - 1 - j) & 3) == 3) {
+            const float sc = pow2_rescale_noexp(vec_max<K>(nb));
+#pragma unroll
+            for (int k = 0; k < K; ++k) nb[k] *= sc;
+          }
+#pragma unroll
+          for (int k = 0; k < K; ++k) bv[k] = nb[k];
+          if (K == 2) {
+            const float2 t2 = *reinterpret_cast<const float2*>(stack + (j - 1) * 2);
+            alc[0] = t2.x;
+            alc[1 % K] = t2.y;
+          } else if (K == 4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(stack + (j - 1) * 4);
+            alc[0] = t4.x;
+            alc[1 % K] = t4.y;
+            alc[2 % K] = t4.z;
+            alc[3 % K] = t4.w;
+          } else {
+#pragma unroll
+            for (int k = 0; k < K; ++k) alc[k] = stack[(j - 1) * K + k];
+          }
+        }
+      }
+    } else
     {
       float al[K];
       int e = 0;
