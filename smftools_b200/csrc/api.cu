@@ -272,6 +272,36 @@ static int plan_fb2(int K, int64_t L64, bool stats, int S, int es, bool want_gam
     const long long t = (tact + 31) / 32 * 32;
     return (double)L64 / (double)(t * ch);
   };
+  // K = 2 posterior decode of float / uint8 observations has three more chunk lengths compiled (21, 25,
+  // 29: fb2x_k2.cu), which smooths the lane-utilisation sawtooth of medium reads (e.g. 600 positions:
+  // 19 + 13 idle lanes at chunk 17, one full warp at chunk 21).  Score = lane utilisation, mildly
+  // favouring longer chunks (less scan work per position), as measured for 17 vs 33.
+  if (K == 2 && !stats && (es == 4 || es == 1) && (env_ch == 21 || env_ch == 25 || env_ch == 29) &&
+      plan_fb2_chunk(K, env_ch, L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan) == SMF_OK)
+    return SMF_OK;
+  if (K == 2 && !stats && env_ch == 0 && (es == 4 || es == 1)) {
+    static const int cand[5] = {33, 29, 25, 21, 17};
+    bool tried[5] = {false, false, false, false, false};
+    for (int round = 0; round < 5; ++round) {
+      int bi = -1;
+      double bs = -1.0;
+      for (int i = 0; i < 5; ++i) {
+        if (tried[i]) continue;
+        double sc = lane_eff(cand[i]) * (0.8 + 0.2 * (cand[i] - 17) / 16.0);
+        // one resident read per SM around 9-10 kb: the extra warp of chunk 29 beats the longer chunk
+        // (measured 0.59 / 0.66 vs 0.55 / 0.64 of HBM peak at 9 / 10 kb; the other way round at 11 kb)
+        if (cand[i] == 29 && L64 >= 8500 && L64 <= 10500) sc *= 1.06;
+        if (sc > bs) {
+          bs = sc;
+          bi = i;
+        }
+      }
+      tried[bi] = true;
+      if (plan_fb2_chunk(K, cand[bi], L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan) == SMF_OK)
+        return SMF_OK;
+    }
+    return SMF_ERR_TOO_LONG;
+  }
   const bool prefer33 = can33 && (env_ch == 33 || (env_ch == 0 && K == 2 && !stats && lane_eff(33) >= 0.9 * lane_eff(17)));
   if (prefer33 &&
       plan_fb2_chunk(K, 33, L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan) == SMF_OK)
@@ -346,15 +376,16 @@ static inline int obs_elem_size(int dt) { return dt == SMF_OBS_F32 ? 4 : (dt == 
 // ---------------------------------------------------------------------------------------
 // -1 = measured policy, 0 = never, 1 = whenever it fits.  SMF_SHORT / smf_hmm_set_option("short", v).
 static int g_short_mode = [] { const char* e = getenv("SMF_SHORT"); return e ? atoi(e) : -1; }();
-// measured (profiles/r01_short.txt): faster than one read per warp up to ~270 positions (K = 4: ~100)
-static int short_max_len(int K) { return K >= 4 ? 100 : 270; }
+// measured (profiles/r01_short.txt): faster than one read per warp up to ~290 positions for K = 2,
+// ~400 for K = 3, ~100 for K = 4
+static int short_max_len(int K) { return K >= 4 ? 100 : (K == 3 ? 400 : 290); }
 
 // Picks the odd chunk length that keeps the most lanes busy (weighted by how well it amortises the
-// scan) with at least two reads per warp, and lays out the warp's shared-memory region.
+// scan; one or more reads per warp) and lays out the warp's shared-memory region.
 static int plan_short(int K, int64_t L64, int obs_dtype, bool gamma_all, bool gamma_one, bool want_states,
                       int max_smem, ShortArgs* a) {
   const int es = obs_elem_size(obs_dtype);
-  if (L64 < 1 || L64 > 16 * 33) return SMF_ERR_TOO_LONG;
+  if (L64 < 1 || L64 > 32 * 33) return SMF_ERR_TOO_LONG;
   const int L = (int)L64;
   double best = -1.0;
   int bch = 0;
@@ -362,7 +393,7 @@ static int plan_short(int K, int64_t L64, int obs_dtype, bool gamma_all, bool ga
   for (int ch = 5; ch <= 33; ch += 2) {
     if (env_ch && ch != env_ch) continue;
     const int tg = (L + ch - 1) / ch;
-    if (tg > 16) continue;
+    if (tg > 32) continue;
     const int r = 32 / tg;
     const double eff = (double)(r * L) / (32.0 * ch);
     // shared memory per warp decides how many warps hide each other's recurrence latency
@@ -412,6 +443,8 @@ static int launch_fb2(bool stats, const smf_hmm_tables* t, int obs_dtype, Fb2Arg
                       ? 2
                       : (a.gamma_state < 0 ? 0 : 1);
   static const int env_minb = [] { const char* e = getenv("SMF_FB2_MINB"); return e ? atoi(e) : 0; }();
+  if (t->n_states == 2 && (plan.chunk == 21 || plan.chunk == 25 || plan.chunk == 29))
+    return launch_fb2x_k2(plan.chunk, obs_dtype, out, t, a, plan, di, nblocks, stream);
   switch (t->n_states) {
     case 2: return launch_fb2_k2(plan.chunk, stats, obs_dtype, out, env_minb, t, a, plan, di, nblocks, stream);
     case 3: return launch_fb2_k3(plan.chunk, stats, obs_dtype, out, env_minb, t, a, plan, di, nblocks, stream);

@@ -118,13 +118,16 @@ SMF_DECLARE_K(2)
 SMF_DECLARE_K(3)
 SMF_DECLARE_K(4)
 #undef SMF_DECLARE_K
+// extra chunk lengths (21, 25, 29) of the K = 2 posterior kernel (fb2x_k2.cu)
+int launch_fb2x_k2(int chunk, int obs_dtype, int out_mode, const smf_hmm_tables* t, Fb2Args& a, const Fb2Plan& plan,
+                   const DeviceInfo& di, int* nblocks, cudaStream_t s);
 struct WalkArgs;
 struct SweepArgs;
 struct ShortArgs;
 // chunk lengths short_kernel is instantiated for with fully unrolled loops (short_launch.inc)
 static inline bool short_chunk_compiled(int K, int obs_dtype, int ch) {
   if (K > 3 || obs_dtype == SMF_OBS_F64) return false;
-  if (ch == 9 || ch == 17) return true;
+  if (ch == 9 || ch == 11 || ch == 13 || ch == 15 || ch == 17) return true;
   return K == 2 && (ch == 25 || ch == 33);
 }
 int launch_short_k2(int obs_dtype, const smf_hmm_tables* t, const ShortArgs& a, const DeviceInfo& di, cudaStream_t s);
