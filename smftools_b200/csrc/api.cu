@@ -378,12 +378,16 @@ static inline int obs_elem_size(int dt) { return dt == SMF_OBS_F32 ? 4 : (dt == 
 static int g_short_mode = [] { const char* e = getenv("SMF_SHORT"); return e ? atoi(e) : -1; }();
 // measured (profiles/r01_short.txt): faster than one read per warp up to ~290 positions for K = 2,
 // ~400 for K = 3, ~100 for K = 4
-static int short_max_len(int K) { return K >= 4 ? 100 : (K == 3 ? 400 : 290); }
+// (posterior); the E-step variant (K = 2, 3) wins up to ~450
+static int short_max_len(int K, bool stats = false) {
+  if (stats) return 450;
+  return K >= 4 ? 100 : (K == 3 ? 400 : 290);
+}
 
 // Picks the odd chunk length that keeps the most lanes busy (weighted by how well it amortises the
 // scan; one or more reads per warp) and lays out the warp's shared-memory region.
 static int plan_short(int K, int64_t L64, int obs_dtype, bool gamma_all, bool gamma_one, bool want_states,
-                      int max_smem, ShortArgs* a) {
+                      int max_smem, ShortArgs* a, bool stats = false) {
   const int es = obs_elem_size(obs_dtype);
   if (L64 < 1 || L64 > 32 * 33) return SMF_ERR_TOO_LONG;
   const int L = (int)L64;
@@ -394,6 +398,7 @@ static int plan_short(int K, int64_t L64, int obs_dtype, bool gamma_all, bool ga
     if (env_ch && ch != env_ch) continue;
     const int tg = (L + ch - 1) / ch;
     if (tg > 32) continue;
+    if (stats && !short_stats_chunk_compiled(K, obs_dtype, ch)) continue;
     const int r = 32 / tg;
     const double eff = (double)(r * L) / (32.0 * ch);
     // shared memory per warp decides how many warps hide each other's recurrence latency
@@ -743,6 +748,28 @@ int smf_hmm_estep(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int
   const int cadence = rescale_cadence(tab);
   if (tab->n_channels == 1 && tab->n_bins == 1 && !g_force_generic && cadence == 4 &&
       fb2_aligned(obs, obs_dtype, nullptr, tab->n_states, -1)) {
+    // short reads: several reads per warp (E-step variant of short_kernel)
+    if (g_short_mode != 0 && tab->n_states <= 3 && obs_dtype != SMF_OBS_F64 &&
+        (g_short_mode == 1 || n_pos <= short_max_len(tab->n_states, true))) {
+      ShortArgs sa;
+      memset(&sa, 0, sizeof(sa));
+      if (plan_short(tab->n_states, n_pos, obs_dtype, false, false, false, di.max_smem_optin - align_up(kShortWarps * S * 8, 16),
+                     &sa, true) == SMF_OK) {
+        sa.obs = obs;
+        sa.N = n_reads;
+        sa.gamma_state = -1;
+        sa.partials = reinterpret_cast<double*>(workspace);
+        sa.S = S;
+        sa.flush_every = 8;
+        sa.wacc_bytes = align_up(kShortWarps * S * 8, 16);
+        int nb2 = kMaxEstepBlocks;
+        rc = (tab->n_states == 2) ? launch_short_stats_k2(obs_dtype, tab, sa, di, &nb2, st)
+                                  : launch_short_stats_k3(obs_dtype, tab, sa, di, &nb2, st);
+        if (rc != SMF_OK) return rc;
+        reduce_partials_kernel<<<(S + 127) / 128, 128, 0, st>>>(sa.partials, nb2, S, stats);
+        return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
+      }
+    }
     Fb2Args b;
     memset(&b, 0, sizeof(b));
     Fb2Plan p2;

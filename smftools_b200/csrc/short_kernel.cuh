@@ -33,6 +33,10 @@ struct ShortArgs {
   int gamma_state;  // < 0: all states
   int8_t* states;   // [N,L] / nullptr
   double* loglik;   // [N] / nullptr
+  double* partials; // STATS: [gridDim.x][S] per-CTA partial statistics
+  int S;            // STATS: statistics length
+  int flush_every;  // STATS: bundles between fp32 -> fp64 flushes
+  int wacc_bytes;   // STATS: CTA-wide fp64 accumulators [warps][S] in front of the warp regions
   int in_bytes;     // one observation buffer
   int stack_off;    // byte offsets inside a warp's region
   int gam_off, st_off;
@@ -43,7 +47,10 @@ struct ShortArgs {
 // (no loop / address / predicate arithmetic, emission ratios cached in registers) and a lane simply
 // skips the copies beyond its chunk; CHT == 0: run-time chunk length a.CH with rolled, software-
 // pipelined loops (any odd length, any observation type).
-template <int K, typename ObsT, int CHT>
+// STATS = true (compile-time chunk only): Baum-Welch E-step -- no outputs; the backward sweep
+// accumulates start / transition / emission statistics and the log-likelihood exactly like
+// fb2_kernel<STATS> (fp32 registers -> per-warp fp64 shared accumulators -> per-CTA partials).
+template <int K, typename ObsT, int CHT, bool STATS = false>
 __global__ void __launch_bounds__(kShortWarps * 32, 2) short_kernel(const __grid_constant__ FbTables<K> tab,
                                                                    const __grid_constant__ ShortArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -59,7 +66,49 @@ __global__ void __launch_bounds__(kShortWarps * 32, 2) short_kernel(const __grid
   const bool last = (li == Tg - 1);
   const int len = (seg < R) ? max(0, min(CH, L - t0)) : 0;
 
-  unsigned char* wbase = smem + (size_t)warp * a.warp_bytes;
+  static_assert(!STATS || CHT > 0, "the E-step variant needs a compile-time chunk length");
+  constexpr int KK = K * K;
+  unsigned char* wbase = smem + (STATS ? a.wacc_bytes : 0) + (size_t)warp * a.warp_bytes;
+  double* wacc = reinterpret_cast<double*>(smem) + (size_t)warp * (STATS ? a.S : 0);
+  if (STATS) {
+    for (int i = lane; i < a.S; i += 32) wacc[i] = 0.0;
+  }
+  constexpr int NXI = STATS ? KK : 1;
+  constexpr int NEM = STATS ? K : 1;
+  float acc_xi[NXI], acc_num[NEM], acc_den[NEM], acc_start[NEM];
+  double acc_ll = 0.0;
+#pragma unroll
+  for (int i = 0; i < NXI; ++i) acc_xi[i] = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NEM; ++i) {
+    acc_num[i] = 0.0f;
+    acc_den[i] = 0.0f;
+    acc_start[i] = 0.0f;
+  }
+  auto flush_stats = [&]() {
+    if (!STATS) return;
+#pragma unroll
+    for (int k = 0; k < NEM; ++k) {
+      const float r0 = warp_sum_f32(acc_start[k]);
+      const float r1 = warp_sum_f32(acc_num[k]);
+      const float r2 = warp_sum_f32(acc_den[k]);
+      if (lane == 0) {
+        wacc[k] += (double)r0;
+        wacc[K + KK + k] += (double)r1;
+        wacc[K + KK + K + k] += (double)r2;
+      }
+      acc_start[k] = 0.0f;
+      acc_num[k] = 0.0f;
+      acc_den[k] = 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < NXI; ++i) {
+      const float r = warp_sum_f32(acc_xi[i]);
+      // the constant factor Ap[i][j] of xi is applied here, once per flush
+      if (lane == 0) wacc[K + i] += (double)r * (double)tab.Ap[(i / K) % K][i % K];
+      acc_xi[i] = 0.0f;
+    }
+  };
   uint64_t* mbar = reinterpret_cast<uint64_t*>(wbase);  // [2]
   unsigned char* in_raw = wbase + 16;
   float* stack = reinterpret_cast<float*>(wbase + a.stack_off) + (size_t)lane * CH * K;
@@ -96,11 +145,11 @@ __global__ void __launch_bounds__(kShortWarps * 32, 2) short_kernel(const __grid
     return m;
   };
 
-  const bool want_ll = (a.loglik != nullptr);
+  const bool want_ll = STATS || (a.loglik != nullptr);
   const int gs = a.gamma_state;
-  const bool w_gamma_all = (a.gamma != nullptr && gs < 0);
-  const bool w_gamma_one = (a.gamma != nullptr && gs >= 0);
-  const bool w_states = (a.states != nullptr);
+  const bool w_gamma_all = !STATS && (a.gamma != nullptr && gs < 0);
+  const bool w_gamma_one = !STATS && (a.gamma != nullptr && gs >= 0);
+  const bool w_states = !STATS && (a.states != nullptr);
   const char* obs_base = static_cast<const char*>(a.obs);
   const long long nbundles = (a.N + R - 1) / R;
   const long long wstride = (long long)gridDim.x * kShortWarps;
@@ -138,6 +187,13 @@ __global__ void __launch_bounds__(kShortWarps * 32, 2) short_kernel(const __grid
     float ll_sumo = 0.0f;
     int ll_cnt = 0;
     float rt[NRT][K];  // cached emission ratios (compile-time chunk only)
+    using mask_t = typename std::conditional<(CHT > 32), unsigned long long, unsigned>::type;
+    mask_t obsmask = 0;      // bit j: position t0 + j observed (E-step)
+    bool prev_obs0 = false;  // position just before the chunk observed (xi needs both ends, HMM.py:1583-1591)
+    if (STATS && active && !first) {
+      const float op = obs_to_float<ObsT>(s_in[-1]);  // same read, previous lane's last position
+      prev_obs0 = (op == op);
+    }
     if constexpr (CHT > 0) {
       // Positions past the end of the chunk (ragged last chunk of a read, idle lanes) are treated as
       // missing observations: they leave the posteriors of the real positions unchanged (beta of the
@@ -148,6 +204,7 @@ __global__ void __launch_bounds__(kShortWarps * 32, 2) short_kernel(const __grid
         const float o = (j < mylen) ? obs_to_float<ObsT>(s_in[j]) : kMissing;
         float c[K];
         const bool m = ratios(o, c);
+        if (STATS) obsmask |= m ? ((mask_t)1 << j) : (mask_t)0;
 #pragma unroll
         for (int k = 0; k < K; ++k) rt[j][k] = c[k];
         if (want_ll && m) {
@@ -348,6 +405,20 @@ __global__ void __launch_bounds__(kShortWarps * 32, 2) short_kernel(const __grid
         const float gr = rcp_approx(gsum);
 #pragma unroll
         for (int k = 0; k < K; ++k) gk[k] *= gr;
+        if (STATS) {
+          const bool mj = ((obsmask >> j) & (mask_t)1) != 0;  // pads are never observed
+          if (j == 0 && first && active) {
+#pragma unroll
+            for (int k = 0; k < NEM; ++k) acc_start[k] += gk[k];
+          }
+          const float oj = mj ? obs_to_float<ObsT>(s_in[j]) : 0.0f;
+#pragma unroll
+          for (int k = 0; k < NEM; ++k) {
+            const float g = mj ? gk[k] : 0.0f;
+            acc_num[k] = fmaf(g, oj, acc_num[k]);
+            acc_den[k] += g;
+          }
+        }
         if (real) {
           if (w_gamma_all) {
             if (K == 2) {
@@ -375,7 +446,7 @@ __global__ void __launch_bounds__(kShortWarps * 32, 2) short_kernel(const __grid
             sout[j] = (int8_t)best;
           }
         }
-        if (j > 0) {
+        if (j > 0 || STATS) {
           float cb[K], nb[K];
           cb[0] = bv[0];
 #pragma unroll
@@ -388,14 +459,45 @@ __global__ void __launch_bounds__(kShortWarps * 32, 2) short_kernel(const __grid
               if (jj != i) s = fmaf(A[i][jj], cb[jj], s);
             nb[i] = s;
           }
-          if (((CHT - 1 - j) & 3) == 3) {
+          if (STATS) {
+            // xi_{t-1}(i,jj) ~ alpha_{t-1}(i) Ap[i][jj] cb[jj], t = t0 + j > 0, both ends observed
+            float alp[K];
+            if (j > 0) {
+              if (K == 2) {
+                const float2 t2 = *reinterpret_cast<const float2*>(stack + (j > 0 ? j - 1 : 0) * 2);
+                alp[0] = t2.x;
+                alp[1 % K] = t2.y;
+              } else {
+#pragma unroll
+                for (int k = 0; k < K; ++k) alp[k] = stack[(j > 0 ? j - 1 : 0) * K + k];
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < K; ++k) alp[k] = v[k];
+            }
+            const bool prev_obs = (j > 0) ? (((obsmask >> (j > 0 ? j - 1 : 0)) & (mask_t)1) != 0) : prev_obs0;
+            const bool valid = (((obsmask >> j) & (mask_t)1) != 0) && prev_obs && !(j == 0 && first);
+            float s2 = 0.0f;
+#pragma unroll
+            for (int i = 0; i < K; ++i) s2 = fmaf(alp[i], nb[i], s2);
+            const float r2 = valid ? rcp_approx(s2) : 0.0f;
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+              const float ai = alp[i] * r2;
+#pragma unroll
+              for (int jj = 0; jj < K; ++jj) acc_xi[(i * K + jj) % NXI] = fmaf(ai, cb[jj], acc_xi[(i * K + jj) % NXI]);
+            }
+          }
+          if (j > 0 && ((CHT - 1 - j) & 3) == 3) {
             const float sc = pow2_rescale_noexp(vec_max<K>(nb));
 #pragma unroll
             for (int k = 0; k < K; ++k) nb[k] *= sc;
           }
 #pragma unroll
           for (int k = 0; k < K; ++k) bv[k] = nb[k];
-          if (K == 2) {
+          if (j == 0) {
+            // nothing left to do in this chunk
+          } else if (K == 2) {
             const float2 t2 = *reinterpret_cast<const float2*>(stack + (j - 1) * 2);
             alc[0] = t2.x;
             alc[1 % K] = t2.y;
@@ -531,17 +633,21 @@ __global__ void __launch_bounds__(kShortWarps * 32, 2) short_kernel(const __grid
       }
     }
 
+    if (STATS) {
+      acc_ll += ll_thread;
+      if (((it + 1) % a.flush_every) == 0) flush_stats();
+    }
     // ---------------- store: one bulk store per output for the whole bundle ----------------
     fence_proxy_async();
     __syncwarp();
-    {
+    if (!STATS) {
       const uint32_t npos = (uint32_t)(nr * L);
       if (w_gamma_all) store_row_bulk<float>(a.gamma + (size_t)n0 * L * K, s_gam, npos * K * 4u, lane);
       if (w_gamma_one) store_row_bulk<float>(a.gamma + (size_t)n0 * L, s_gam, npos * 4u, lane);
       if (w_states) store_row_bulk<int8_t>(a.states + (size_t)n0 * L, s_st, npos, lane);
       if (lane == 0) bulk_commit();
     }
-    if (want_ll) {
+    if (!STATS && want_ll) {
       // segmented sum over the lanes of a read
       double s = ll_thread;
       for (int d = 1; d < Tg; d <<= 1) {
@@ -554,6 +660,18 @@ __global__ void __launch_bounds__(kShortWarps * 32, 2) short_kernel(const __grid
     __syncwarp();  // every lane is done with this observation buffer before it is refilled
   }
   if (lane == 0) bulk_wait_all();
+  if (STATS) {
+    flush_stats();
+    const double wl = warp_sum_f64(acc_ll);
+    if (lane == 0) wacc[a.S - 1] += wl;
+    __syncthreads();
+    const double* all = reinterpret_cast<const double*>(smem);
+    for (int sidx = threadIdx.x; sidx < a.S; sidx += blockDim.x) {
+      double tot = 0.0;
+      for (int wv = 0; wv < kShortWarps; ++wv) tot += all[(size_t)wv * a.S + sidx];
+      a.partials[(size_t)blockIdx.x * a.S + sidx] = tot;
+    }
+  }
 }
 
 }  // namespace smf

@@ -83,3 +83,45 @@ def test_short_kernel_large_batch_unaligned_rows(short_off):
     idx = np.r_[0:100, N - 100:N]
     g_ref, ll_ref = O.posterior(X32[idx].astype(np.float64), p)
     assert np.abs(g[torch.from_numpy(idx).to(dev)].cpu().numpy() - g_ref).max() <= GAMMA_TOL
+
+
+@pytest.mark.parametrize("K", [2, 3])
+@pytest.mark.parametrize("L", [1, 2, 5, 34, 100, 170, 257])
+def test_short_estep_matches_oracle(K, L, short_off):
+    """Baum-Welch statistics from the bundled short-read kernel vs the oracle and vs one read per warp."""
+    from smftools_b200 import engine
+
+    dev = torch.device("cuda")
+    N = 1203
+    p = O.synth_params(K)
+    tables = model_from_params(p)._host_tables()
+    X32 = O.synth_reads(N, L, K, 80 + K + L, prob=(L % 2 == 0), nan_rate=0.3)
+    ref = O.stats_vector(O.estep(X32.astype(np.float64), p, None))
+    scale = np.maximum(np.abs(ref), 1.0)
+    obs = torch.from_numpy(X32).to(dev)
+    short_off(1)
+    st = engine.estep(tables, obs, None).cpu().numpy()
+    assert np.all(np.abs(st - ref) / scale <= 2e-6), (np.abs(st - ref) / scale).max()
+    assert np.array_equal(st, engine.estep(tables, obs, None).cpu().numpy())  # deterministic reduction
+    if L % 2 == 1:
+        X8 = np.where(np.isnan(X32), 255, X32).astype(np.uint8)
+        st8 = engine.estep(tables, torch.from_numpy(X8).to(dev), None).cpu().numpy()
+        assert np.all(np.abs(st8 - ref) / scale <= 2e-6)
+    short_off(0)
+    st0 = engine.estep(tables, obs, None).cpu().numpy()
+    assert np.all(np.abs(st0 - st) / scale <= 4e-6)
+
+
+def test_short_fit_matches_oracle(short_off):
+    """A short-read fit (the reference's amplicon case) goes through the bundled E-step end to end."""
+    K, L, N = 2, 170, 4000
+    p0 = O.init_params(K, init_emission=[0.8, 0.2])
+    X32 = O.synth_reads(N, L, K, 91, prob=False, nan_rate=0.3)
+    p_ref, hist_ref = O.fit(X32.astype(np.float64), p0, None, max_iter=4, tol=0.0)
+    m = model_from_params(p0)
+    hist = m.fit(X32, None, max_iter=4, tol=0.0)
+    assert np.allclose(hist, hist_ref, rtol=1e-6)
+    sd = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+    assert np.abs(sd["trans"] - p_ref.trans).max() <= 1e-4
+    assert np.abs(sd["emission"].ravel() - p_ref.emission.ravel()).max() <= 1e-4
+    assert np.abs(sd["start"] - p_ref.start).max() <= 1e-4
