@@ -386,6 +386,10 @@ def run_ours(args, wl):
             max_intervals=int(N) * 64)
 
     launches = {"n": 0}
+    # E-step launches per call: two-kernel path (walk + sweeps + reduce) for K = 4 and long K = 3 batches
+    # (api.cu walk_eligible), otherwise one forward-backward kernel + reduce
+    two_kernel = N >= 8192 and (K == 4 or (K == 3 and L > 8704))
+    estep_launches = 3 if two_kernel else 2
 
     def step():
         if op == "posterior":
@@ -399,7 +403,7 @@ def run_ours(args, wl):
             launches["n"] += 2
         else:
             engine.estep(tables, obs, None, out_stats=stats, workspace=ws)
-            launches["n"] += 2
+            launches["n"] += estep_launches
             if world > 1:
                 dist.all_reduce(stats)
 
@@ -518,7 +522,9 @@ def run_ours(args, wl):
                          "algorithmic_bytes_per_read_position": algo, "kernel_ms": k_ms,
                          "kernel": {"posterior": "smf::fb2_kernel<K, CH, STATS=false, ...> (one launch per step)",
                                     "viterbi": "smf::viterbi_kernel (+ smf::call_intervals_kernel)",
-                                    "estep": "smf::fb2_kernel<K, CH, STATS=true, ...> (+ reduce_partials_kernel)"}[op]},
+                                    "estep": ("smf::walk_kernel + smf::estep_sweep_kernel (+ reduce_partials_kernel)"
+                                              if two_kernel else
+                                              "smf::fb2_kernel<K, CH, STATS=true, ...> (+ reduce_partials_kernel)")}[op]},
             "baum_welch": bw,
         }
         if world == 1 and not args.no_cpu:
