@@ -279,6 +279,9 @@ static int plan_fb2(int K, int64_t L64, bool stats, int S, int es, bool want_gam
   if (K == 2 && !stats && (es == 4 || es == 1) && (env_ch == 21 || env_ch == 25 || env_ch == 29) &&
       plan_fb2_chunk(K, env_ch, L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan) == SMF_OK)
     return SMF_OK;
+  if (K == 3 && !stats && (es == 4 || es == 1) && (env_ch == 13 || env_ch == 21) &&
+      plan_fb2_chunk(K, env_ch, L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan) == SMF_OK)
+    return SMF_OK;
   if (K == 2 && !stats && env_ch == 0 && (es == 4 || es == 1)) {
     static const int cand[5] = {33, 29, 25, 21, 17};
     bool tried[5] = {false, false, false, false, false};
@@ -298,6 +301,29 @@ static int plan_fb2(int K, int64_t L64, bool stats, int S, int es, bool want_gam
       }
       tried[bi] = true;
       if (plan_fb2_chunk(K, cand[bi], L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan) == SMF_OK)
+        return SMF_OK;
+    }
+    return SMF_ERR_TOO_LONG;
+  }
+  // K = 3 posterior decode: chunks 13 and 21 (fb2x_k3.cu) fill the troughs of the same sawtooth; at equal
+  // lane utilisation 17 is the sweet spot (measured weights 0.88 / 1 / 0.90 for 13 / 17 / 21).
+  if (K == 3 && !stats && env_ch == 0 && (es == 4 || es == 1)) {
+    static const int cand3[3] = {17, 21, 13};
+    static const double w3[3] = {1.0, 0.90, 0.88};
+    bool tried[3] = {false, false, false};
+    for (int round = 0; round < 3; ++round) {
+      int bi = -1;
+      double bs = -1.0;
+      for (int i = 0; i < 3; ++i) {
+        if (tried[i]) continue;
+        const double sc = lane_eff(cand3[i]) * w3[i];
+        if (sc > bs) {
+          bs = sc;
+          bi = i;
+        }
+      }
+      tried[bi] = true;
+      if (plan_fb2_chunk(K, cand3[bi], L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan) == SMF_OK)
         return SMF_OK;
     }
     return SMF_ERR_TOO_LONG;
@@ -450,6 +476,8 @@ static int launch_fb2(bool stats, const smf_hmm_tables* t, int obs_dtype, Fb2Arg
   static const int env_minb = [] { const char* e = getenv("SMF_FB2_MINB"); return e ? atoi(e) : 0; }();
   if (t->n_states == 2 && (plan.chunk == 21 || plan.chunk == 25 || plan.chunk == 29))
     return launch_fb2x_k2(plan.chunk, obs_dtype, out, t, a, plan, di, nblocks, stream);
+  if (t->n_states == 3 && (plan.chunk == 13 || plan.chunk == 21))
+    return launch_fb2x_k3(plan.chunk, obs_dtype, out, t, a, plan, di, nblocks, stream);
   switch (t->n_states) {
     case 2: return launch_fb2_k2(plan.chunk, stats, obs_dtype, out, env_minb, t, a, plan, di, nblocks, stream);
     case 3: return launch_fb2_k3(plan.chunk, stats, obs_dtype, out, env_minb, t, a, plan, di, nblocks, stream);
