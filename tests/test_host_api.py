@@ -189,6 +189,37 @@ def test_c_abi_exports_every_declared_symbol():
         _lib.check(_lib.SMF_ERR_CUDA, "x")
 
 
+def test_tuning_options_and_workspace_policy():
+    """smf_hmm_set_option / smf_hmm_workspace_bytes are pure host logic (no CUDA call)."""
+    lib = _lib.load()
+    assert lib.smf_hmm_set_option(b"walk", 2) == _lib.SMF_ERR_BAD_ARG
+    assert lib.smf_hmm_set_option(b"short", -2) == _lib.SMF_ERR_BAD_ARG
+    assert lib.smf_hmm_set_option(b"no_such_key", 0) == _lib.SMF_ERR_BAD_ARG
+    assert lib.smf_hmm_set_option(None, 0) == _lib.SMF_ERR_BAD_ARG
+    t2 = S.create_hmm({"hmm_n_states": 2}, arch="single")._host_tables()
+    t4 = S.create_hmm({"hmm_n_states": 4}, arch="single")._host_tables()
+    t4m = S.create_hmm({"hmm_n_states": 4, "hmm_n_channels": 2}, arch="multi")._host_tables()
+    S4 = int(lib.smf_hmm_stats_len(t4.ref))
+    partials = 148 * 8 * S4 * 8
+    try:
+        # measured policy: two-kernel path (and its boundary-vector workspace) for large K = 4 batches only
+        assert lib.smf_hmm_workspace_bytes(_lib.OP_POSTERIOR, t2.ref, 100_000, 500) == 0
+        assert lib.smf_hmm_workspace_bytes(_lib.OP_POSTERIOR, t4.ref, 100, 500) == 0
+        assert lib.smf_hmm_workspace_bytes(_lib.OP_POSTERIOR, t4m.ref, 100_000, 500) == 0
+        need = lib.smf_hmm_workspace_bytes(_lib.OP_POSTERIOR, t4.ref, 100_000, 500)
+        assert need == 2 * 30 * 100_000 * 4 * 4 + 100_000 * 8  # 2 x ceil(500/17) chunks x N x K floats + N doubles
+        assert lib.smf_hmm_workspace_bytes(_lib.OP_ESTEP, t4.ref, 100_000, 500) == partials + need
+        assert lib.smf_hmm_workspace_bytes(_lib.OP_ESTEP, t4.ref, 100, 500) == partials
+        assert lib.smf_hmm_set_option(b"walk", 0) == _lib.SMF_OK
+        assert lib.smf_hmm_workspace_bytes(_lib.OP_POSTERIOR, t4.ref, 100_000, 500) == 0
+        assert lib.smf_hmm_workspace_bytes(_lib.OP_ESTEP, t4.ref, 100_000, 500) == partials
+        assert lib.smf_hmm_set_option(b"walk", 1) == _lib.SMF_OK
+        assert lib.smf_hmm_workspace_bytes(_lib.OP_POSTERIOR, t4.ref, 100, 500) > 0
+    finally:
+        assert lib.smf_hmm_set_option(b"walk", -1) == _lib.SMF_OK
+        assert lib.smf_hmm_set_option(b"short", -1) == _lib.SMF_OK
+
+
 def test_log_tables_are_the_reference_expressions():
     m = S.create_hmm({"hmm_n_states": 2, "hmm_init_emission_probs": [0.9, 0.07]}, arch="single")
     t = m._host_tables()
