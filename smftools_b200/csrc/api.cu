@@ -971,7 +971,16 @@ int smf_hmm_call_features(const int8_t* states, const float* post, int target_st
     long long blocks = (warps_needed + kFeatWarps - 1) / kFeatWarps;
     const long long capb = (long long)di.num_sms * 8;
     if (blocks > capb) blocks = capb;
-    call_intervals_kernel<<<(int)blocks, kFeatThreads, 0, (cudaStream_t)stream>>>(ct, a);
+    // rows that start on 16-byte boundaries take the vectorised variant (128-bit loads, bit-mask runs)
+    static const int env_vec = [] { const char* e = getenv("SMF_INTERVALS_VEC"); return e ? atoi(e) : 1; }();
+    const bool vec_states = states != nullptr && (n_pos % 16) == 0 && (reinterpret_cast<uintptr_t>(states) & 15u) == 0;
+    const bool vec_post = post != nullptr && (n_pos % 4) == 0 && (reinterpret_cast<uintptr_t>(post) & 15u) == 0;
+    if (env_vec && vec_states)
+      call_intervals_vec_kernel<false><<<(int)blocks, kFeatThreads, 0, (cudaStream_t)stream>>>(ct, a);
+    else if (env_vec && vec_post)
+      call_intervals_vec_kernel<true><<<(int)blocks, kFeatThreads, 0, (cudaStream_t)stream>>>(ct, a);
+    else
+      call_intervals_kernel<<<(int)blocks, kFeatThreads, 0, (cudaStream_t)stream>>>(ct, a);
     return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
   }
   long long cap = (long long)di.num_sms * occ;

@@ -228,6 +228,105 @@ __global__ void __launch_bounds__(kFeatThreads) call_intervals_kernel(const __gr
   }
 }
 
+// Vectorised variant of call_intervals_kernel for 16-byte aligned rows (L % 16 == 0): a warp still owns
+// a read, but walks it in super-blocks of 1024 positions -- each lane loads its 32 positions with
+// 128-bit loads and folds them into one membership word with byte-compare / nibble-gather
+// arithmetic (1 instruction per position instead of a load + compare + ballot per position).
+// A run end at bit i of a lane's word finds its start from the clear bits below i, or -- when the
+// run began before the word -- from a warp-level exclusive max-scan of the lanes' last clear
+// positions (plus the carry from earlier super-blocks).  Lanes with several ends take them in rounds;
+// each round appends its records through one warp-aggregated atomic.  Same records as
+// call_intervals_kernel (order within the output is unspecified in both).
+template <bool POST>
+__global__ void __launch_bounds__(kFeatThreads) call_intervals_vec_kernel(const __grid_constant__ ClassTable ct,
+                                                                           const __grid_constant__ FeatArgs a) {
+  constexpr unsigned kFull = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  const int L = a.L;
+  const uint32_t target4 = (uint32_t)(uint8_t)a.target * 0x01010101u;
+  for (long long n = warp0; n < a.N; n += nwarps) {
+    const int8_t* srow = POST ? nullptr : a.states + n * (long long)L;
+    const float* prow = POST ? a.post + n * (long long)L : nullptr;
+    int carry_lz = -1;        // last non-member position before this super-block (-1: none)
+    unsigned carry_bit = 0;   // membership of the position just before this super-block
+    for (int base = 0; base <= L; base += 1024) {
+      const int p0 = base + 32 * lane;
+      unsigned m = 0;
+      if (!POST) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (p0 + 16 * h < L) {
+            const uint4 x = __ldg(reinterpret_cast<const uint4*>(srow + p0 + 16 * h));
+            const uint32_t c[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              m |= ((((__vcmpeq4(c[q], target4)) & 0x01010101u) * 0x01020408u) >> 24) << (16 * h + 4 * q);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (p0 + 4 * q < L) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(prow + p0 + 4 * q));
+            const unsigned nib = (x.x >= a.thr ? 1u : 0u) | (x.y >= a.thr ? 2u : 0u) | (x.z >= a.thr ? 4u : 0u) |
+                                 (x.w >= a.thr ? 8u : 0u);
+            m |= nib << (4 * q);
+          }
+        }
+      }
+      // membership of the position before my word
+      unsigned prevbit = __shfl_up_sync(kFull, m >> 31, 1);
+      if (lane == 0) prevbit = carry_bit;
+      unsigned ends = ~m & ((m << 1) | prevbit);  // bit i: a run ended at position p0 + i (exclusive)
+      // last clear position at or before the end of each lane's word: exclusive max-scan over lanes
+      const unsigned z = ~m;
+      const int lz = z ? (p0 + 31 - __clz(z)) : -1;
+      int inc = lz;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(kFull, inc, d);
+        if (lane >= d) inc = max(inc, o);
+      }
+      int before = __shfl_up_sync(kFull, inc, 1);
+      if (lane == 0) before = -1;
+      before = max(before, carry_lz);
+      // run ends, one per lane and round
+      while (__any_sync(kFull, ends != 0u)) {
+        bool keep = false;
+        int gs = 0, ge = 0, cls = -1;
+        if (ends) {
+          const int i = __ffs(ends) - 1;
+          ends &= ends - 1u;
+          const int e0 = p0 + i;
+          const unsigned zb = z & ((1u << i) - 1u);  // clear bits below the end
+          const int s0 = (zb ? (p0 + 31 - __clz(zb)) : before) + 1;
+          const long long glen = __ldg(a.coords + e0 - 1) - __ldg(a.coords + s0) + 1;
+          gs = __ldg(a.grid_left + s0);
+          ge = __ldg(a.grid_right + e0 - 1);
+          if (glen > 0) cls = pick_class(ct, (double)glen);
+          keep = (cls >= 0) && (gs < ge);
+        }
+        const unsigned bk = __ballot_sync(kFull, keep);
+        if (bk) {
+          unsigned long long basei = 0;
+          if (lane == 0) basei = atomicAdd(a.n_intervals, (unsigned long long)__popc(bk));
+          basei = __shfl_sync(kFull, basei, 0);
+          if (keep) {
+            const unsigned long long slot = basei + __popc(bk & lt);
+            if (slot < (unsigned long long)a.max_intervals)
+              *reinterpret_cast<int4*>(a.intervals + slot * 4) = make_int4((int)n, gs, ge, cls);
+          }
+        }
+      }
+      carry_lz = max(carry_lz, __shfl_sync(kFull, inc, 31));
+      carry_bit = __shfl_sync(kFull, m >> 31, 31);
+    }
+  }
+}
+
 struct MergeArgs {
   const uint8_t* layer;  // [N, V]
   long long N;

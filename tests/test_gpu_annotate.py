@@ -101,7 +101,9 @@ def test_annotate_in_small_read_chunks_gives_identical_layers(name):
     assert ad2.layers["GpC_states"].dtype == np.int8 and not np.isnan(ad2.layers["GpC_posterior_modified"]).any()
 
 
-@pytest.mark.parametrize("N,L,seed", [(257, 700, 1), (64, 3001, 2), (1, 40, 3), (300, 5, 4)])
+@pytest.mark.parametrize("N,L,seed", [(257, 700, 1), (64, 3001, 2), (1, 40, 3), (300, 5, 4),
+                                      # rows on 16-byte boundaries: vectorised interval kernel (1024-position super-blocks)
+                                      (130, 2048, 5), (33, 1024, 6), (70, 4112, 7), (9, 16, 8), (40, 1040, 9)])
 def test_feature_kernels_against_oracle(N, L, seed):
     from smftools_b200 import engine
 
@@ -151,6 +153,12 @@ def test_feature_kernels_against_oracle(N, L, seed):
             coords=torch.from_numpy(coords).to(dev), grid_left=torch.from_numpy(left).to(dev),
             grid_right=torch.from_numpy(right).to(dev), n_grid=V, ranges=ranges)
         assert torch.equal(cls_p, cls_d) and torch.equal(len_p, len_d)
+        _, _, iv3 = engine.call_features(
+            states=None, post=torch.from_numpy(post).to(dev), target=target, threshold=0.5,
+            coords=torch.from_numpy(coords).to(dev), grid_left=torch.from_numpy(left).to(dev),
+            grid_right=torch.from_numpy(right).to(dev), n_grid=V, ranges=ranges, want_dense=False,
+            max_intervals=N * (L // 2 + 2))
+        np.testing.assert_array_equal(key(iv3.cpu().numpy()), key(iv))
         # merge + size classes
         for dt in (0, 10, 60):
             mg, ml = O.merge_runs(all_l, full, dt)
