@@ -156,8 +156,9 @@ __global__ void __launch_bounds__(kVitReads, 4) viterbi_kernel(const __grid_cons
     if (tile0 + kVitTile < L) fetch_tile(tile0 + kVitTile);  // loads stay in flight during the decode below
     if (live) {
       const obs_t* my = tile + tid * row_stride;
-#pragma unroll 4
-      for (int j = 0; j < tw; ++j) {
+      uint8_t* mybp = bpt + tid * kBpStride;
+      // one position: emission, max-plus step, packed back-pointers.  FIRST_TILE keeps the t == 0 test.
+      auto step = [&](int j, bool first_tile) {
         const int t = tile0 + j;
         double logB[K];
 #pragma unroll
@@ -171,14 +172,14 @@ __global__ void __launch_bounds__(kVitReads, 4) viterbi_kernel(const __grid_cons
             for (int k = 0; k < K; ++k) logB[k] = m ? (o != 0.0 ? tab.l1[k][0] : tab.l0[k][0]) : 0.0;
           } else {
             // branch-free (lanes of a warp hold different reads): the three-rounding expression is
-            // also exact for o in {0, 1}
+            // also exact for o in {0, 1}.  A missing site uses os = om = 0: both products are (signed)
+            // zeros, their sum is a zero, and delta + (+-0) == delta bit for bit -- the same as adding
+            // the reference's masked 0 -- so no per-state select is needed.
             const double os = m ? o : 0.0;
-            const double om = __dsub_rn(1.0, os);
+            const double om = m ? __dsub_rn(1.0, os) : 0.0;
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-              const double val = __dadd_rn(__dmul_rn(os, tab.l1[k][0]), __dmul_rn(om, tab.l0[k][0]));
-              logB[k] = m ? val : 0.0;
-            }
+            for (int k = 0; k < K; ++k)
+              logB[k] = __dadd_rn(__dmul_rn(os, tab.l1[k][0]), __dmul_rn(om, tab.l0[k][0]));
           }
         } else {
           for (int c = 0; c < C; ++c) {
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(kVitReads, 4) viterbi_kernel(const __grid_cons
           }
         }
         unsigned packed = 0;
-        if (t == 0) {
+        if (first_tile && t == 0) {
 #pragma unroll
           for (int k = 0; k < K; ++k) delta[k] = __dadd_rn(tab.log_pi[k], logB[k]);
         } else {
@@ -216,7 +217,15 @@ __global__ void __launch_bounds__(kVitReads, 4) viterbi_kernel(const __grid_cons
 #pragma unroll
           for (int k = 0; k < K; ++k) delta[k] = nd[k];
         }
-        bpt[tid * kBpStride + j] = (uint8_t)packed;
+        mybp[j] = (uint8_t)packed;
+      };
+      if (tile0 > 0 && tw == kVitTile && !MULTI) {
+        // full interior tile: fully unrolled (no loop counter, immediate shared-memory offsets)
+#pragma unroll
+        for (int j = 0; j < kVitTile; ++j) step(j, false);
+      } else {
+#pragma unroll 4
+        for (int j = 0; j < tw; ++j) step(j, true);
       }
     }
     __syncthreads();
