@@ -122,9 +122,8 @@ __global__ void __launch_bounds__(kVitReads, (K >= 4 ? 7 : 8)) walk_kernel(const
       if (ti + 1 < ntiles) fetch_tile(tile0 + kWalkTile);
       if (live) {
         float tsum = 0.0f;  // per-tile partial of sumo (<= 32 terms in fp32, then fp64)
-#pragma unroll 4
-        for (int j = 0; j < tw; ++j) {
-          const int t = tile0 + j;
+        const int ej = next_emit - tile0;  // tile-local position after which v is recorded (chunks are longer than a tile)
+        auto fstep = [&](int j, bool first_tile) {
           const float o = my[j];
           float c[K];
           const bool m = ratios(o, c);
@@ -137,26 +136,33 @@ __global__ void __launch_bounds__(kVitReads, (K >= 4 ? 7 : 8)) walk_kernel(const
 #pragma unroll
             for (int i = 0; i < K; ++i)
               if (i != jj) s = fmaf(al[i], A[i][jj], s);
-            y[jj] = (t == 0) ? al[jj] : s;  // alpha_0 = pi2 * c: no transition
+            y[jj] = (first_tile && j == 0) ? al[jj] : s;  // alpha_0 = pi2 * c: no transition
           }
 #pragma unroll
           for (int k = 1; k < K; ++k) y[k] *= c[k];
-          if ((t & 3) == 3) {
+          if ((j & 3) == 3) {  // tiles start at multiples of 16: (t & 3) == (j & 3)
             const float sc = pow2_rescale(vec_max<K>(y), e);
 #pragma unroll
             for (int k = 0; k < K; ++k) y[k] *= sc;
           }
 #pragma unroll
           for (int k = 0; k < K; ++k) al[k] = y[k];
-          if (t == next_emit) {
-            if (chunk_i < a.Tact) {
+          if (j == ej && chunk_i < a.Tact) {
 #pragma unroll
-              for (int k = 0; k < K; ++k) dstv[k] = al[k];
-            }
-            ++chunk_i;
-            dstv += bstride;
-            next_emit += a.CH;
+            for (int k = 0; k < K; ++k) dstv[k] = al[k];
           }
+        };
+        if (ti > 0 && tw == kWalkTile) {
+#pragma unroll
+          for (int j = 0; j < kWalkTile; ++j) fstep(j, false);
+        } else {
+#pragma unroll 4
+          for (int j = 0; j < tw; ++j) fstep(j, ti == 0);
+        }
+        if (ej < tw) {
+          ++chunk_i;
+          dstv += bstride;
+          next_emit += a.CH;
         }
         sumo += (double)tsum;
       }
@@ -185,14 +191,11 @@ __global__ void __launch_bounds__(kVitReads, (K >= 4 ? 7 : 8)) walk_kernel(const
       __syncthreads();
       if (ti > 0) fetch_tile(tile0 - kWalkTile);
       if (live) {
-#pragma unroll 4
-        for (int j = tw - 1; j >= 0; --j) {
-          const int t = tile0 + j;
-          if (t == wpos) {  // bv == beta_t
+        const int wj = wpos - tile0;  // tile-local position whose beta is recorded (at most one per tile)
+        auto bstep = [&](int j) {
+          if (j == wj) {  // bv == beta_t
 #pragma unroll
             for (int k = 0; k < K; ++k) dstw[k] = bv[k];
-            dstw -= bstride;
-            wpos -= a.CH;
           }
           const float o = my[j];
           float c[K];
@@ -209,13 +212,24 @@ __global__ void __launch_bounds__(kVitReads, (K >= 4 ? 7 : 8)) walk_kernel(const
               if (jj != i) s = fmaf(A[i][jj], cb[jj], s);
             nb[i] = s;
           }
-          if ((t & 3) == 0) {
+          if ((j & 3) == 0) {
             const float sc = pow2_rescale_noexp(vec_max<K>(nb));
 #pragma unroll
             for (int k = 0; k < K; ++k) nb[k] *= sc;
           }
 #pragma unroll
           for (int k = 0; k < K; ++k) bv[k] = nb[k];
+        };
+        if (tw == kWalkTile) {
+#pragma unroll
+          for (int j = kWalkTile - 1; j >= 0; --j) bstep(j);
+        } else {
+#pragma unroll 4
+          for (int j = tw - 1; j >= 0; --j) bstep(j);
+        }
+        if (wj >= 0 && wj < tw) {
+          dstw -= bstride;
+          wpos -= a.CH;
         }
       }
     }
