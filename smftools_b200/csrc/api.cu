@@ -402,12 +402,12 @@ static inline int obs_elem_size(int dt) { return dt == SMF_OBS_F32 ? 4 : (dt == 
 // ---------------------------------------------------------------------------------------
 // -1 = measured policy, 0 = never, 1 = whenever it fits.  SMF_SHORT / smf_hmm_set_option("short", v).
 static int g_short_mode = [] { const char* e = getenv("SMF_SHORT"); return e ? atoi(e) : -1; }();
-// measured (profiles/r01_short.txt): faster than one read per warp up to ~290 positions for K = 2,
+// measured (profiles/r01_short.txt): faster than one read per warp up to ~340 positions for K = 2,
 // ~400 for K = 3, ~100 for K = 4
 // (posterior); the E-step variant (K = 2, 3) wins up to ~450
 static int short_max_len(int K, bool stats = false) {
   if (stats) return 450;
-  return K >= 4 ? 100 : (K == 3 ? 400 : 290);
+  return K >= 4 ? 100 : (K == 3 ? 400 : 340);
 }
 
 // Picks the odd chunk length that keeps the most lanes busy (weighted by how well it amortises the
@@ -430,7 +430,7 @@ static int plan_short(int K, int64_t L64, int obs_dtype, bool gamma_all, bool ga
     // shared memory per warp decides how many warps hide each other's recurrence latency
     const int kout_c = gamma_all ? K : (gamma_one ? 1 : 0);
     const double wb = 16.0 + 2.0 * (r * L * es + 32) + 32.0 * ch * K * 4 + r * L * kout_c * 4.0 + (want_states ? r * L : 0) + 64;
-    const double warps = 227.0 * 1024.0 / wb;
+    const double warps = kShortWarps * floor(227.0 * 1024.0 / (kShortWarps * wb + 1024.0));  // whole CTAs
     if (kShortWarps * wb > max_smem) continue;
     double score = eff * ch / (ch + 6.0) * (warps >= 16.0 ? 1.0 : warps / 16.0);
     // fully unrolled instantiations run ~2.5x fewer instructions per position than the rolled variant

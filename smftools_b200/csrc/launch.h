@@ -130,7 +130,7 @@ struct ShortArgs;
 static inline bool short_chunk_compiled(int K, int obs_dtype, int ch) {
   if (K > 3 || obs_dtype == SMF_OBS_F64) return false;
   if (ch == 9 || ch == 11 || ch == 13 || ch == 15 || ch == 17) return true;
-  return K == 2 && (ch == 25 || ch == 33);
+  return K == 2 && (ch == 19 || ch == 21 || ch == 23 || ch == 25 || ch == 33);
 }
 // chunk lengths the E-step variant of short_kernel is instantiated for
 static inline bool short_stats_chunk_compiled(int K, int obs_dtype, int ch) {

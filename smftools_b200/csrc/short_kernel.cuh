@@ -20,7 +20,7 @@
 
 namespace smf {
 
-constexpr int kShortWarps = 8;
+constexpr int kShortWarps = 4;
 
 struct ShortArgs {
   const void* obs;
@@ -51,7 +51,7 @@ struct ShortArgs {
 // accumulates start / transition / emission statistics and the log-likelihood exactly like
 // fb2_kernel<STATS> (fp32 registers -> per-warp fp64 shared accumulators -> per-CTA partials).
 template <int K, typename ObsT, int CHT, bool STATS = false>
-__global__ void __launch_bounds__(kShortWarps * 32, 2) short_kernel(const __grid_constant__ FbTables<K> tab,
+__global__ void __launch_bounds__(kShortWarps * 32, 4) short_kernel(const __grid_constant__ FbTables<K> tab,
                                                                    const __grid_constant__ ShortArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr unsigned kFull = 0xffffffffu;
