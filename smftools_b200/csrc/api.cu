@@ -361,7 +361,11 @@ static bool walk_eligible(const smf_hmm_tables* t, int64_t N, int64_t L, bool st
   if (env_walk == 1) return true;
   if (N < kWalkMinReads) return false;
   if (stats) return K == 4 || L > (int64_t)17 * fb2_max_threads_c(K, true);
-  return K == 4 && L <= 6000;
+  // posterior: K = 4 up to ~6 kb and where the single kernel has left its chunk-17 range but the
+  // two-kernel path still has its own (8.7-10.9 kb: 0.31 vs 0.22 of HBM peak at 9 kb); K = 3 beyond the
+  // single kernel's reach (13.4 kb with chunk 21): 0.27 vs 0.10 (generic kernel) at 16 kb
+  if (K == 4) return L <= 6000 || (L > (int64_t)17 * fb2_max_threads_c(4, false) && L <= (int64_t)17 * fb2w_max_threads_c(4, false));
+  return L > (int64_t)21 * fb2_max_threads_c(3, false);
 }
 // boundary vectors for the shorter chunk (an upper bound for the longer one) + per-read log-likelihoods
 static size_t walk_ws_bytes(int K, int64_t N, int64_t L) {
@@ -403,11 +407,11 @@ static inline int obs_elem_size(int dt) { return dt == SMF_OBS_F32 ? 4 : (dt == 
 // -1 = measured policy, 0 = never, 1 = whenever it fits.  SMF_SHORT / smf_hmm_set_option("short", v).
 static int g_short_mode = [] { const char* e = getenv("SMF_SHORT"); return e ? atoi(e) : -1; }();
 // measured (profiles/r01_short.txt): faster than one read per warp up to ~340 positions for K = 2,
-// ~400 for K = 3, ~100 for K = 4
-// (posterior); the E-step variant (K = 2, 3) wins up to ~450
+// ~400 for K = 3, ~200 for K = 4
+// (posterior); the E-step variant wins up to ~450 (K = 2, 3) / ~300 (K = 4)
 static int short_max_len(int K, bool stats = false) {
-  if (stats) return 450;
-  return K >= 4 ? 100 : (K == 3 ? 400 : 340);
+  if (stats) return K >= 4 ? 300 : 450;
+  return K >= 4 ? 200 : (K == 3 ? 400 : 340);
 }
 
 // Picks the odd chunk length that keeps the most lanes busy (weighted by how well it amortises the
@@ -777,7 +781,7 @@ int smf_hmm_estep(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int
   if (tab->n_channels == 1 && tab->n_bins == 1 && !g_force_generic && cadence == 4 &&
       fb2_aligned(obs, obs_dtype, nullptr, tab->n_states, -1)) {
     // short reads: several reads per warp (E-step variant of short_kernel)
-    if (g_short_mode != 0 && tab->n_states <= 3 && obs_dtype != SMF_OBS_F64 &&
+    if (g_short_mode != 0 && obs_dtype != SMF_OBS_F64 &&
         (g_short_mode == 1 || n_pos <= short_max_len(tab->n_states, true))) {
       ShortArgs sa;
       memset(&sa, 0, sizeof(sa));
@@ -791,8 +795,9 @@ int smf_hmm_estep(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int
         sa.flush_every = 8;
         sa.wacc_bytes = align_up(kShortWarps * S * 8, 16);
         int nb2 = kMaxEstepBlocks;
-        rc = (tab->n_states == 2) ? launch_short_stats_k2(obs_dtype, tab, sa, di, &nb2, st)
-                                  : launch_short_stats_k3(obs_dtype, tab, sa, di, &nb2, st);
+        rc = (tab->n_states == 2)   ? launch_short_stats_k2(obs_dtype, tab, sa, di, &nb2, st)
+             : (tab->n_states == 3) ? launch_short_stats_k3(obs_dtype, tab, sa, di, &nb2, st)
+                                    : launch_short_stats_k4(obs_dtype, tab, sa, di, &nb2, st);
         if (rc != SMF_OK) return rc;
         reduce_partials_kernel<<<(S + 127) / 128, 128, 0, st>>>(sa.partials, nb2, S, stats);
         return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;

@@ -128,17 +128,19 @@ struct SweepArgs;
 struct ShortArgs;
 // chunk lengths short_kernel is instantiated for with fully unrolled loops (short_launch.inc)
 static inline bool short_chunk_compiled(int K, int obs_dtype, int ch) {
-  if (K > 3 || obs_dtype == SMF_OBS_F64) return false;
+  if (K > 4 || obs_dtype == SMF_OBS_F64) return false;
   if (ch == 9 || ch == 11 || ch == 13 || ch == 15 || ch == 17) return true;
   return K == 2 && (ch == 19 || ch == 21 || ch == 23 || ch == 25 || ch == 33);
 }
 // chunk lengths the E-step variant of short_kernel is instantiated for
 static inline bool short_stats_chunk_compiled(int K, int obs_dtype, int ch) {
-  return K <= 3 && obs_dtype != SMF_OBS_F64 && (ch == 9 || ch == 13 || ch == 17);
+  return K <= 4 && obs_dtype != SMF_OBS_F64 && (ch == 9 || ch == 13 || ch == 17);
 }
 int launch_short_stats_k2(int obs_dtype, const smf_hmm_tables* t, const ShortArgs& a, const DeviceInfo& di,
                           int* nblocks, cudaStream_t s);
 int launch_short_stats_k3(int obs_dtype, const smf_hmm_tables* t, const ShortArgs& a, const DeviceInfo& di,
+                          int* nblocks, cudaStream_t s);
+int launch_short_stats_k4(int obs_dtype, const smf_hmm_tables* t, const ShortArgs& a, const DeviceInfo& di,
                           int* nblocks, cudaStream_t s);
 int launch_short_k2(int obs_dtype, const smf_hmm_tables* t, const ShortArgs& a, const DeviceInfo& di, cudaStream_t s);
 int launch_short_k3(int obs_dtype, const smf_hmm_tables* t, const ShortArgs& a, const DeviceInfo& di, cudaStream_t s);
