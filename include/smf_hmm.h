@@ -82,7 +82,8 @@ const char* smf_hmm_strerror(int code);
  * Process-wide tuning knobs (not needed for correct results).  Keys:
  *   "walk"   -1 (default) let the library choose between the single-kernel and the two-kernel
  *            forward-backward path from its measured policy; 0 never / 1 whenever possible use the
- *            two-kernel path.  smf_hmm_workspace_bytes() follows the setting.
+ *            two-kernel path; 2 additionally always takes its any-length sweep kernels (posterior: all K).
+ *            smf_hmm_workspace_bytes() follows the setting.
  *   "short"  -1 (default) posterior decode of reads up to ~340 positions runs on the several-reads-
  *            per-warp kernel; 0 never / 1 whenever the read fits it (<= 1056 positions).
  * Returns SMF_ERR_BAD_ARG for an unknown key or value.

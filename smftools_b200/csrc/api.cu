@@ -11,6 +11,7 @@
 #include "features_kernel.cuh"
 #include "launch.h"
 #include "smf_hmm.h"
+#include "post_sweep_kernel.cuh"
 #include "short_kernel.cuh"
 #include "sweep_kernel.cuh"
 #include "walk_kernel.cuh"
@@ -354,17 +355,20 @@ static bool walk_eligible(const smf_hmm_tables* t, int64_t N, int64_t L, bool st
   const int env_walk = g_walk_mode;
   if (env_walk == 0 || g_force_generic) return false;
   const int K = t->n_states;
-  if (K < 3 || t->n_channels != 1 || t->n_bins != 1) return false;
+  if (t->n_channels != 1 || t->n_bins != 1) return false;
   if (L < 2 || L > (1 << 24)) return false;
-  if (!stats && L > (int64_t)33 * fb2w_max_threads_c(K, false)) return false;
   if (rescale_cadence(t) != 4) return false;
+  if (env_walk == 2) return !stats || K >= 3;  // any-length sweep kernels wherever they exist
+  // reads that do not fit on chip: boundary walk + warp-independent sweeps (post_sweep_kernel), any K
+  const bool off_chip = L > (int64_t)33 * fb2w_max_threads_c(K, false);
+  if (K < 3) return !stats && off_chip && N >= kWalkMinReads;
   if (env_walk == 1) return true;
   if (N < kWalkMinReads) return false;
   if (stats) return K == 4 || L > (int64_t)17 * fb2_max_threads_c(K, true);
-  // posterior: K = 4 up to ~6 kb and where the single kernel has left its chunk-17 range but the
-  // two-kernel path still has its own (8.7-10.9 kb: 0.31 vs 0.22 of HBM peak at 9 kb); K = 3 beyond the
-  // single kernel's reach (13.4 kb with chunk 21): 0.27 vs 0.10 (generic kernel) at 16 kb
-  if (K == 4) return L <= 6000 || (L > (int64_t)17 * fb2_max_threads_c(4, false) && L <= (int64_t)17 * fb2w_max_threads_c(4, false));
+  // posterior: K = 4 up to ~6 kb and beyond the single kernel's chunk-17 range (8.7 kb; 0.31 vs 0.22 of
+  // HBM peak at 9 kb); K = 3 beyond the single kernel's reach (13.4 kb with chunk 21): 0.27 vs 0.10
+  // (generic kernel) at 16 kb
+  if (K == 4) return L <= 6000 || L > (int64_t)17 * fb2_max_threads_c(4, false);
   return L > (int64_t)21 * fb2_max_threads_c(3, false);
 }
 // boundary vectors for the shorter chunk (an upper bound for the longer one) + per-read log-likelihoods
@@ -612,7 +616,7 @@ const char* smf_hmm_strerror(int code) {
 int smf_hmm_set_option(const char* key, int value) {
   if (key == nullptr) return SMF_ERR_BAD_ARG;
   if (strcmp(key, "walk") == 0) {
-    if (value < -1 || value > 1) return SMF_ERR_BAD_ARG;
+    if (value < -1 || value > 2) return SMF_ERR_BAD_ARG;
     g_walk_mode = value;
     return SMF_OK;
   }
@@ -704,9 +708,50 @@ int smf_hmm_posterior(const smf_hmm_tables* tab, const void* obs, int obs_dtype,
     // two-kernel path when the caller provided the boundary-vector workspace
     if (workspace != nullptr && walk_eligible(tab, n_reads, n_pos, false)) {
       if (workspace_bytes < walk_ws_bytes(tab->n_states, n_reads, n_pos)) return SMF_ERR_WORKSPACE;
-      if (plan_fb2(tab->n_states, n_pos, false, stats_len(tab), obs_elem_size(obs_dtype),
-                   gamma != nullptr && gamma_state >= 0, states != nullptr, di.max_smem_optin, &b, &p2,
-                   true) == SMF_OK) {
+      const bool on_chip = tab->n_states >= 3 && g_walk_mode != 2 &&
+                           plan_fb2(tab->n_states, n_pos, false, stats_len(tab), obs_elem_size(obs_dtype),
+                                    gamma != nullptr && gamma_state >= 0, states != nullptr, di.max_smem_optin, &b,
+                                    &p2, true) == SMF_OK;
+      // K = 4 beyond the chunk-17 range would run the spilling chunk-33 variant on chip: sweep instead
+      const bool prefer_sweep = tab->n_states == 4 && n_pos > (int64_t)17 * fb2w_max_threads_c(4, false);
+      if (!on_chip || prefer_sweep) {
+        // any read length: boundary walk + warp-independent posterior sweeps
+        const int K = tab->n_states;
+        const int CH = 17;
+        const size_t cap = (size_t)((n_pos + 16) / 17) * (size_t)n_reads * K;
+        char* wws = reinterpret_cast<char*>(workspace);
+        WalkArgs w;
+        w.obs = obs;
+        w.N = n_reads;
+        w.L = (int)n_pos;
+        w.CH = CH;
+        w.Tact = (int)((n_pos + CH - 1) / CH);
+        w.bnd_v = reinterpret_cast<float*>(wws);
+        w.bnd_w = w.bnd_v + cap;
+        w.ll = loglik;
+        cudaStream_t st = (cudaStream_t)stream;
+        rc = (K == 2) ? launch_walk_k2(obs_dtype, tab, w, st)
+                      : (K == 3 ? launch_walk_k3(obs_dtype, tab, w, st) : launch_walk_k4(obs_dtype, tab, w, st));
+        if (rc != SMF_OK) return rc;
+        if (gamma == nullptr && states == nullptr) return SMF_OK;  // log-likelihood only
+        PostSweepArgs ps;
+        memset(&ps, 0, sizeof(ps));
+        ps.obs = obs;
+        ps.N = n_reads;
+        ps.L = (int)n_pos;
+        ps.CH = CH;
+        ps.Tact = w.Tact;
+        ps.slices = (w.Tact + 31) / 32;
+        ps.bnd_v = w.bnd_v;
+        ps.bnd_w = w.bnd_w;
+        ps.gamma = gamma;
+        ps.gamma_state = gamma_state;
+        ps.states = states;
+        return (K == 2) ? launch_post_sweep_k2(obs_dtype, tab, ps, di, st)
+                        : (K == 3 ? launch_post_sweep_k3(obs_dtype, tab, ps, di, st)
+                                  : launch_post_sweep_k4(obs_dtype, tab, ps, di, st));
+      }
+      {
         b.obs = obs;
         b.N = n_reads;
         b.L = (int)n_pos;

@@ -126,6 +126,11 @@ int launch_fb2x_k3(int chunk, int obs_dtype, int out_mode, const smf_hmm_tables*
 struct WalkArgs;
 struct SweepArgs;
 struct ShortArgs;
+struct PostSweepArgs;
+int launch_walk_k2(int obs_dtype, const smf_hmm_tables* t, const WalkArgs& a, cudaStream_t s);
+int launch_post_sweep_k2(int obs_dtype, const smf_hmm_tables* t, PostSweepArgs& a, const DeviceInfo& di, cudaStream_t s);
+int launch_post_sweep_k3(int obs_dtype, const smf_hmm_tables* t, PostSweepArgs& a, const DeviceInfo& di, cudaStream_t s);
+int launch_post_sweep_k4(int obs_dtype, const smf_hmm_tables* t, PostSweepArgs& a, const DeviceInfo& di, cudaStream_t s);
 // chunk lengths short_kernel is instantiated for with fully unrolled loops (short_launch.inc)
 static inline bool short_chunk_compiled(int K, int obs_dtype, int ch) {
   if (K > 4 || obs_dtype == SMF_OBS_F64) return false;

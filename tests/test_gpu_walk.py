@@ -93,3 +93,38 @@ def test_walk_estep_matches_oracle(K, L):
     assert np.all(np.abs(stats - ref) / scale <= 2e-6), (np.abs(stats - ref) / scale).max()
     stats2 = engine.estep(tables, obs, None).cpu().numpy()
     assert np.array_equal(stats, stats2)
+
+
+@pytest.mark.parametrize("K,L,N", [(2, 2, 50), (2, 45, 130), (3, 600, 77), (4, 1203, 41), (2, 5000, 19), (3, 5001, 13),
+                                    # beyond the on-chip reach of every single-kernel variant
+                                    (2, 30000, 12), (4, 12000, 20), (3, 23000, 10)])
+def test_any_length_posterior_sweeps(K, L, N):
+    """walk_kernel + post_sweep_kernel (option "walk" = 2): warp-independent slices, no read-length limit."""
+    from smftools_b200 import engine
+
+    dev = torch.device("cuda")
+    p = O.synth_params(K)
+    tables = model_from_params(p)._host_tables()
+    X32 = O.synth_reads(N, L, K, 70 + K + L % 97, prob=(L % 2 == 0), nan_rate=0.3)
+    g_ref, ll_ref = O.posterior(X32.astype(np.float64), p)
+    obs = torch.from_numpy(X32).to(dev)
+    engine.set_option("walk", 2)
+    engine.set_option("short", 0)
+    try:
+        g, s, ll = engine.posterior(tables, obs, None, want_loglik=True)
+        assert np.abs(g.cpu().numpy() - g_ref).max() <= GAMMA_TOL
+        assert np.allclose(ll.cpu().numpy(), ll_ref, rtol=LL_RTOL, atol=2e-6)
+        assert_states_match_up_to_ties(s.cpu().numpy().astype(np.int64), g_ref.argmax(axis=2), g_ref)
+        g1, s1, _ = engine.posterior(tables, obs, None, gamma_state=K - 1)
+        assert torch.equal(s1, s) and (g1 - g[:, :, K - 1]).abs().max().item() <= 1e-6
+        _, s2, _ = engine.posterior(tables, obs, None, want_gamma=False)
+        assert torch.equal(s2, s)
+        X8 = np.where(np.isnan(X32), 255, (X32 > 0.5)).astype(np.uint8)
+        g8_ref, _ = O.posterior(np.where(X8 == 255, np.nan, X8).astype(np.float64), p)
+        g8, _, _ = engine.posterior(tables, torch.from_numpy(X8).to(dev), None)
+        assert np.abs(g8.cpu().numpy() - g8_ref).max() <= GAMMA_TOL
+        g64, _, _ = engine.posterior(tables, torch.from_numpy(X32.astype(np.float64)).to(dev), None)
+        assert (g64 - g).abs().max().item() <= 1e-6
+    finally:
+        engine.set_option("walk", -1)
+        engine.set_option("short", -1)

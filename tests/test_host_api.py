@@ -192,7 +192,7 @@ def test_c_abi_exports_every_declared_symbol():
 def test_tuning_options_and_workspace_policy():
     """smf_hmm_set_option / smf_hmm_workspace_bytes are pure host logic (no CUDA call)."""
     lib = _lib.load()
-    assert lib.smf_hmm_set_option(b"walk", 2) == _lib.SMF_ERR_BAD_ARG
+    assert lib.smf_hmm_set_option(b"walk", 3) == _lib.SMF_ERR_BAD_ARG
     assert lib.smf_hmm_set_option(b"short", -2) == _lib.SMF_ERR_BAD_ARG
     assert lib.smf_hmm_set_option(b"no_such_key", 0) == _lib.SMF_ERR_BAD_ARG
     assert lib.smf_hmm_set_option(None, 0) == _lib.SMF_ERR_BAD_ARG
