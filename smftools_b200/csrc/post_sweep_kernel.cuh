@@ -33,14 +33,18 @@ struct PostSweepArgs {
   int warp_bytes;
 };
 
-template <int K, typename ObsT>
+// CHT > 0: compile-time chunk length -- fully unrolled sweeps, emission ratios cached in registers,
+// positions past the end of a ragged chunk treated as missing observations (only the loads and the
+// output stores are predicated); CHT == 0: run-time chunk length, rolled software-pipelined loops.
+template <int K, typename ObsT, int CHT = 0>
 __global__ void __launch_bounds__(kPostWarps * 32, 4) post_sweep_kernel(const __grid_constant__ FbTables<K> tab,
                                                                        const __grid_constant__ PostSweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int L = a.L;
-  const int CH = a.CH;
+  const int CH = (CHT > 0) ? CHT : a.CH;
+  constexpr int NRT = (CHT > 0) ? CHT : 1;
 
   unsigned char* wbase = smem + (size_t)warp * a.warp_bytes;
   uint64_t* mbar = reinterpret_cast<uint64_t*>(wbase);  // [2]
@@ -147,25 +151,27 @@ __global__ void __launch_bounds__(kPostWarps * 32, 4) post_sweep_kernel(const __
     __syncwarp();
     mbar_wait(&mbar[buf], (uint32_t)((it >> 1) & 1));
 
-    // ---------------- forward sweep (ratios of position j + 1 formed while j is folded in) ----------------
-    float al[K];
+    if constexpr (CHT > 0) {
+      // ---------------- unrolled sweeps ----------------
+      const float kMissing = __int_as_float(0x7fc00000);
+      float rt[NRT][K];
+      float al[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) al[k] = v[k];
-    {
-      float fn[K];
-      ratios((len > 0) ? obs_to_float<ObsT>(s_in[0]) : 0.0f, fn);
-      for (int j = 0; j < len; ++j) {
+      for (int k = 0; k < K; ++k) al[k] = v[k];
+#pragma unroll
+      for (int j = 0; j < CHT; ++j) {
+        const float o = (j < len) ? obs_to_float<ObsT>(s_in[j]) : kMissing;
         float cf[K], y[K];
+        ratios(o, cf);
 #pragma unroll
-        for (int k = 0; k < K; ++k) cf[k] = fn[k];
-        if (j + 1 < len) ratios(obs_to_float<ObsT>(s_in[j + 1]), fn);
+        for (int k = 0; k < K; ++k) rt[j][k] = cf[k];
 #pragma unroll
         for (int jj = 0; jj < K; ++jj) {
           float acc = al[jj];
 #pragma unroll
           for (int i = 0; i < K; ++i)
             if (i != jj) acc = fmaf(al[i], A[i][jj], acc);
-          const float x = (first && j == 0) ? al[jj] : acc;  // alpha_0 = pi2 * c: no transition
+          const float x = (j == 0 && first) ? al[jj] : acc;
           y[jj] = (jj == 0) ? x : x * cf[jj];
         }
         if ((j & 3) == 3) {
@@ -174,38 +180,25 @@ __global__ void __launch_bounds__(kPostWarps * 32, 4) post_sweep_kernel(const __
           for (int k = 0; k < K; ++k) y[k] *= sc;
         }
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-          al[k] = y[k];
-          stg[j * K + k] = y[k];
+        for (int k = 0; k < K; ++k) al[k] = y[k];
+        if (active) {  // idle lanes of the last slice own no column
+          if (K == 4) {
+            *reinterpret_cast<float4*>(stg + j * 4) = make_float4(y[0], y[1 % K], y[2 % K], y[3 % K]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < K; ++k) stg[j * K + k] = y[k];
+          }
         }
       }
-    }
-    // ---------------- backward sweep: gamma over alpha in place, arg-max states ----------------
-    {
       float bv[K], alc[K];
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         bv[k] = w[k];
         alc[k] = al[k];
       }
-      float rn[K], an[K];
-      ratios((len > 0) ? obs_to_float<ObsT>(s_in[len - 1]) : 0.0f, rn);
 #pragma unroll
-      for (int k = 0; k < K; ++k) an[k] = (len > 1) ? stg[(len - 2) * K + k] : 0.0f;
-      for (int j = len - 1; j >= 0; --j) {
-        float cr[K], alp[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          cr[k] = rn[k];
-          alp[k] = an[k];
-        }
-        if (j > 0) {
-          ratios(obs_to_float<ObsT>(s_in[j - 1]), rn);
-          if (j > 1) {
-#pragma unroll
-            for (int k = 0; k < K; ++k) an[k] = stg[(j - 2) * K + k];
-          }
-        }
+      for (int j = CHT - 1; j >= 0; --j) {
+        const bool real = j < len;
         float gk[K];
         float gsum = 0.0f;
 #pragma unroll
@@ -216,32 +209,51 @@ __global__ void __launch_bounds__(kPostWarps * 32, 4) post_sweep_kernel(const __
         const float gr = rcp_approx(gsum);
 #pragma unroll
         for (int k = 0; k < K; ++k) gk[k] *= gr;
-        if (w_gamma_all) {
+        float alp[K];
+        if (j > 0) {
+          if (K == 4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(stg + (j - 1) * 4);
+            alp[0] = t4.x;
+            alp[1 % K] = t4.y;
+            alp[2 % K] = t4.z;
+            alp[3 % K] = t4.w;
+          } else {
 #pragma unroll
-          for (int k = 0; k < K; ++k) stg[j * K + k] = gk[k];
-        } else if (w_gamma_one) {
-          float gsel = gk[0];
-#pragma unroll
-          for (int k = 1; k < K; ++k)
-            if (gs == k) gsel = gk[k];
-          s_one[lane * CH + j] = gsel;
+            for (int k = 0; k < K; ++k) alp[k] = stg[(j - 1) * K + k];
+          }
         }
-        if (w_states) {
-          int best = 0;
-          float gbest = gk[0];
+        if (real) {
+          if (w_gamma_all) {
+            if (K == 4) {
+              *reinterpret_cast<float4*>(stg + j * 4) = make_float4(gk[0], gk[1 % K], gk[2 % K], gk[3 % K]);
+            } else {
 #pragma unroll
-          for (int k = 1; k < K; ++k)
-            if (gk[k] > gbest) {
-              gbest = gk[k];
-              best = k;
+              for (int k = 0; k < K; ++k) stg[j * K + k] = gk[k];
             }
-          s_st[lane * CH + j] = (int8_t)best;
+          } else if (w_gamma_one) {
+            float gsel = gk[0];
+#pragma unroll
+            for (int k = 1; k < K; ++k)
+              if (gs == k) gsel = gk[k];
+            s_one[lane * CHT + j] = gsel;
+          }
+          if (w_states) {
+            int best = 0;
+            float gbest = gk[0];
+#pragma unroll
+            for (int k = 1; k < K; ++k)
+              if (gk[k] > gbest) {
+                gbest = gk[k];
+                best = k;
+              }
+            s_st[lane * CHT + j] = (int8_t)best;
+          }
         }
         if (j > 0) {
           float cb[K], nb[K];
           cb[0] = bv[0];
 #pragma unroll
-          for (int k = 1; k < K; ++k) cb[k] = cr[k] * bv[k];
+          for (int k = 1; k < K; ++k) cb[k] = rt[j][k] * bv[k];
 #pragma unroll
           for (int i = 0; i < K; ++i) {
             float acc = cb[i];
@@ -250,7 +262,7 @@ __global__ void __launch_bounds__(kPostWarps * 32, 4) post_sweep_kernel(const __
               if (jj != i) acc = fmaf(A[i][jj], cb[jj], acc);
             nb[i] = acc;
           }
-          if (((len - 1 - j) & 3) == 3) {
+          if (((CHT - 1 - j) & 3) == 3) {
             const float sc = pow2_rescale_noexp(vec_max<K>(nb));
 #pragma unroll
             for (int k = 0; k < K; ++k) nb[k] *= sc;
@@ -259,6 +271,123 @@ __global__ void __launch_bounds__(kPostWarps * 32, 4) post_sweep_kernel(const __
           for (int k = 0; k < K; ++k) {
             bv[k] = nb[k];
             alc[k] = alp[k];
+          }
+        }
+      }
+    } else {
+      // ---------------- forward sweep (ratios of position j + 1 formed while j is folded in) ----------------
+      float al[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) al[k] = v[k];
+      {
+        float fn[K];
+        ratios((len > 0) ? obs_to_float<ObsT>(s_in[0]) : 0.0f, fn);
+        for (int j = 0; j < len; ++j) {
+          float cf[K], y[K];
+#pragma unroll
+          for (int k = 0; k < K; ++k) cf[k] = fn[k];
+          if (j + 1 < len) ratios(obs_to_float<ObsT>(s_in[j + 1]), fn);
+#pragma unroll
+          for (int jj = 0; jj < K; ++jj) {
+            float acc = al[jj];
+#pragma unroll
+            for (int i = 0; i < K; ++i)
+              if (i != jj) acc = fmaf(al[i], A[i][jj], acc);
+            const float x = (first && j == 0) ? al[jj] : acc;  // alpha_0 = pi2 * c: no transition
+            y[jj] = (jj == 0) ? x : x * cf[jj];
+          }
+          if ((j & 3) == 3) {
+            const float sc = pow2_rescale_noexp(vec_max<K>(y));
+#pragma unroll
+            for (int k = 0; k < K; ++k) y[k] *= sc;
+          }
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            al[k] = y[k];
+            stg[j * K + k] = y[k];
+          }
+        }
+      }
+      // ---------------- backward sweep: gamma over alpha in place, arg-max states ----------------
+      {
+        float bv[K], alc[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          bv[k] = w[k];
+          alc[k] = al[k];
+        }
+        float rn[K], an[K];
+        ratios((len > 0) ? obs_to_float<ObsT>(s_in[len - 1]) : 0.0f, rn);
+#pragma unroll
+        for (int k = 0; k < K; ++k) an[k] = (len > 1) ? stg[(len - 2) * K + k] : 0.0f;
+        for (int j = len - 1; j >= 0; --j) {
+          float cr[K], alp[K];
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            cr[k] = rn[k];
+            alp[k] = an[k];
+          }
+          if (j > 0) {
+            ratios(obs_to_float<ObsT>(s_in[j - 1]), rn);
+            if (j > 1) {
+#pragma unroll
+              for (int k = 0; k < K; ++k) an[k] = stg[(j - 2) * K + k];
+            }
+          }
+          float gk[K];
+          float gsum = 0.0f;
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            gk[k] = alc[k] * bv[k];
+            gsum += gk[k];
+          }
+          const float gr = rcp_approx(gsum);
+#pragma unroll
+          for (int k = 0; k < K; ++k) gk[k] *= gr;
+          if (w_gamma_all) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) stg[j * K + k] = gk[k];
+          } else if (w_gamma_one) {
+            float gsel = gk[0];
+#pragma unroll
+            for (int k = 1; k < K; ++k)
+              if (gs == k) gsel = gk[k];
+            s_one[lane * CH + j] = gsel;
+          }
+          if (w_states) {
+            int best = 0;
+            float gbest = gk[0];
+#pragma unroll
+            for (int k = 1; k < K; ++k)
+              if (gk[k] > gbest) {
+                gbest = gk[k];
+                best = k;
+              }
+            s_st[lane * CH + j] = (int8_t)best;
+          }
+          if (j > 0) {
+            float cb[K], nb[K];
+            cb[0] = bv[0];
+#pragma unroll
+            for (int k = 1; k < K; ++k) cb[k] = cr[k] * bv[k];
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+              float acc = cb[i];
+#pragma unroll
+              for (int jj = 0; jj < K; ++jj)
+                if (jj != i) acc = fmaf(A[i][jj], cb[jj], acc);
+              nb[i] = acc;
+            }
+            if (((len - 1 - j) & 3) == 3) {
+              const float sc = pow2_rescale_noexp(vec_max<K>(nb));
+#pragma unroll
+              for (int k = 0; k < K; ++k) nb[k] *= sc;
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+              bv[k] = nb[k];
+              alc[k] = alp[k];
+            }
           }
         }
       }
