@@ -15,6 +15,6 @@ from .hmm import (  # noqa: F401
     register_hmm,
 )
 
-from .merges import apply_merges, expand_merge_chain, merge_chain_packed  # noqa: F401,E402
+from .merges import apply_merges, expand_merge_chain, expand_merge_chain_device, merge_chain_packed  # noqa: F401,E402
 
 __version__ = "0.1.0"

@@ -14,6 +14,8 @@ formed on the host, with the same torch ops (and therefore the same rounding) as
 """
 from __future__ import annotations
 
+import os
+
 import ast
 import json
 from pathlib import Path
@@ -255,6 +257,30 @@ def mask_layers_outside_read_span(
         adata.layers[layer] = arr
         done.append(layer)
     return done
+
+
+def _alloc_host_layers(shape, dtypes: Dict[str, Any]) -> Dict[str, np.ndarray]:
+    """Allocate dense host layers and touch their pages from several threads: first-touch page faults
+    (the kernel zeroing 4 KB pages) run at ~3 GB/s on one core and dominate the cost of materialising
+    tens of GB of float64 layers; ``ndarray.fill`` releases the GIL, so a small pool spreads them."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    out = {nm: np.empty(shape, dtype=dt) for nm, dt in dtypes.items()}
+    n = shape[0]
+    total = sum(a.nbytes for a in out.values())
+    workers = min(8, os.cpu_count() or 1)
+    if total < (64 << 20) or workers < 2 or n < workers:
+        return out
+    step = (n + workers - 1) // workers
+    jobs = [(a, lo, min(n, lo + step)) for a in out.values() for lo in range(0, n, step)]
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        list(pool.map(lambda j: j[0][j[1]:j[2]].fill(0), jobs))
+    return out
+
+
+def _device_to_host_layer(dst: np.ndarray, src: torch.Tensor) -> None:
+    """Copy a device tensor straight into (a row block of) a host layer -- no intermediate host tensor."""
+    torch.from_numpy(dst).copy_(src)
 
 
 def _run_lengths_np(bin_mat: np.ndarray) -> np.ndarray:
@@ -1008,6 +1034,7 @@ class BaseHMM(nn.Module):
 
         # ---- allocate / register the output layers in the reference's order (HMM.py:1256-1315) ----
         states_name = f"{prefix}_states"
+        fresh_base = states_name not in adata.layers
         if states_name not in adata.layers:
             adata.layers[states_name] = np.full((n_obs, n_vars), -1, dtype=np.int8)
         note(states_name)
@@ -1019,6 +1046,8 @@ class BaseHMM(nn.Module):
             post_name = f"{prefix}_posterior_{tag}"
             if post_name not in adata.layers:
                 adata.layers[post_name] = np.zeros((n_obs, n_vars), dtype=np.float32)
+            else:
+                fresh_base = False
             note(post_name)
 
         if feature_sets is None:
@@ -1068,13 +1097,37 @@ class BaseHMM(nn.Module):
             left_d = torch.from_numpy(np.ascontiguousarray(left, dtype=np.int32)).to(device)
             right_d = torch.from_numpy(np.ascontiguousarray(right, dtype=np.int32)).to(device)
 
+        # Final-form fast path: when every layer of this call is new and the read-span mask follows anyway,
+        # the layers are expanded to their final dtype (float64 / float32 posterior) and NaN-masked ON THE
+        # DEVICE, chunk by chunk, and land in host memory once -- instead of uint8 / int32 host layers that
+        # mask_layers_outside_read_span re-reads, converts and masks on one CPU core (HMM.py:1372-1377).
+        fast_final = bool(kernel_ok and mask_to_read_span and feature_sets and fresh_base
+                          and all(gr["clean"] for gr in groups))
+        if fast_final:
+            if "reference_start" not in adata.obs or "reference_end" not in adata.obs:
+                raise KeyError("Missing 'reference_start' or 'reference_end' in adata.obs.")
+            span_in = _span_inputs(adata, start_key="reference_start", end_key="reference_end",
+                                   use_original_var_names=mask_use_original_var_names, device=device)
+            fresh_names = [states_name] + ([post_name] if post_name is not None else [])
+            for gr in groups:
+                fresh_names += [gr["all_layer"], f"{gr['all_layer']}_lengths"]
+                for feat in gr["feats"]:
+                    fresh_names += [f"{prefix}_{feat}", f"{prefix}_{feat}_lengths"]
+            for nm, arr in _alloc_host_layers(
+                    (n_obs, n_vars), {nm: (np.float32 if nm == post_name else np.float64) for nm in fresh_names}).items():
+                adata.layers[nm] = arr
+            masked_idx_d = torch.from_numpy(np.ascontiguousarray(masked_idx, dtype=np.int64)).to(device)
+            take_d = torch.from_numpy(np.ascontiguousarray(take, dtype=np.int64)).to(device)
+            nan64 = torch.tensor(float("nan"), dtype=torch.float64, device=device)
+            nan32 = torch.tensor(float("nan"), dtype=torch.float32, device=device)
+
         # ---- decode + feature calling on the device, one chunk of reads at a time ----
         tables = self._host_tables()
         bins = self._bins_for(coords, L, device)
         K = self.n_states
         C = int(src.shape[2]) if src.ndim == 3 else 1
         item = src.element_size() if isinstance(src, torch.Tensor) else src.dtype.itemsize
-        per_read = L * (C * item + 4 * K + 2) + n_vars * 5 * max(1, len(groups)) + 64
+        per_read = L * (C * item + 4 * K + 2) + n_vars * (5 * max(1, len(groups)) + (26 if fast_final else 0)) + 64
         rows = max(1, int(self.device_chunk_bytes // per_read))
         for lo in range(0, N, rows):
             hi = min(N, lo + rows)
@@ -1084,11 +1137,40 @@ class BaseHMM(nn.Module):
             if use_viterbi:
                 states_d = engine.viterbi(tables, obs, bins)
             del obs
-            states_h = states_d.cpu().numpy()
-            adata.layers[states_name][lo:hi, masked_idx] = states_h[:, take]
-            if post_name is not None:
-                post_h = gamma_d[:, :, t_post].contiguous().cpu().numpy()
-                adata.layers[post_name][lo:hi, masked_idx] = post_h[:, take]
+            if fast_final:
+                n_chunk = hi - lo
+                if "covered" in span_in:
+                    valid_u8 = engine.span_mask(n_chunk, n_vars, device, covered=span_in["covered"][lo:hi].contiguous())
+                else:
+                    valid_u8 = engine.span_mask(n_chunk, n_vars, device, coords=span_in["coords"],
+                                                start=span_in["start"][lo:hi].contiguous(),
+                                                end=span_in["end"][lo:hi].contiguous())
+                valid_b = valid_u8 != 0
+                del valid_u8
+
+                def put(name, values, is_post=False):
+                    """final dtype + NaN outside the read span on the device, one copy to the host layer"""
+                    if is_post:
+                        out = torch.where(valid_b, values.to(torch.float32), nan32)
+                    else:
+                        out = torch.where(valid_b, values.to(torch.float64), nan64)
+                    _device_to_host_layer(adata.layers[name][lo:hi], out)
+
+                full_s = torch.full((n_chunk, n_vars), -1, dtype=torch.int8, device=device)
+                full_s[:, masked_idx_d] = states_d.index_select(1, take_d)
+                put(states_name, full_s)
+                del full_s
+                if post_name is not None:
+                    full_p = torch.zeros((n_chunk, n_vars), dtype=torch.float32, device=device)
+                    full_p[:, masked_idx_d] = gamma_d[:, :, t_post].index_select(1, take_d)
+                    put(post_name, full_p, is_post=True)
+                    del full_p
+            else:
+                states_h = states_d.cpu().numpy()
+                adata.layers[states_name][lo:hi, masked_idx] = states_h[:, take]
+                if post_name is not None:
+                    post_h = gamma_d[:, :, t_post].contiguous().cpu().numpy()
+                    adata.layers[post_name][lo:hi, masked_idx] = post_h[:, take]
             for gr in groups:
                 all_layer, feats, ranges, target_idx = gr["all_layer"], gr["feats"], gr["ranges"], gr["target"]
                 if kernel_ok:
@@ -1101,6 +1183,17 @@ class BaseHMM(nn.Module):
                         cls_d, len_d, _ = engine.call_features(
                             states=None, post=post_d, target=target_idx, threshold=float(prob_threshold),
                             coords=coords_d, grid_left=left_d, grid_right=right_d, n_grid=n_vars, ranges=ranges)
+                    if fast_final:
+                        any_hit_d = cls_d > 0
+                        zero_d = torch.zeros((), dtype=len_d.dtype, device=device)
+                        put(all_layer, any_hit_d)
+                        put(f"{all_layer}_lengths", torch.where(any_hit_d, len_d, zero_d))
+                        for ci, feat in enumerate(feats):
+                            hit_d = cls_d == (ci + 1)
+                            put(f"{prefix}_{feat}", hit_d)
+                            put(f"{prefix}_{feat}_lengths", torch.where(hit_d, len_d, zero_d))
+                        del cls_d, len_d
+                        continue
                     cls_h = cls_d.cpu().numpy()
                     len_h = len_d.cpu().numpy()
                     any_hit = cls_h > 0
@@ -1142,7 +1235,13 @@ class BaseHMM(nn.Module):
             return None
 
         if mask_to_read_span and appended:
-            mask_layers_outside_read_span(adata, appended, use_original_var_names=mask_use_original_var_names)
+            if fast_final:
+                # this call's layers are final already; layers appended by earlier calls get the (idempotent) pass
+                others = [nm for nm in appended if nm not in set(fresh_names)]
+                if others:
+                    mask_layers_outside_read_span(adata, others, use_original_var_names=mask_use_original_var_names)
+            else:
+                mask_layers_outside_read_span(adata, appended, use_original_var_names=mask_use_original_var_names)
 
         adata.uns[uns_key] = appended
         adata.uns[uns_flag] = True

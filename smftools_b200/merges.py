@@ -22,7 +22,8 @@ import numpy as np
 import torch
 
 from . import engine
-from .hmm import BaseHMM, _default_cuda_device, _safe_int_coords, _span_inputs
+from .hmm import (BaseHMM, _alloc_host_layers, _default_cuda_device, _device_to_host_layer, _safe_int_coords,
+                  _span_inputs)
 
 CODE_CLASS_MASK = 0x0F
 CODE_MEMBER = 0x40
@@ -110,6 +111,52 @@ def expand_merge_chain(
     return names
 
 
+def expand_merge_chain_device(
+    adata,
+    base_layer: str,
+    code: torch.Tensor,
+    run_len: torch.Tensor,
+    *,
+    out_prefix: str,
+    feature_ranges: Optional[Mapping[str, Tuple[float, float]]] = None,
+    suffix: str = "_merged",
+    rows_per_step: int = 0,
+) -> List[str]:
+    """``expand_merge_chain`` with the float64 / NaN expansion done on the device, a block of reads at a
+    time, so every dense layer is written to host memory exactly once (the numpy version converts and
+    masks each layer on one CPU core)."""
+    n_obs, n_vars = int(code.shape[0]), int(code.shape[1])
+    dev = code.device
+    merged_name = f"{base_layer}{suffix}"
+    feats = list(feature_ranges or {})
+    names = [merged_name, f"{merged_name}_lengths"]
+    for feat in feats:
+        names.extend([f"{out_prefix}_{feat}{suffix}", f"{out_prefix}_{feat}{suffix}_lengths"])
+    for nm, arr in _alloc_host_layers((n_obs, n_vars), {nm: np.float64 for nm in names}).items():
+        adata.layers[nm] = arr
+    nan = torch.tensor(float("nan"), dtype=torch.float64, device=dev)
+    zero = torch.zeros((), dtype=run_len.dtype, device=dev)
+    rows = rows_per_step or max(1, int((1 << 28) // max(n_vars, 1)))  # ~2 GB of float64 per block
+    for lo in range(0, n_obs, rows):
+        hi = min(n_obs, lo + rows)
+        c = code[lo:hi]
+        rl = run_len[lo:hi]
+        valid = (c & CODE_VALID) != 0
+        cls = c & CODE_CLASS_MASK
+
+        def put(name, values):
+            _device_to_host_layer(adata.layers[name][lo:hi], torch.where(valid, values.to(torch.float64), nan))
+
+        put(merged_name, (c & CODE_MEMBER) != 0)
+        put(f"{merged_name}_lengths", rl)
+        for ci, feat in enumerate(feats):
+            hit = cls == (ci + 1)
+            put(f"{out_prefix}_{feat}{suffix}", hit)
+            put(f"{out_prefix}_{feat}{suffix}_lengths", torch.where(hit, rl, zero))
+    BaseHMM._register_appended_layers(adata, names)
+    return names
+
+
 def apply_merges(adata, model, prefix: str, feature_sets: dict, cfg) -> None:
     """Drop-in for ``_apply_merges(adata, model, prefix, feature_sets, cfg)``
     (tools/partitioned_hmm.py:78-108); ``model`` is accepted for signature parity only."""
@@ -124,5 +171,5 @@ def apply_merges(adata, model, prefix: str, feature_sets: dict, cfg) -> None:
         feature_ranges = feature_ranges_for_merged_layer(core_layer, feature_sets)
         code, run_len = merge_chain_packed(adata, base_layer, distance_threshold=int(distance),
                                            feature_ranges=feature_ranges)
-        expand_merge_chain(adata, base_layer, code.cpu().numpy(), run_len.cpu().numpy(), out_prefix=prefix,
-                           feature_ranges=feature_ranges, suffix=merged_suffix)
+        expand_merge_chain_device(adata, base_layer, code, run_len, out_prefix=prefix,
+                                  feature_ranges=feature_ranges, suffix=merged_suffix)
