@@ -259,23 +259,33 @@ def mask_layers_outside_read_span(
     return done
 
 
-def _alloc_host_layers(shape, dtypes: Dict[str, Any]) -> Dict[str, np.ndarray]:
-    """Allocate dense host layers and touch their pages from several threads: first-touch page faults
-    (the kernel zeroing 4 KB pages) run at ~3 GB/s on one core and dominate the cost of materialising
-    tens of GB of float64 layers; ``ndarray.fill`` releases the GIL, so a small pool spreads them."""
+def _alloc_host_arrays(specs: Dict[str, Tuple[Tuple[int, ...], Any]]) -> Dict[str, np.ndarray]:
+    """Allocate host arrays ``name -> (shape, dtype)`` and touch their pages from several threads:
+    first-touch page faults (the kernel zeroing 4 KB pages) run at ~3 GB/s on one core and dominate the
+    cost of materialising tens of GB of results; ``ndarray.fill`` releases the GIL, so a small pool
+    spreads them over the cores."""
     from concurrent.futures import ThreadPoolExecutor
 
-    out = {nm: np.empty(shape, dtype=dt) for nm, dt in dtypes.items()}
-    n = shape[0]
+    out = {nm: np.empty(shape, dtype=dt) for nm, (shape, dt) in specs.items()}
     total = sum(a.nbytes for a in out.values())
     workers = min(8, os.cpu_count() or 1)
-    if total < (64 << 20) or workers < 2 or n < workers:
+    if total < (64 << 20) or workers < 2 or os.environ.get("SMF_NO_PRETOUCH"):
         return out
-    step = (n + workers - 1) // workers
-    jobs = [(a, lo, min(n, lo + step)) for a in out.values() for lo in range(0, n, step)]
+    jobs = []
+    for a in out.values():
+        n = a.shape[0] if a.ndim else 0
+        if n < workers:
+            continue
+        step = (n + workers - 1) // workers
+        jobs.extend((a, lo, min(n, lo + step)) for lo in range(0, n, step))
     with ThreadPoolExecutor(max_workers=workers) as pool:
         list(pool.map(lambda j: j[0][j[1]:j[2]].fill(0), jobs))
     return out
+
+
+def _alloc_host_layers(shape, dtypes: Dict[str, Any]) -> Dict[str, np.ndarray]:
+    """Dense (n_obs, n_vars) layers with pre-touched pages (see ``_alloc_host_arrays``)."""
+    return _alloc_host_arrays({nm: (tuple(shape), dt) for nm, dt in dtypes.items()})
 
 
 def _device_to_host_layer(dst: np.ndarray, src: torch.Tensor) -> None:
@@ -529,8 +539,8 @@ class BaseHMM(nn.Module):
             if states_out.dtype != st_dtype or gamma_out.dtype != g_dtype:
                 raise ValueError(f"out buffers must be ({np.dtype(st_dtype)}, {np.dtype(g_dtype)})")
         else:
-            states_out = np.empty((N, L), dtype=st_dtype)
-            gamma_out = np.empty((N, L, K), dtype=g_dtype)
+            bufs = _alloc_host_arrays({"states": ((N, L), st_dtype), "gamma": ((N, L, K), g_dtype)})
+            states_out, gamma_out = bufs["states"], bufs["gamma"]
         if N == 0 or L == 0:
             return states_out, gamma_out
         self._decode_stream(src, tables, bins, use_viterbi, states_out, gamma_out, device, C)
