@@ -354,7 +354,13 @@ def run_ours(args, wl):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    numa_node = None
     if world > 1:
+        # several ranks stream through host memory at once (e2e leg): keep each rank's host buffers and
+        # copy threads on the NUMA node of its GPU
+        from smftools_b200.dist import bind_to_gpu_numa_node
+
+        numa_node = bind_to_gpu_numa_node(local)
         dist.init_process_group("nccl", device_id=device)
     N, L, K, op = wl["N"], wl["L"], wl["K"], wl["op"]
     C = 1
@@ -470,6 +476,7 @@ def run_ours(args, wl):
             "h2d_bytes_per_step": int(n_e2e * L * 4), "d2h_bytes_per_step": int(n_e2e * L * (4 * K + 1)),
             "steps": e2e_steps, "reads_per_step": n_e2e,
             "api": "SingleBernoulliHMM.decode(X_host_f32, decode='marginal', compact=True, out=pinned buffers)",
+            "numa_node_rank0": numa_node,
         }
         del host_in, out_states, out_gamma
 

@@ -8,6 +8,7 @@ bit-identical parameters.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -39,3 +40,43 @@ def broadcast_parameters(model, src: int = 0, process_group=None):
         if buf is not t:
             p.data = buf.to(t.device)
     return model
+
+
+def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (Linux sysfs), so that pinned /
+    pageable host buffers allocated afterwards are first-touched on that node and host<->device copies
+    of several ranks do not all cross the same socket link.  Returns the node, or None when the
+    topology cannot be read (then nothing is changed)."""
+    try:
+        bdf = torch.cuda.get_device_properties(device_index).pci_bus_id  # e.g. "0000:1B:00.0"
+    except Exception:
+        try:
+            import ctypes
+
+            buf = ctypes.create_string_buffer(32)
+            rt = ctypes.CDLL("libcudart.so")
+            if rt.cudaDeviceGetPCIBusId(buf, 32, int(device_index)) != 0:
+                return None
+            bdf = buf.value.decode()
+        except Exception:
+            return None
+    try:
+        with open(f"/sys/bus/pci/devices/{str(bdf).lower()}/numa_node") as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                if "-" in part:
+                    a, b = part.split("-")
+                    cpus.update(range(int(a), int(b) + 1))
+                elif part:
+                    cpus.add(int(part))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, ValueError, AttributeError):
+        return None
