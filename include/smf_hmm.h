@@ -84,7 +84,7 @@ const char* smf_hmm_strerror(int code);
  *            forward-backward path from its measured policy; 0 never / 1 whenever possible use the
  *            two-kernel path; 2 additionally always takes its any-length sweep kernels (posterior: all K).
  *            smf_hmm_workspace_bytes() follows the setting.
- *   "short"  -1 (default) posterior decode of reads up to ~340 positions runs on the several-reads-
+ *   "short"  -1 (default) posterior decode of reads up to ~275 positions (K = 2) runs on the several-reads-
  *            per-warp kernel; 0 never / 1 whenever the read fits it (<= 1056 positions).
  * Returns SMF_ERR_BAD_ARG for an unknown key or value.
  */

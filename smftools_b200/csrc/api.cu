@@ -277,19 +277,22 @@ static int plan_fb2(int K, int64_t L64, bool stats, int S, int es, bool want_gam
   // 29: fb2x_k2.cu), which smooths the lane-utilisation sawtooth of medium reads (e.g. 600 positions:
   // 19 + 13 idle lanes at chunk 17, one full warp at chunk 21).  Score = lane utilisation, mildly
   // favouring longer chunks (less scan work per position), as measured for 17 vs 33.
-  if (K == 2 && !stats && (es == 4 || es == 1) && (env_ch == 21 || env_ch == 25 || env_ch == 29) &&
+  if (K == 2 && !stats && (es == 4 || es == 1) &&
+      (env_ch == 9 || env_ch == 11 || env_ch == 13 || env_ch == 15 || env_ch == 21 || env_ch == 25 || env_ch == 29) &&
       plan_fb2_chunk(K, env_ch, L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan) == SMF_OK)
     return SMF_OK;
   if (K == 3 && !stats && (es == 4 || es == 1) && (env_ch == 13 || env_ch == 21) &&
       plan_fb2_chunk(K, env_ch, L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan) == SMF_OK)
     return SMF_OK;
   if (K == 2 && !stats && env_ch == 0 && (es == 4 || es == 1)) {
-    static const int cand[5] = {33, 29, 25, 21, 17};
-    bool tried[5] = {false, false, false, false, false};
-    for (int round = 0; round < 5; ++round) {
+    // (9..15 only matter for reads of one warp: with several warps the longer chunks always win)
+    static const int cand[9] = {33, 29, 25, 21, 17, 15, 13, 11, 9};
+    const int ncand = (L64 <= 32 * 17) ? 9 : 5;
+    bool tried[9] = {false, false, false, false, false, false, false, false, false};
+    for (int round = 0; round < ncand; ++round) {
       int bi = -1;
       double bs = -1.0;
-      for (int i = 0; i < 5; ++i) {
+      for (int i = 0; i < ncand; ++i) {
         if (tried[i]) continue;
         double sc = lane_eff(cand[i]) * (0.8 + 0.2 * (cand[i] - 17) / 16.0);
         // one resident read per SM around 9-10 kb: the extra warp of chunk 29 beats the longer chunk
@@ -410,12 +413,13 @@ static inline int obs_elem_size(int dt) { return dt == SMF_OBS_F32 ? 4 : (dt == 
 // ---------------------------------------------------------------------------------------
 // -1 = measured policy, 0 = never, 1 = whenever it fits.  SMF_SHORT / smf_hmm_set_option("short", v).
 static int g_short_mode = [] { const char* e = getenv("SMF_SHORT"); return e ? atoi(e) : -1; }();
-// measured (profiles/r01_short.txt): faster than one read per warp up to ~340 positions for K = 2,
+// measured (profiles/r01_short.txt): faster than one read per warp up to ~275 positions for K = 2
+// (beyond that fb2_kernel's short chunks 9..15 keep a warp's lanes busy),
 // ~400 for K = 3, ~200 for K = 4
 // (posterior); the E-step variant wins up to ~450 (K = 2, 3) / ~300 (K = 4)
 static int short_max_len(int K, bool stats = false) {
   if (stats) return K >= 4 ? 300 : 450;
-  return K >= 4 ? 200 : (K == 3 ? 400 : 340);
+  return K >= 4 ? 200 : (K == 3 ? 400 : 275);
 }
 
 // Picks the odd chunk length that keeps the most lanes busy (weighted by how well it amortises the
@@ -484,6 +488,8 @@ static int launch_fb2(bool stats, const smf_hmm_tables* t, int obs_dtype, Fb2Arg
   static const int env_minb = [] { const char* e = getenv("SMF_FB2_MINB"); return e ? atoi(e) : 0; }();
   if (t->n_states == 2 && (plan.chunk == 21 || plan.chunk == 25 || plan.chunk == 29))
     return launch_fb2x_k2(plan.chunk, obs_dtype, out, t, a, plan, di, nblocks, stream);
+  if (t->n_states == 2 && plan.chunk < 17)
+    return launch_fb2y_k2(plan.chunk, obs_dtype, out, t, a, plan, di, nblocks, stream);
   if (t->n_states == 3 && (plan.chunk == 13 || plan.chunk == 21))
     return launch_fb2x_k3(plan.chunk, obs_dtype, out, t, a, plan, di, nblocks, stream);
   switch (t->n_states) {

@@ -121,6 +121,8 @@ SMF_DECLARE_K(4)
 // extra chunk lengths (21, 25, 29) of the K = 2 posterior kernel (fb2x_k2.cu)
 int launch_fb2x_k2(int chunk, int obs_dtype, int out_mode, const smf_hmm_tables* t, Fb2Args& a, const Fb2Plan& plan,
                    const DeviceInfo& di, int* nblocks, cudaStream_t s);
+int launch_fb2y_k2(int chunk, int obs_dtype, int out_mode, const smf_hmm_tables* t, Fb2Args& a, const Fb2Plan& plan,
+                   const DeviceInfo& di, int* nblocks, cudaStream_t s);
 int launch_fb2x_k3(int chunk, int obs_dtype, int out_mode, const smf_hmm_tables* t, Fb2Args& a, const Fb2Plan& plan,
                    const DeviceInfo& di, int* nblocks, cudaStream_t s);
 struct WalkArgs;
