@@ -167,6 +167,7 @@ static int plan_fb(int K, int C, int nb, int64_t L64, bool stats, int S, int max
 // Resident reads per SM for a candidate layout: shared memory (228 KB per SM, 1 KB reserved per CTA),
 // registers (64 K per SM) and the 32-CTA limit.
 constexpr int kWalkChunkDefault = 17;
+static bool g_plan_gc_ok = false;
 static int fb2_resident(int total_smem, int block, int groups, int regs) {
   const int by_smem = (228 * 1024) / (total_smem + 1024);
   const int by_regs = 65536 / (regs * block);
@@ -177,6 +178,7 @@ static int fb2_resident(int total_smem, int block, int groups, int regs) {
 
 static int plan_fb2_chunk(int K, int CH, int64_t L64, bool stats, int S, int es, bool want_gamma_one,
                           bool want_states, int max_smem, Fb2Args* a, Fb2Plan* plan, bool walk = false) {
+  const bool gc_ok = g_plan_gc_ok;  // set by smf_hmm_posterior for the one output set the compact staging serves
   if (L64 < 1) return SMF_ERR_TOO_LONG;
   if (L64 > (int64_t)CH * 1024) return SMF_ERR_TOO_LONG;
   const int L = (int)L64;
@@ -189,7 +191,15 @@ static int plan_fb2_chunk(int K, int CH, int64_t L64, bool stats, int S, int es,
   const int regs = walk ? (stats ? 128 : 96) : (((stats && K >= 3) || K == 4) ? 128 : 96);
   const int bar_b = 16;
   const int in_b = align_up((Lpad + 16) * es + 16, 16);
-  const int stage_b = align_up((Lpad * K + 4) * 4, 16);
+  // compact staging (fb2_kernel OUT == 3, opt-in): one float per position instead of K
+  static const int env_gc = [] { const char* e = getenv("SMF_FB2_GC"); return e ? atoi(e) : 0; }();
+  // measured: the extra encode / decode / expand instructions cost more than the residency brings
+  // (C2 0.64 vs 0.80, 10 kb 0.55 vs 0.66) except where the regular layout no longer fits with a prefetch
+  // buffer (>= ~18 kb: 0.65 vs 0.53 at 20 kb); SMF_FB2_GC=1 forces it for A/B runs
+  const bool gc = (env_gc == 1 || (env_gc == 0 && L64 >= 18000 && CH == 33)) && gc_ok && K == 2 && !stats && !walk &&
+                  !want_gamma_one && es == 4 && (CH == 33 || CH == 29);
+  a->gc = gc ? 1 : 0;
+  const int stage_b = align_up((Lpad * (gc ? 1 : K) + 4) * 4, 16);
   const int out1_b = want_gamma_one ? align_up((Lpad + 4) * 4, 16) : 0;
   const int st_b = want_states ? align_up(Lpad + 32, 16) : 0;
   const int scan_b = align_up(32 * (KK + 2 * K) * 4 + 32 * 8, 16);
@@ -481,10 +491,12 @@ static int launch_short(const smf_hmm_tables* t, int obs_dtype, const ShortArgs&
 static int launch_fb2(bool stats, const smf_hmm_tables* t, int obs_dtype, Fb2Args& a, const Fb2Plan& plan,
                       const DeviceInfo& di, int* nblocks, cudaStream_t stream) {
   // output-set specialisations exist for float observations; everything else decides at run time
-  const int out = (stats || obs_dtype != SMF_OBS_F32 || a.gamma == nullptr || a.states == nullptr ||
-                   a.loglik != nullptr)
-                      ? 2
-                      : (a.gamma_state < 0 ? 0 : 1);
+  int out = (stats || obs_dtype != SMF_OBS_F32 || a.gamma == nullptr || a.states == nullptr ||
+             a.loglik != nullptr)
+                ? 2
+                : (a.gamma_state < 0 ? 0 : 1);
+  if (a.gc && out == 0 && t->n_states == 2 && (plan.chunk == 33 || plan.chunk == 29)) out = 3;
+  if (a.gc && out != 3) return SMF_ERR_BAD_ARG;  // the staging tile was sized for the compact layout
   static const int env_minb = [] { const char* e = getenv("SMF_FB2_MINB"); return e ? atoi(e) : 0; }();
   if (t->n_states == 2 && (plan.chunk == 21 || plan.chunk == 25 || plan.chunk == 29))
     return launch_fb2x_k2(plan.chunk, obs_dtype, out, t, a, plan, di, nblocks, stream);
@@ -771,8 +783,12 @@ int smf_hmm_posterior(const smf_hmm_tables* tab, const void* obs, int obs_dtype,
       }
       memset(&b, 0, sizeof(b));
     }
-    if (plan_fb2(tab->n_states, n_pos, false, stats_len(tab), obs_elem_size(obs_dtype),
-                 gamma != nullptr && gamma_state >= 0, states != nullptr, di.max_smem_optin, &b, &p2) == SMF_OK) {
+    g_plan_gc_ok = gamma != nullptr && gamma_state < 0 && states != nullptr && loglik == nullptr &&
+                   obs_dtype == SMF_OBS_F32;
+    const int prc = plan_fb2(tab->n_states, n_pos, false, stats_len(tab), obs_elem_size(obs_dtype),
+                             gamma != nullptr && gamma_state >= 0, states != nullptr, di.max_smem_optin, &b, &p2);
+    g_plan_gc_ok = false;
+    if (prc == SMF_OK) {
       b.obs = obs;
       b.N = n_reads;
       b.L = (int)n_pos;

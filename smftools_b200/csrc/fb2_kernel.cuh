@@ -46,6 +46,7 @@ struct Fb2Args {
   const float* bnd_w;
   const double* ll_in;
   int Tact;  // chunks per read
+  int gc;    // 1: staging tile sized for the compact (OUT == 3) layout
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -220,7 +221,14 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
   const bool first = (t0 == 0);
   const bool want_ll = !WALK && (STATS || (a.loglik != nullptr));
   const int gs = a.gamma_state;
-  const bool w_gamma_all = !STATS && (OUT == 0 || (OUT == 2 && a.gamma != nullptr && gs < 0));
+  // OUT == 3 (K = 2 only): all-state posterior + states like OUT == 0, but the staging tile holds ONE float
+  // per position -- the forward sweep stashes alpha as a signed ratio (the smaller component over the
+  // larger, sign = which one), the backward sweep overwrites it with gamma_0, and the warp expands
+  // (gamma_0, 1 - gamma_0) on its way out with coalesced 64-bit stores.  9 instead of 13 bytes of
+  // shared memory per position: more reads resident per SM.
+  constexpr bool GC = (OUT == 3);
+  static_assert(!GC || (K == 2 && !STATS), "compact staging is for the K = 2 posterior kernel");
+  const bool w_gamma_all = !STATS && (OUT == 0 || GC || (OUT == 2 && a.gamma != nullptr && gs < 0));
   const bool w_gamma_one = !STATS && (OUT == 1 || (OUT == 2 && a.gamma != nullptr && gs >= 0));
   const bool w_states = !STATS && (OUT != 2 || a.states != nullptr);
   const uint32_t row_bytes = (uint32_t)L * (uint32_t)sizeof(ObsT);
@@ -281,7 +289,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
     float* s_stage = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_stage_base) + obuf);
     float* s_out1 = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_out1_base) + obuf);
     int8_t* s_st = s_st_base + obuf;
-    if (w_gamma_all) s_stage += (reinterpret_cast<uintptr_t>(a.gamma + (size_t)n * L * K) & 15u) >> 2;
+    if (w_gamma_all && !GC) s_stage += (reinterpret_cast<uintptr_t>(a.gamma + (size_t)n * L * K) & 15u) >> 2;
     if (w_gamma_one) s_out1 += (reinterpret_cast<uintptr_t>(a.gamma + (size_t)n * L) & 15u) >> 2;
     if (w_states) s_st += reinterpret_cast<uintptr_t>(a.states + (size_t)n * L) & 15u;
 
@@ -601,7 +609,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
       int e = 0;
 #pragma unroll
       for (int k = 0; k < K; ++k) al[k] = v[k];
-      float* stg = s_stage + (size_t)t0 * K;
+      float* stg = s_stage + (size_t)t0 * (GC ? 1 : K);
 #pragma unroll
       for (int j = 0; j < CH; ++j) {
         float nx[K];
@@ -628,7 +636,11 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
         }
 #pragma unroll
         for (int k = 0; k < K; ++k) al[k] = nx[k];
-        if (K == 2) {
+        if (GC) {
+          const float lo = fminf(nx[0], nx[1 % K]), hi = fmaxf(nx[0], nx[1 % K]);
+          const float rho = lo * rcp_approx(hi);
+          stg[j] = (nx[0] <= nx[1 % K]) ? rho : -rho;  // >= 0: alpha ~ (rho, 1); < 0: alpha ~ (1, rho)
+        } else if (K == 2) {
           *reinterpret_cast<float2*>(stg + j * 2) = make_float2(nx[0], nx[1 % K]);
         } else if (K == 4) {
           *reinterpret_cast<float4*>(stg + j * 4) = make_float4(nx[0], nx[1 % K], nx[2 % K], nx[3 % K]);
@@ -668,7 +680,12 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
         // alpha of the previous position (this thread's chunk, or the incoming prefix vector)
         float alp[K];
         if (j > 0) {
-          if (K == 2) {
+          if (GC) {
+            const float e1 = stg[j - 1];
+            const float rho = fabsf(e1);
+            alp[0] = (e1 >= 0.0f) ? rho : 1.0f;
+            alp[1 % K] = (e1 >= 0.0f) ? 1.0f : rho;
+          } else if (K == 2) {
             const float2 t2 = *reinterpret_cast<const float2*>(stg + (j - 1) * 2);
             alp[0] = t2.x;
             alp[1 % K] = t2.y;
@@ -687,7 +704,9 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
           for (int k = 0; k < K; ++k) alp[k] = v[k];
         }
         if (!STATS) {
-          if (w_gamma_all) {
+          if (GC) {
+            stg[j] = gk[0];
+          } else if (w_gamma_all) {
             if (K == 2) {
               *reinterpret_cast<float2*>(stg + j * 2) = make_float2(gk[0], gk[1 % K]);
             } else if (K == 4) {
@@ -776,7 +795,15 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
       __syncwarp();
       if (w0 < L) {
         const uint32_t npos = (uint32_t)(w1 - w0);
-        if (w_gamma_all)
+        if (GC) {
+          // expand (gamma_0, 1 - gamma_0) with coalesced 64-bit stores (global rows are 8-byte aligned)
+          float2* grow = reinterpret_cast<float2*>(a.gamma) + (size_t)n * L + w0;
+          const float* srow = s_stage + w0;
+          for (uint32_t i = lane; i < npos; i += 32) {
+            const float g0 = srow[i];
+            grow[i] = make_float2(g0, 1.0f - g0);
+          }
+        } else if (w_gamma_all)
           store_row_bulk<float>(a.gamma + ((size_t)n * L + w0) * K, s_stage + (size_t)w0 * K, npos * K * 4u, lane);
         if (w_gamma_one) store_row_bulk<float>(a.gamma + (size_t)n * L + w0, s_out1 + w0, npos * 4u, lane);
         if (w_states) store_row_bulk<int8_t>(a.states + (size_t)n * L + w0, s_st + w0, npos, lane);

@@ -76,3 +76,27 @@ def test_random_viterbi(case):
         obs = torch.from_numpy(X32).to(dev)
     st = engine.viterbi(tables, obs, None).cpu().numpy().astype(np.int64)
     assert_viterbi_matches(X32.astype(np.float64), p, None, st)
+
+
+@pytest.mark.parametrize("L,N", [(18500, 9), (21000, 5)])
+def test_k2_reads_near_the_on_chip_limit(L, N):
+    """K = 2 reads of 18-21 kb use the compact staging layout (one float per position, gamma expanded on
+    the way out): posterior, states and the one-state / log-likelihood variants that use the regular one."""
+    from smftools_b200 import engine
+
+    dev = torch.device("cuda")
+    K = 2
+    p = O.synth_params(K)
+    tables = model_from_params(p)._host_tables()
+    X32 = O.synth_reads(N, L, K, 321 + L, prob=False, nan_rate=0.3)
+    g_ref, ll_ref = O.posterior(X32.astype(np.float64), p)
+    obs = torch.from_numpy(X32).to(dev)
+    g, s, _ = engine.posterior(tables, obs, None)
+    assert np.abs(g.cpu().numpy() - g_ref).max() <= GAMMA_TOL
+    assert (g.sum(dim=2) - 1.0).abs().max().item() <= 1e-6
+    assert_states_match_up_to_ties(s.cpu().numpy().astype(np.int64), g_ref.argmax(axis=2), g_ref)
+    g2, s2, ll = engine.posterior(tables, obs, None, want_loglik=True)
+    assert np.abs(g2.cpu().numpy() - g_ref).max() <= GAMMA_TOL and torch.equal(s2, s)
+    assert np.allclose(ll.cpu().numpy(), ll_ref, rtol=1e-6)
+    g1, _, _ = engine.posterior(tables, obs, None, gamma_state=1)
+    assert np.abs(g1.cpu().numpy() - g_ref[:, :, 1]).max() <= GAMMA_TOL
