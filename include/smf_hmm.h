@@ -84,8 +84,9 @@ const char* smf_hmm_strerror(int code);
  *            forward-backward path from its measured policy; 0 never / 1 whenever possible use the
  *            two-kernel path; 2 additionally always takes its any-length sweep kernels (posterior: all K).
  *            smf_hmm_workspace_bytes() follows the setting.
- *   "short"  -1 (default) posterior decode of reads up to ~275 positions (K = 2) runs on the several-reads-
- *            per-warp kernel; 0 never / 1 whenever the read fits it (<= 1056 positions).
+ *   "short"  -1 (default) posterior decode and E-step of short reads (posterior: up to ~275 / 400 / 200
+ *            positions for K = 2 / 3 / 4; E-step: ~450 / 450 / 300) run on the several-reads-per-warp
+ *            kernel; 0 never / 1 whenever the read fits it (<= 1056 positions).
  * Returns SMF_ERR_BAD_ARG for an unknown key or value.
  */
 int smf_hmm_set_option(const char* key, int value);
