@@ -16,7 +16,11 @@
  *     `_host`; the small model tables are HOST pointers (they are copied into the kernel
  *     parameter space, no hidden device allocation).
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), allocates
- *     nothing, keeps no global state, and returns SMF_OK or a negative error code.
+ *     nothing on the device or the host heap, and returns SMF_OK or a negative error code.
+ *   - process state, all of it mutex-/atomic-protected and none of it affecting results: cached device
+ *     attributes, per-kernel shared-memory opt-ins and occupancy answers, the two path-selection knobs of
+ *     smf_hmm_set_option(), and the SMF_* environment overrides (read once when the library is loaded;
+ *     listed in DESIGN.md).  Calls may be issued concurrently from several host threads (one per GPU).
  *   - caller-owned workspaces: ask smf_hmm_workspace_bytes() first.
  */
 #ifndef SMF_HMM_H
@@ -29,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SMF_HMM_ABI_VERSION 2
+#define SMF_HMM_ABI_VERSION 3
 
 #define SMF_MAX_STATES 4
 #define SMF_MAX_CHANNELS 4
@@ -143,7 +147,8 @@ int smf_hmm_estep(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int
  * Footprint / feature calling on decoded reads.  Replaces the per-read Python loops of
  * BaseHMM.annotate_adata (HMM.py:1318-1370) for one feature group:
  *   membership[n,t] = states[n,t] == target            (post == NULL, Viterbi mode)
- *                   = post[n,t] >= threshold           (post != NULL, marginal mode)
+ *                   = (double)post[n,t] >= threshold   (post != NULL, marginal mode; fp64 comparison as in
+ *                                                       the reference, for any threshold value)
  *   every run [s,e) of membership gets genomic length coords[e-1]-coords[s]+1, the first
  *   size class with lo <= len < hi, and is span-filled into the full grid columns
  *   [left[s], right[e-1]) (searchsorted left/right of the site coordinate in the full grid,
@@ -160,7 +165,7 @@ int smf_hmm_estep(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int
  *   n_intervals device uint64 counter (zeroed by the caller); total runs found, may exceed max_intervals
  */
 int smf_hmm_call_features(const int8_t* states, const float* post, int target_state,
-                          float threshold, int64_t n_reads, int64_t n_pos,
+                          double threshold, int64_t n_reads, int64_t n_pos,
                           const int64_t* coords, const int32_t* grid_left,
                           const int32_t* grid_right, int64_t n_grid, const double* class_lo_host,
                           const double* class_hi_host, int n_classes, uint8_t* class_out,
@@ -209,6 +214,72 @@ int smf_hmm_merge_chain(const uint8_t* layer, int64_t n_reads, int64_t n_grid, c
 int smf_hmm_span_mask(const uint8_t* covered, const int64_t* coords, const double* read_start,
                       const double* read_end, int64_t n_reads, int64_t n_grid, uint8_t* valid_out,
                       void* stream);
+
+/*
+ * ---- boundary to the reference's host-side array contract -------------------------------------------
+ *
+ * BaseHMM.decode returns int64 states and posteriors in the model dtype (float64 by default) as host
+ * numpy arrays (HMM.py:718-720); annotate_adata leaves float64 layers with NaN outside the read span
+ * (HMM.py:1256-1377, 148-231).  The kernels above produce int8 / float / packed codes; the entry points
+ * below convert on the device so that the wide result crosses the host link exactly once, straight into
+ * page-locked destination arrays.
+ */
+
+/* int8 states -> int64 and float posteriors -> double, one launch (either pair may be NULL / 0 elements).
+ * states8 must be 4-byte aligned, gamma32 / the outputs 16-byte aligned. */
+int smf_hmm_widen_decode(const int8_t* states8, int64_t* states64, int64_t n_states_elems,
+                         const float* gamma32, double* gamma64, int64_t n_gamma_elems, void* stream);
+
+/* layer kinds of smf_hmm_expand_layers() */
+#define SMF_LAYER_STATES 0    /* {prefix}_states: state at site columns, -1 elsewhere     (HMM.py:1256-1262) */
+#define SMF_LAYER_POSTERIOR 1 /* {prefix}_posterior_<state>: posterior at site columns, 0 elsewhere (:1264-1273) */
+#define SMF_LAYER_ANY 2       /* all_{group}_features (class_out > 0)  /  {layer}_merged (code & 0x40)      */
+#define SMF_LAYER_ANY_LEN 3   /* its _lengths layer                                                          */
+#define SMF_LAYER_CLASS 4     /* {prefix}_{feature}: size class `cls` of the group                           */
+#define SMF_LAYER_CLASS_LEN 5 /* its _lengths layer                                                          */
+
+typedef struct smf_hmm_layer_group {
+  const uint8_t* cls_or_code; /* device [N, V]: class_out of smf_hmm_call_features, or code_out of smf_hmm_merge_chain */
+  const int32_t* run_len;     /* device [N, V] run lengths (may be NULL when no *_LEN layer is requested)             */
+  int32_t packed;             /* 1: cls_or_code is a merge-chain code byte (class bits 0-3, member 0x40, valid 0x80)   */
+  int32_t reserved;
+} smf_hmm_layer_group;
+
+typedef struct smf_hmm_layer_desc {
+  void* out;       /* device [N, V], double (out_f32 == 0) or float (out_f32 == 1) */
+  int32_t kind;    /* SMF_LAYER_* */
+  int32_t group;   /* index into groups for kinds >= SMF_LAYER_ANY */
+  int32_t cls;     /* size class index for SMF_LAYER_CLASS / _CLASS_LEN */
+  int32_t out_f32;
+} smf_hmm_layer_desc;
+
+/*
+ * Expand the packed per-chunk annotation results into the final dense layers in ONE pass: every cell of
+ * every requested layer is written once, already in its final dtype and NaN-masked where `valid` is 0 (or,
+ * for packed groups, where the code byte's 0x80 bit is clear).  Replaces the host-side layer fills of
+ * annotate_adata (HMM.py:1256-1273, 1348-1370), the dtype cast + NaN masking of
+ * mask_layers_outside_read_span (HMM.py:227-231) and the layer writes of _apply_merges
+ * (tools/partitioned_hmm.py:78-108).
+ *   states / post      decoded states int8 [N, L] and one posterior column: element (n, t) is read at
+ *                      post[(n * L + t) * post_stride]; either may be NULL when no layer needs it
+ *   site_of_col        device int32 [V]: site index of a grid column, -1 where the column is not a site
+ *   valid              device uint8 [N, V] from smf_hmm_span_mask, or NULL (keep everything)
+ *   groups / layers    HOST arrays (copied into the kernel parameters); <= 8 groups, <= 64 layers
+ */
+int smf_hmm_expand_layers(int64_t n_reads, int64_t n_grid, int64_t n_pos, const int8_t* states,
+                          const float* post, int64_t post_stride, const int32_t* site_of_col,
+                          const uint8_t* valid, const smf_hmm_layer_group* groups_host, int n_groups,
+                          const smf_hmm_layer_desc* layers_host, int n_layers, void* stream);
+
+/* Page-lock / release caller-owned host memory (cudaHostRegister, portable) so that copies into it run
+ * at link speed and asynchronously; plain async copy on `stream`. */
+#define SMF_COPY_H2D 0
+#define SMF_COPY_D2H 1
+#define SMF_COPY_D2D 2
+int smf_hmm_host_register(void* host_ptr, size_t bytes);
+int smf_hmm_host_unregister(void* host_ptr);
+int smf_hmm_host_is_pinned(const void* host_ptr); /* 1 when the address is page-locked (registered or cudaHostAlloc) */
+int smf_hmm_copy_async(void* dst, const void* src, size_t bytes, int kind, void* stream);
 
 #ifdef __cplusplus
 }

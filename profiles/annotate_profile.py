@@ -46,13 +46,21 @@ def run():
     return ad
 
 
-run()  # warm-up
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+ad = run()  # cold: page-locked pool empty
+dt = time.perf_counter() - t0
+gb = sum(np.asarray(v).nbytes for v in ad.layers.values()) / 1e9
+print(f"N={N} L={L} V={V}: [cold pool] annotate_adata + apply_merges {dt:.3f} s, {gb:.2f} GB of layers = {gb / dt:.1f} GB/s")
+del ad
 torch.cuda.synchronize()
 t0 = time.perf_counter()
 ad = run()
 dt = time.perf_counter() - t0
 print(f"N={N} L={L} V={V}: annotate_adata + apply_merges {dt:.3f} s, {len(ad.layers)} layers, "
-      f"{sum(np.asarray(v).nbytes for v in ad.layers.values()) / 1e9:.2f} GB of layers")
+      f"{sum(np.asarray(v).nbytes for v in ad.layers.values()) / 1e9:.2f} GB of layers = "
+      f"{sum(np.asarray(v).nbytes for v in ad.layers.values()) / 1e9 / dt:.1f} GB/s [warm pool]")
+del ad
 pr = cProfile.Profile()
 pr.enable()
 run()

@@ -39,7 +39,28 @@ EXPORTS = (
     "smf_hmm_merge_runs",
     "smf_hmm_merge_chain",
     "smf_hmm_span_mask",
+    "smf_hmm_widen_decode",
+    "smf_hmm_expand_layers",
+    "smf_hmm_host_register",
+    "smf_hmm_host_unregister",
+    "smf_hmm_host_is_pinned",
+    "smf_hmm_copy_async",
 )
+
+LAYER_STATES, LAYER_POSTERIOR, LAYER_ANY, LAYER_ANY_LEN, LAYER_CLASS, LAYER_CLASS_LEN = range(6)
+COPY_H2D, COPY_D2H, COPY_D2D = 0, 1, 2
+
+
+class LayerGroup(ctypes.Structure):
+    """Mirror of ``smf_hmm_layer_group``."""
+
+    _fields_ = [("cls_or_code", c_void_p), ("run_len", c_void_p), ("packed", c_int32), ("reserved", c_int32)]
+
+
+class LayerDesc(ctypes.Structure):
+    """Mirror of ``smf_hmm_layer_desc``."""
+
+    _fields_ = [("out", c_void_p), ("kind", c_int32), ("group", c_int32), ("cls", c_int32), ("out_f32", c_int32)]
 
 
 class Tables(ctypes.Structure):
@@ -93,7 +114,7 @@ def library_built() -> bool:
     return os.path.isfile(LIB_PATH)
 
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 def load():
@@ -130,7 +151,7 @@ def load():
     lib.smf_hmm_estep.argtypes = [T, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                   c_size_t, c_void_p]
     lib.smf_hmm_call_features.restype = c_int
-    lib.smf_hmm_call_features.argtypes = [c_void_p, c_void_p, c_int, c_float, c_int64, c_int64, c_void_p,
+    lib.smf_hmm_call_features.argtypes = [c_void_p, c_void_p, c_int, c_double, c_int64, c_int64, c_void_p,
                                           c_void_p, c_void_p, c_int64, POINTER(c_double), POINTER(c_double),
                                           c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
     lib.smf_hmm_merge_runs.restype = c_int
@@ -144,6 +165,19 @@ def load():
     lib.smf_hmm_span_mask.restype = c_int
     lib.smf_hmm_span_mask.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p,
                                       c_void_p]
+    lib.smf_hmm_widen_decode.restype = c_int
+    lib.smf_hmm_widen_decode.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p]
+    lib.smf_hmm_expand_layers.restype = c_int
+    lib.smf_hmm_expand_layers.argtypes = [c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                          POINTER(LayerGroup), c_int, POINTER(LayerDesc), c_int, c_void_p]
+    lib.smf_hmm_host_register.restype = c_int
+    lib.smf_hmm_host_register.argtypes = [c_void_p, c_size_t]
+    lib.smf_hmm_host_unregister.restype = c_int
+    lib.smf_hmm_host_unregister.argtypes = [c_void_p]
+    lib.smf_hmm_host_is_pinned.restype = c_int
+    lib.smf_hmm_host_is_pinned.argtypes = [c_void_p]
+    lib.smf_hmm_copy_async.restype = c_int
+    lib.smf_hmm_copy_async.argtypes = [c_void_p, c_void_p, c_size_t, c_int, c_void_p]
     if lib.smf_hmm_abi_version() != ABI_VERSION:
         raise RuntimeError("libsmfhmm.so ABI version mismatch; rebuild the extension")
     _lib = lib

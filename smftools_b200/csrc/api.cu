@@ -1,12 +1,18 @@
 // C-ABI of libsmfhmm.so (see include/smf_hmm.h): argument checks, launch-shape selection and
-// dispatch to the per-K launchers.  No torch, no allocation, no global state other than cached
-// device attributes.
+// dispatch to the per-K launchers.  No torch, no device allocation.  Process state (all of it thread-safe,
+// none of it affects results): cached device attributes, the per-kernel shared-memory opt-ins, the two
+// path-selection knobs of smf_hmm_set_option, and environment overrides read once at load.
 #include <cuda_runtime.h>
 #include <limits.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <tuple>
 
 #include "features_kernel.cuh"
 #include "launch.h"
@@ -31,21 +37,65 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partials, int 
 // E-step workspace: per-CTA partial statistics, for at most this many CTAs.
 static const int kMaxEstepBlocks = 148 * 8;
 
+static std::mutex g_state_mutex;  // guards the caches below (short critical sections, host only)
+
 static int get_device_info(DeviceInfo* out) {
   static DeviceInfo cache[64];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return SMF_ERR_CUDA;
+  std::lock_guard<std::mutex> lock(g_state_mutex);
   if (cache[dev].device != dev) {
     DeviceInfo d;
-    d.device = dev;
     if (cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
       return SMF_ERR_CUDA;
     if (cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) !=
         cudaSuccess)
       return SMF_ERR_CUDA;
+    d.device = dev;
     cache[dev] = d;
   }
   *out = cache[dev];
+  return SMF_OK;
+}
+
+struct KernelState {
+  int smem_set = -1;      // largest dynamic shared-memory size opted in so far
+  bool carveout = false;  // max-shared carve-out already requested
+  std::map<std::pair<int, int>, int> occ;  // (block, smem) -> resident CTAs per SM
+};
+static std::map<std::pair<const void*, int>, KernelState> g_kernels;
+
+int prepare_kernel(const void* kern, int smem_bytes, bool max_carveout) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return SMF_ERR_CUDA;
+  std::lock_guard<std::mutex> lock(g_state_mutex);
+  KernelState& ks = g_kernels[std::make_pair(kern, dev)];
+  if (smem_bytes > ks.smem_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
+      return SMF_ERR_CUDA;
+    ks.smem_set = smem_bytes;
+  }
+  if (max_carveout && !ks.carveout) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    ks.carveout = true;
+  }
+  return SMF_OK;
+}
+
+int cached_occupancy(const void* kern, int block, int smem_bytes, int* occ_out) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return SMF_ERR_CUDA;
+  std::lock_guard<std::mutex> lock(g_state_mutex);
+  KernelState& ks = g_kernels[std::make_pair(kern, dev)];
+  auto key = std::make_pair(block, smem_bytes);
+  auto it = ks.occ.find(key);
+  if (it == ks.occ.end()) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, (size_t)smem_bytes) != cudaSuccess)
+      return SMF_ERR_CUDA;
+    it = ks.occ.emplace(key, occ).first;
+  }
+  *occ_out = it->second;
   return SMF_OK;
 }
 
@@ -66,7 +116,7 @@ static int check_tables(const smf_hmm_tables* t) {
 
 // two-kernel path selection: -1 = measured policy (walk_eligible), 0 = never, 1 = whenever possible.
 // Initialised from SMF_FB2_WALK, changed at run time with smf_hmm_set_option("walk", v).
-static int g_walk_mode = [] { const char* e = getenv("SMF_FB2_WALK"); return e ? atoi(e) : -1; }();
+static std::atomic<int> g_walk_mode{[] { const char* e = getenv("SMF_FB2_WALK"); return e ? atoi(e) : -1; }()};
 static int rescale_cadence(const smf_hmm_tables* t);
 
 static int fb_max_threads(int K, bool stats) { return fb_max_threads_c(K, stats); }
@@ -167,7 +217,6 @@ static int plan_fb(int K, int C, int nb, int64_t L64, bool stats, int S, int max
 // Resident reads per SM for a candidate layout: shared memory (228 KB per SM, 1 KB reserved per CTA),
 // registers (64 K per SM) and the 32-CTA limit.
 constexpr int kWalkChunkDefault = 17;
-static bool g_plan_gc_ok = false;
 static int fb2_resident(int total_smem, int block, int groups, int regs) {
   const int by_smem = (228 * 1024) / (total_smem + 1024);
   const int by_regs = 65536 / (regs * block);
@@ -177,8 +226,8 @@ static int fb2_resident(int total_smem, int block, int groups, int regs) {
 }
 
 static int plan_fb2_chunk(int K, int CH, int64_t L64, bool stats, int S, int es, bool want_gamma_one,
-                          bool want_states, int max_smem, Fb2Args* a, Fb2Plan* plan, bool walk = false) {
-  const bool gc_ok = g_plan_gc_ok;  // set by smf_hmm_posterior for the one output set the compact staging serves
+                          bool want_states, int max_smem, Fb2Args* a, Fb2Plan* plan, bool walk = false,
+                          bool gc_ok = false /* caller produces the one output set the compact staging serves */) {
   if (L64 < 1) return SMF_ERR_TOO_LONG;
   if (L64 > (int64_t)CH * 1024) return SMF_ERR_TOO_LONG;
   const int L = (int)L64;
@@ -261,7 +310,7 @@ static int plan_fb2_chunk(int K, int CH, int64_t L64, bool stats, int S, int es,
 
 // chunk 17 whenever the read fits its thread budget; chunk 33 (K = 2, 4) for reads up to twice as long
 static int plan_fb2(int K, int64_t L64, bool stats, int S, int es, bool want_gamma_one, bool want_states,
-                    int max_smem, Fb2Args* a, Fb2Plan* plan, bool walk = false) {
+                    int max_smem, Fb2Args* a, Fb2Plan* plan, bool walk = false, bool gc_ok = false) {
   // Measured on B200 (profiles/r01_chunk_sweep.txt): for K = 2 posterior decode the longer chunk wins
   // whenever it keeps the lanes about as busy (half the scan / barrier overhead per position outweighs
   // the halved warp count); for K = 4 (register pressure) and for the E-step (more live registers)
@@ -289,10 +338,10 @@ static int plan_fb2(int K, int64_t L64, bool stats, int S, int es, bool want_gam
   // favouring longer chunks (less scan work per position), as measured for 17 vs 33.
   if (K == 2 && !stats && (es == 4 || es == 1) &&
       (env_ch == 9 || env_ch == 11 || env_ch == 13 || env_ch == 15 || env_ch == 21 || env_ch == 25 || env_ch == 29) &&
-      plan_fb2_chunk(K, env_ch, L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan) == SMF_OK)
+      plan_fb2_chunk(K, env_ch, L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan, false, gc_ok) == SMF_OK)
     return SMF_OK;
   if (K == 3 && !stats && (es == 4 || es == 1) && (env_ch == 13 || env_ch == 21) &&
-      plan_fb2_chunk(K, env_ch, L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan) == SMF_OK)
+      plan_fb2_chunk(K, env_ch, L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan, false, gc_ok) == SMF_OK)
     return SMF_OK;
   if (K == 2 && !stats && env_ch == 0 && (es == 4 || es == 1)) {
     // (9..15 only matter for reads of one warp: with several warps the longer chunks always win)
@@ -314,7 +363,7 @@ static int plan_fb2(int K, int64_t L64, bool stats, int S, int es, bool want_gam
         }
       }
       tried[bi] = true;
-      if (plan_fb2_chunk(K, cand[bi], L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan) == SMF_OK)
+      if (plan_fb2_chunk(K, cand[bi], L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan, false, gc_ok) == SMF_OK)
         return SMF_OK;
     }
     return SMF_ERR_TOO_LONG;
@@ -337,18 +386,18 @@ static int plan_fb2(int K, int64_t L64, bool stats, int S, int es, bool want_gam
         }
       }
       tried[bi] = true;
-      if (plan_fb2_chunk(K, cand3[bi], L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan) == SMF_OK)
+      if (plan_fb2_chunk(K, cand3[bi], L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan, false, gc_ok) == SMF_OK)
         return SMF_OK;
     }
     return SMF_ERR_TOO_LONG;
   }
   const bool prefer33 = can33 && (env_ch == 33 || (env_ch == 0 && K == 2 && !stats && lane_eff(33) >= 0.9 * lane_eff(17)));
   if (prefer33 &&
-      plan_fb2_chunk(K, 33, L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan) == SMF_OK)
+      plan_fb2_chunk(K, 33, L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan, false, gc_ok) == SMF_OK)
     return SMF_OK;
-  if (plan_fb2_chunk(K, 17, L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan) == SMF_OK)
+  if (plan_fb2_chunk(K, 17, L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan, false, gc_ok) == SMF_OK)
     return SMF_OK;
-  if (can33 && plan_fb2_chunk(K, 33, L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan) == SMF_OK)
+  if (can33 && plan_fb2_chunk(K, 33, L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan, false, gc_ok) == SMF_OK)
     return SMF_OK;
   return SMF_ERR_TOO_LONG;
 }
@@ -422,7 +471,7 @@ static inline int obs_elem_size(int dt) { return dt == SMF_OBS_F32 ? 4 : (dt == 
 // short reads (short_kernel): several reads per warp
 // ---------------------------------------------------------------------------------------
 // -1 = measured policy, 0 = never, 1 = whenever it fits.  SMF_SHORT / smf_hmm_set_option("short", v).
-static int g_short_mode = [] { const char* e = getenv("SMF_SHORT"); return e ? atoi(e) : -1; }();
+static std::atomic<int> g_short_mode{[] { const char* e = getenv("SMF_SHORT"); return e ? atoi(e) : -1; }()};
 // measured (profiles/r01_short.txt): faster than one read per warp up to ~275 positions for K = 2
 // (beyond that fb2_kernel's short chunks 9..15 keep a warp's lanes busy),
 // ~400 for K = 3, ~200 for K = 4
@@ -783,11 +832,11 @@ int smf_hmm_posterior(const smf_hmm_tables* tab, const void* obs, int obs_dtype,
       }
       memset(&b, 0, sizeof(b));
     }
-    g_plan_gc_ok = gamma != nullptr && gamma_state < 0 && states != nullptr && loglik == nullptr &&
-                   obs_dtype == SMF_OBS_F32;
+    const bool gc_ok = gamma != nullptr && gamma_state < 0 && states != nullptr && loglik == nullptr &&
+                       obs_dtype == SMF_OBS_F32;
     const int prc = plan_fb2(tab->n_states, n_pos, false, stats_len(tab), obs_elem_size(obs_dtype),
-                             gamma != nullptr && gamma_state >= 0, states != nullptr, di.max_smem_optin, &b, &p2);
-    g_plan_gc_ok = false;
+                             gamma != nullptr && gamma_state >= 0, states != nullptr, di.max_smem_optin, &b, &p2,
+                             false, gc_ok);
     if (prc == SMF_OK) {
       b.obs = obs;
       b.N = n_reads;
@@ -991,7 +1040,7 @@ int smf_hmm_viterbi(const smf_hmm_tables* tab, const void* obs, int obs_dtype, i
 }
 
 int smf_hmm_call_features(const int8_t* states, const float* post, int target_state,
-                          float threshold, int64_t n_reads, int64_t n_pos,
+                          double threshold, int64_t n_reads, int64_t n_pos,
                           const int64_t* coords, const int32_t* grid_left,
                           const int32_t* grid_right, int64_t n_grid, const double* class_lo_host,
                           const double* class_hi_host, int n_classes, uint8_t* class_out,
@@ -1013,18 +1062,19 @@ int smf_hmm_call_features(const int8_t* states, const float* post, int target_st
   const int maxruns = ((int)n_pos + 1) / 2 + 1;
   const size_t smem = (size_t)maxruns * 8 + (2 * kFeatWarps + 2) * 4 + (size_t)align_up(maxruns, 16);
   if ((long long)smem > di.max_smem_optin) return SMF_ERR_TOO_LONG;
-  if (cudaFuncSetAttribute(call_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-      cudaSuccess)
-    return SMF_ERR_CUDA;
+  if (prepare_kernel((const void*)call_features_kernel, (int)smem, false) != SMF_OK) return SMF_ERR_CUDA;
   int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, call_features_kernel, kFeatThreads, smem) !=
-          cudaSuccess || occ < 1)
+  if (cached_occupancy((const void*)call_features_kernel, kFeatThreads, (int)smem, &occ) != SMF_OK || occ < 1)
     return SMF_ERR_CUDA;
   FeatArgs a;
   a.states = states;
   a.post = post;
   a.target = target_state;
-  a.thr = threshold;
+  // (double)post >= threshold  <=>  post >= the smallest float that is >= threshold: the kernels compare
+  // floats and still decide exactly like the reference's fp64 comparison (HMM.py:1318-1322)
+  float thr_up = (float)threshold;
+  if ((double)thr_up < threshold) thr_up = nextafterf(thr_up, INFINITY);
+  a.thr = thr_up;
   a.N = n_reads;
   a.L = (int)n_pos;
   a.coords = reinterpret_cast<const long long*>(coords);
@@ -1080,12 +1130,9 @@ int smf_hmm_merge_runs(const uint8_t* layer, int64_t n_reads, int64_t n_grid,
   // five word arrays (bit masks + word scans) + one staging tile per warp
   const size_t smem = (size_t)(((((int)n_grid + 31) / 32) + 3) & ~3) * 20 + (size_t)kMcWarps * kMcTileBytes;
   if ((long long)smem > di.max_smem_optin) return SMF_ERR_TOO_LONG;
-  if (cudaFuncSetAttribute(merge_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-      cudaSuccess)
-    return SMF_ERR_CUDA;
+  if (prepare_kernel((const void*)merge_runs_kernel, (int)smem, false) != SMF_OK) return SMF_ERR_CUDA;
   int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, merge_runs_kernel, kMcThreads, smem) !=
-          cudaSuccess || occ < 1)
+  if (cached_occupancy((const void*)merge_runs_kernel, kMcThreads, (int)smem, &occ) != SMF_OK || occ < 1)
     return SMF_ERR_CUDA;
   MergeArgs a;
   memset(&a, 0, sizeof(a));
@@ -1128,12 +1175,9 @@ int smf_hmm_merge_chain(const uint8_t* layer, int64_t n_reads, int64_t n_grid, c
   // five word arrays (bit masks + word scans) + one staging tile per warp
   const size_t smem = (size_t)(((((int)n_grid + 31) / 32) + 3) & ~3) * 20 + (size_t)kMcWarps * kMcTileBytes;
   if ((long long)smem > di.max_smem_optin) return SMF_ERR_TOO_LONG;
-  if (cudaFuncSetAttribute(merge_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-      cudaSuccess)
-    return SMF_ERR_CUDA;
+  if (prepare_kernel((const void*)merge_runs_kernel, (int)smem, false) != SMF_OK) return SMF_ERR_CUDA;
   int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, merge_runs_kernel, kMcThreads, smem) !=
-          cudaSuccess || occ < 1)
+  if (cached_occupancy((const void*)merge_runs_kernel, kMcThreads, (int)smem, &occ) != SMF_OK || occ < 1)
     return SMF_ERR_CUDA;
   MergeArgs a;
   memset(&a, 0, sizeof(a));

@@ -19,6 +19,12 @@ struct DeviceInfo {
   int max_smem_optin = 0;
 };
 
+// Per-(kernel, device) launch state, kept behind a mutex in api.cu: the dynamic shared-memory opt-in is
+// raised only when a launch needs more than any earlier one did (cudaFuncSetAttribute is not free), and
+// occupancy queries are answered from a small cache.
+int prepare_kernel(const void* kern, int smem_bytes, bool max_carveout);
+int cached_occupancy(const void* kern, int block, int smem_bytes, int* occ_out);
+
 struct FbPlan {
   int T, chunk, groups, smem, block;
 };

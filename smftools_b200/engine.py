@@ -315,3 +315,95 @@ def span_mask(n_reads: int, n_grid: int, device, *, covered: Optional[torch.Tens
                                    int(n_grid), _ptr(valid), _stream_ptr(dev))
     _lib.check(rc, "smf_hmm_span_mask")
     return valid
+
+
+# ---------------------------------------------------------------------------------------------
+# boundary helpers: widening, layer expansion, explicit async copies (csrc/host_io.cu)
+# ---------------------------------------------------------------------------------------------
+def widen_decode(states8: Optional[torch.Tensor], states64: Optional[torch.Tensor],
+                 gamma32: Optional[torch.Tensor], gamma64: Optional[torch.Tensor]) -> None:
+    """int8 states -> int64 and float posteriors -> double in one launch (``smf_hmm_widen_decode``)."""
+    lib = _lib.load()
+    ref = states8 if states8 is not None else gamma32
+    if ref is None:
+        return
+    _require_cuda(ref, "states/gamma")
+    for t, dt, nm in ((states8, torch.int8, "states8"), (states64, torch.int64, "states64"),
+                      (gamma32, torch.float32, "gamma32"), (gamma64, torch.float64, "gamma64")):
+        if t is not None and (t.dtype != dt or not t.is_contiguous()):
+            raise ValueError(f"{nm} must be contiguous {dt}")
+    if (states8 is None) != (states64 is None) or (gamma32 is None) != (gamma64 is None):
+        raise ValueError("widen_decode needs source and destination of each pair")
+    ns = states8.numel() if states8 is not None else 0
+    ng = gamma32.numel() if gamma32 is not None else 0
+    if (states64 is not None and states64.numel() != ns) or (gamma64 is not None and gamma64.numel() != ng):
+        raise ValueError("widen_decode: size mismatch")
+    dev = ref.device
+    with torch.cuda.device(dev):
+        rc = lib.smf_hmm_widen_decode(_ptr(states8), _ptr(states64), ns, _ptr(gamma32), _ptr(gamma64), ng,
+                                      _stream_ptr(dev))
+    _lib.check(rc, "smf_hmm_widen_decode")
+
+
+def expand_layers(n_reads: int, n_grid: int, n_pos: int, *, states: Optional[torch.Tensor],
+                  post: Optional[torch.Tensor], post_stride: int, site_of_col: Optional[torch.Tensor],
+                  valid: Optional[torch.Tensor], groups: Sequence[Tuple[torch.Tensor, Optional[torch.Tensor], bool]],
+                  layers: Sequence[Tuple[int, int, int, torch.Tensor]]) -> None:
+    """Write final dense layers from packed results (``smf_hmm_expand_layers``).
+
+    ``groups``: ``(class_or_code uint8 [N,V], run_len int32 [N,V] | None, packed)``;
+    ``layers``: ``(kind, group, cls, out)`` with ``out`` a float64 / float32 CUDA tensor of N*V elements.
+    ``post`` is the tensor whose element ``(n, t)`` sits at ``post.data_ptr() + 4 * (n*L + t) * post_stride``.
+    """
+    lib = _lib.load()
+    if not layers:
+        return
+    dev = layers[0][3].device
+    G = (_lib.LayerGroup * max(1, len(groups)))()
+    for i, (cls, rl, packed) in enumerate(groups):
+        _require_cuda(cls, "group class/code")
+        if cls.dtype != torch.uint8 or cls.numel() != n_reads * n_grid or not cls.is_contiguous():
+            raise ValueError("group class/code must be contiguous uint8 [N, V]")
+        if rl is not None and (rl.dtype != torch.int32 or rl.numel() != n_reads * n_grid or not rl.is_contiguous()):
+            raise ValueError("group run_len must be contiguous int32 [N, V]")
+        G[i] = _lib.LayerGroup(_ptr(cls), _ptr(rl), 1 if packed else 0, 0)
+    D = (_lib.LayerDesc * len(layers))()
+    for i, (kind, group, cls_idx, out) in enumerate(layers):
+        _require_cuda(out, "layer output")
+        if out.dtype not in (torch.float64, torch.float32) or out.numel() != n_reads * n_grid or not out.is_contiguous():
+            raise ValueError("layer outputs must be contiguous float64 / float32 tensors of N*V elements")
+        D[i] = _lib.LayerDesc(_ptr(out), int(kind), int(group), int(cls_idx), 1 if out.dtype == torch.float32 else 0)
+    if site_of_col is not None and (site_of_col.dtype != torch.int32 or site_of_col.numel() != n_grid):
+        raise ValueError("site_of_col must be int32 of length V")
+    if valid is not None and (valid.dtype != torch.uint8 or valid.numel() != n_reads * n_grid or not valid.is_contiguous()):
+        raise ValueError("valid must be contiguous uint8 [N, V]")
+    with torch.cuda.device(dev):
+        rc = lib.smf_hmm_expand_layers(int(n_reads), int(n_grid), int(n_pos), _ptr(states), _ptr(post), int(post_stride),
+                                       _ptr(site_of_col), _ptr(valid), G, len(groups), D, len(layers), _stream_ptr(dev))
+    _lib.check(rc, "smf_hmm_expand_layers")
+
+
+def copy_to_host_async(dst: np.ndarray, src: torch.Tensor, stream: torch.cuda.Stream) -> None:
+    """cudaMemcpyAsync device -> host on ``stream`` (link speed when ``dst`` is page-locked)."""
+    if not (dst.flags.c_contiguous and src.is_contiguous()):
+        raise ValueError("copy_to_host_async needs contiguous source and destination")
+    nbytes = src.numel() * src.element_size()
+    if dst.nbytes != nbytes:
+        raise ValueError(f"copy_to_host_async: {dst.nbytes} destination bytes for {nbytes} source bytes")
+    with torch.cuda.device(src.device):
+        rc = _lib.load().smf_hmm_copy_async(ctypes.c_void_p(dst.ctypes.data), _ptr(src), nbytes, _lib.COPY_D2H,
+                                            int(stream.cuda_stream))
+    _lib.check(rc, "smf_hmm_copy_async")
+
+
+def copy_to_device_async(dst: torch.Tensor, src: np.ndarray, stream: torch.cuda.Stream) -> None:
+    """cudaMemcpyAsync host -> device on ``stream``."""
+    if not (src.flags.c_contiguous and dst.is_contiguous()):
+        raise ValueError("copy_to_device_async needs contiguous source and destination")
+    nbytes = dst.numel() * dst.element_size()
+    if src.nbytes != nbytes:
+        raise ValueError(f"copy_to_device_async: {src.nbytes} source bytes for {nbytes} destination bytes")
+    with torch.cuda.device(dst.device):
+        rc = _lib.load().smf_hmm_copy_async(_ptr(dst), ctypes.c_void_p(src.ctypes.data), nbytes, _lib.COPY_H2D,
+                                            int(stream.cuda_stream))
+    _lib.check(rc, "smf_hmm_copy_async")

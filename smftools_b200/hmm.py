@@ -25,7 +25,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import _lib, engine
+from . import _lib, engine, hostmem
 
 COVERED_BASE_MASK = "covered_base_mask"  # reference constants.py:141
 
@@ -183,8 +183,8 @@ def _default_cuda_device() -> torch.device:
 
 
 def _span_inputs(adata, *, start_key: str, end_key: str, use_original_var_names: bool, device):
-    """Device inputs of the read-span test (HMM.py:178-226): ``{"covered": u8 [N,V]}`` when the
-    coverage mask layer exists, else ``{"coords": i64 [V], "start": f64 [N], "end": f64 [N]}``."""
+    """Inputs of the read-span test (HMM.py:178-226): ``{"covered": u8 [N,V] (HOST numpy)}`` when the
+    coverage mask layer exists, else device tensors ``{"coords": i64 [V], "start": f64 [N], "end": f64 [N]}``."""
     coord_source = adata.var_names
     if use_original_var_names and "Original_var_names" in adata.var:
         orig = np.asarray(adata.var["Original_var_names"])
@@ -202,7 +202,8 @@ def _span_inputs(adata, *, start_key: str, end_key: str, use_original_var_names:
         covered = np.asarray(adata.layers[COVERED_BASE_MASK], dtype=bool)
         if covered.shape != tuple(adata.shape):
             raise ValueError("covered_base_mask must match adata shape")
-        return {"covered": torch.from_numpy(np.ascontiguousarray(covered).view(np.uint8)).to(device)}
+        # host array: callers upload it a block of reads at a time (it is as large as a layer)
+        return {"covered": np.ascontiguousarray(covered).view(np.uint8)}
     try:
         starts = np.asarray(adata.obs[start_key], dtype=float)
         ends = np.asarray(adata.obs[end_key], dtype=float)
@@ -220,8 +221,18 @@ def _span_validity(adata, *, start_key: str, end_key: str, use_original_var_name
     dev = _default_cuda_device()
     inp = _span_inputs(adata, start_key=start_key, end_key=end_key,
                        use_original_var_names=use_original_var_names, device=dev)
-    valid = engine.span_mask(adata.n_obs, adata.n_vars, dev, **inp)
-    return valid.cpu().numpy().astype(bool)
+    n_obs, n_vars = int(adata.n_obs), int(adata.n_vars)
+    out = np.empty((n_obs, n_vars), dtype=bool)
+    rows = max(1, int((1 << 30) // max(n_vars, 1)))
+    for lo in range(0, n_obs, rows):
+        hi = min(n_obs, lo + rows)
+        if "covered" in inp:
+            valid = engine.span_mask(hi - lo, n_vars, dev, covered=torch.from_numpy(inp["covered"][lo:hi]).to(dev))
+        else:
+            valid = engine.span_mask(hi - lo, n_vars, dev, coords=inp["coords"], start=inp["start"][lo:hi].contiguous(),
+                                     end=inp["end"][lo:hi].contiguous())
+        out[lo:hi] = valid.cpu().numpy().astype(bool)
+    return out
 
 
 def mask_layers_outside_read_span(
@@ -260,27 +271,10 @@ def mask_layers_outside_read_span(
 
 
 def _alloc_host_arrays(specs: Dict[str, Tuple[Tuple[int, ...], Any]]) -> Dict[str, np.ndarray]:
-    """Allocate host arrays ``name -> (shape, dtype)`` and touch their pages from several threads:
-    first-touch page faults (the kernel zeroing 4 KB pages) run at ~3 GB/s on one core and dominate the
-    cost of materialising tens of GB of results; ``ndarray.fill`` releases the GIL, so a small pool
-    spreads them over the cores."""
-    from concurrent.futures import ThreadPoolExecutor
-
-    out = {nm: np.empty(shape, dtype=dt) for nm, (shape, dt) in specs.items()}
-    total = sum(a.nbytes for a in out.values())
-    workers = min(8, os.cpu_count() or 1)
-    if total < (64 << 20) or workers < 2 or os.environ.get("SMF_NO_PRETOUCH"):
-        return out
-    jobs = []
-    for a in out.values():
-        n = a.shape[0] if a.ndim else 0
-        if n < workers:
-            continue
-        step = (n + workers - 1) // workers
-        jobs.extend((a, lo, min(n, lo + step)) for lo in range(0, n, step))
-    with ThreadPoolExecutor(max_workers=workers) as pool:
-        list(pool.map(lambda j: j[0][j[1]:j[2]].fill(0), jobs))
-    return out
+    """Result arrays ``name -> (shape, dtype)`` carved from the page-locked host pool (``hostmem``): their
+    pages are first touched by several threads and registered with the driver once, device-to-host copies
+    land in them at link speed, and the memory is reused by later calls once the caller drops the arrays."""
+    return hostmem.pool().empty_many(specs)
 
 
 def _alloc_host_layers(shape, dtypes: Dict[str, Any]) -> Dict[str, np.ndarray]:
@@ -291,6 +285,34 @@ def _alloc_host_layers(shape, dtypes: Dict[str, Any]) -> Dict[str, np.ndarray]:
 def _device_to_host_layer(dst: np.ndarray, src: torch.Tensor) -> None:
     """Copy a device tensor straight into (a row block of) a host layer -- no intermediate host tensor."""
     torch.from_numpy(dst).copy_(src)
+
+
+class CodedU8:
+    """Opt-in marker for observations already in the kernels' compact code: uint8 with 0 = unmodified,
+    1 = modified, anything else = missing (1 byte per position over the host link instead of 8).
+
+    A *plain* uint8 array keeps the reference's meaning, ``np.asarray(X, dtype=float)`` (HMM.py:694): the
+    byte value itself is the observation.  ``smftools_b200.build_obs`` / the input builders return this
+    wrapper; ``CodedU8(array)`` wraps an array the caller coded itself."""
+
+    __slots__ = ("data",)
+
+    def __init__(self, data):
+        dt = data.dtype
+        if dt not in (np.uint8, torch.uint8):
+            raise ValueError("CodedU8 wraps uint8 data")
+        self.data = data
+
+    @property
+    def shape(self):
+        return tuple(self.data.shape)
+
+    @property
+    def ndim(self):
+        return len(self.data.shape)
+
+    def __len__(self):
+        return int(self.data.shape[0])
 
 
 def _run_lengths_np(bin_mat: np.ndarray) -> np.ndarray:
@@ -472,17 +494,25 @@ class BaseHMM(nn.Module):
 
     @staticmethod
     def _as_obs_source(X):
-        """Accept numpy / torch input.  Float64 (the reference's host dtype), float32 and uint8
-        (binary 0/1, other = missing) go to the device unchanged; anything else is widened to
-        float64 like ``np.asarray(X, dtype=float)`` (HMM.py:694)."""
+        """Accept numpy / torch input; returns ``(array, numeric_u8)``.  Float64 (the reference's host
+        dtype) and float32 go to the device unchanged; ``CodedU8`` input is the kernels' 0 / 1 / missing
+        code; plain uint8 keeps its numeric meaning like ``np.asarray(X, dtype=float)`` (HMM.py:694) -- it
+        crosses the link as bytes and is widened on the device (``numeric_u8``); anything else is widened
+        to float64 on the host."""
+        if isinstance(X, CodedU8):
+            return X.data, False
         if isinstance(X, torch.Tensor):
-            if X.dtype not in (torch.float32, torch.float64, torch.uint8):
+            if X.dtype == torch.uint8:
+                return X, True
+            if X.dtype not in (torch.float32, torch.float64):
                 X = X.to(torch.float64)
-            return X
+            return X, False
         X = np.asarray(X)
-        if X.dtype not in (np.float32, np.float64, np.uint8):
+        if X.dtype == np.uint8:
+            return X, True
+        if X.dtype not in (np.float32, np.float64):
             X = np.asarray(X, dtype=float)
-        return X
+        return X, False
 
     def _chunks(self, N: int, L: int, C: int, in_item: int, out_bytes_per_pos: int):
         per_read = L * (C * in_item + out_bytes_per_pos) + 64
@@ -491,10 +521,14 @@ class BaseHMM(nn.Module):
             yield lo, min(N, lo + rows)
 
     @staticmethod
-    def _to_device(chunk, device) -> torch.Tensor:
+    def _to_device(chunk, device, numeric_u8: bool = False) -> torch.Tensor:
         if isinstance(chunk, torch.Tensor):
-            return chunk.to(device).contiguous()
-        return torch.from_numpy(np.ascontiguousarray(chunk)).to(device)
+            t = chunk.to(device).contiguous()
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(chunk)).to(device)
+        if numeric_u8 and t.dtype == torch.uint8:
+            t = t.to(torch.float32)  # byte value = observation (exact in fp32)
+        return t
 
     # ---- decoding (HMM.py:673-720) -----------------------------------------------------------
     def decode(
@@ -512,16 +546,16 @@ class BaseHMM(nn.Module):
         Like the reference, the posterior is always computed; ``decode="viterbi"`` replaces the
         arg-max states with the Viterbi path.  Returns ``(int64, model dtype)`` host arrays, or the
         kernels' native ``(int8, float32)`` when ``compact=True``.  ``out=(states, gamma)`` lets the
-        caller supply (ideally pinned) result buffers.  Host inputs are streamed through the device
-        in read chunks: H2D copy, kernels and D2H copy of consecutive chunks overlap on three
-        streams.
+        caller supply result buffers (page-locked in place for the call when they are not already).
+        Otherwise the results are fresh arrays from the page-locked host pool (``hostmem``).  Host
+        inputs are streamed through the device in read chunks: staging + H2D copy, kernels (incl. the
+        widening to int64 / float64) and D2H copy of consecutive chunks overlap (``stream.py``).
         """
         device = self._ensure_device_dtype(device)
-        src = self._as_obs_source(X)
+        src, numeric_u8 = self._as_obs_source(X)
         if src.ndim not in (2, 3):
             raise ValueError(f"X must be 2D or 3D; got shape {tuple(src.shape)}")
         N, L = int(src.shape[0]), int(src.shape[1])
-        C = int(src.shape[2]) if src.ndim == 3 else 1
         if coords is None:
             coords = np.arange(L, dtype=int)
         coords = np.asarray(coords, dtype=int)
@@ -543,93 +577,10 @@ class BaseHMM(nn.Module):
             states_out, gamma_out = bufs["states"], bufs["gamma"]
         if N == 0 or L == 0:
             return states_out, gamma_out
-        self._decode_stream(src, tables, bins, use_viterbi, states_out, gamma_out, device, C)
+        from .stream import decode_stream
+
+        decode_stream(self, src, numeric_u8, tables, bins, use_viterbi, states_out, gamma_out, device)
         return states_out, gamma_out
-
-    def _decode_stream(self, src, tables, bins, use_viterbi, states_out, gamma_out, device, C):
-        """Chunked, triple-stream decode: chunk i+1 uploads while chunk i computes and chunk i-1
-        downloads.  Device buffers are double-buffered; events order reuse."""
-        N, L = int(src.shape[0]), int(src.shape[1])
-        K = self.n_states
-        src_t = src if isinstance(src, torch.Tensor) else torch.from_numpy(src)
-        on_device = src_t.is_cuda
-        st_t = torch.from_numpy(states_out)
-        g_t = torch.from_numpy(gamma_out)
-        widen_g = g_t.dtype != torch.float32
-        widen_s = st_t.dtype != torch.int8
-        in_item = src_t.element_size()
-        per_read = L * (C * in_item + K * (4 + (g_t.element_size() if widen_g else 0)) + 2 + st_t.element_size())
-        rows = max(1, int(self.device_chunk_bytes // (2 * per_read)))
-        rows = min(rows, max(1, -(-N // 4)) if N >= 4096 else N)  # >= 4 chunks on big inputs so copies overlap
-        cur = torch.cuda.current_stream(device)
-        s_in = torch.cuda.Stream(device)
-        s_out = torch.cuda.Stream(device)
-        # The staging buffers below come from the caching allocator and may be memory that
-        # earlier work on `cur` is still using; the side streams must not touch them before
-        # that work has finished.
-        entry = torch.cuda.Event()
-        entry.record(cur)
-        s_in.wait_event(entry)
-        s_out.wait_event(entry)
-        nbuf = 2
-        obs_shape = (rows, L) if src_t.dim() == 2 else (rows, L, C)
-        d_obs = [None] * nbuf if on_device else [torch.empty(obs_shape, dtype=src_t.dtype, device=device) for _ in range(nbuf)]
-        d_g = [torch.empty((rows, L, K), dtype=torch.float32, device=device) for _ in range(nbuf)]
-        d_s = [torch.empty((rows, L), dtype=torch.int8, device=device) for _ in range(nbuf)]
-        d_gw = [torch.empty((rows, L, K), dtype=g_t.dtype, device=device) for _ in range(nbuf)] if widen_g else None
-        d_sw = [torch.empty((rows, L), dtype=st_t.dtype, device=device) for _ in range(nbuf)] if widen_s else None
-        ws = torch.empty((rows * L,), dtype=torch.uint8, device=device) if use_viterbi else None
-        ev_in = [None] * nbuf
-        ev_cmp = [None] * nbuf
-        ev_out = [None] * nbuf
-        try:
-            self._decode_chunks(src_t, st_t, g_t, tables, bins, use_viterbi, on_device, widen_g, widen_s, rows, N,
-                                cur, s_in, s_out, d_obs, d_g, d_s, d_gw, d_sw, ws, ev_in, ev_cmp, ev_out, nbuf)
-        finally:
-            # also on errors: nothing may still be in flight on the side streams when the staging
-            # buffers go back to the allocator
-            s_in.synchronize()
-            s_out.synchronize()
-            cur.synchronize()
-
-    def _decode_chunks(self, src_t, st_t, g_t, tables, bins, use_viterbi, on_device, widen_g, widen_s, rows, N,
-                       cur, s_in, s_out, d_obs, d_g, d_s, d_gw, d_sw, ws, ev_in, ev_cmp, ev_out, nbuf):
-        for i, lo in enumerate(range(0, N, rows)):
-            hi = min(N, lo + rows)
-            n = hi - lo
-            b = i % nbuf
-            if on_device:
-                obs = src_t[lo:hi].contiguous()
-            else:
-                if ev_cmp[b] is not None:
-                    s_in.wait_event(ev_cmp[b])
-                with torch.cuda.stream(s_in):
-                    d_obs[b][:n].copy_(src_t[lo:hi], non_blocking=True)
-                    ev_in[b] = torch.cuda.Event()
-                    ev_in[b].record(s_in)
-                cur.wait_event(ev_in[b])
-                obs = d_obs[b][:n]
-            if ev_out[b] is not None:
-                cur.wait_event(ev_out[b])
-            engine.posterior(tables, obs, bins, want_gamma=True, want_states=not use_viterbi,
-                             out_gamma=d_g[b][:n], out_states=None if use_viterbi else d_s[b][:n])
-            if use_viterbi:
-                engine.viterbi(tables, obs, bins, out_states=d_s[b][:n], workspace=ws)
-            g_src, s_src = d_g[b][:n], d_s[b][:n]
-            if widen_g:
-                d_gw[b][:n].copy_(g_src)
-                g_src = d_gw[b][:n]
-            if widen_s:
-                d_sw[b][:n].copy_(s_src)
-                s_src = d_sw[b][:n]
-            ev_cmp[b] = torch.cuda.Event()
-            ev_cmp[b].record(cur)
-            s_out.wait_event(ev_cmp[b])
-            with torch.cuda.stream(s_out):
-                g_t[lo:hi].copy_(g_src, non_blocking=True)
-                st_t[lo:hi].copy_(s_src, non_blocking=True)
-                ev_out[b] = torch.cuda.Event()
-                ev_out[b].record(s_out)
 
     # ---- EM fit (HMM.py:724-821, 1518-1630) ----------------------------------------------------
     def fit(
@@ -646,7 +597,7 @@ class BaseHMM(nn.Module):
         verbose: bool = False,
         **kwargs,
     ) -> List[float]:
-        src = self._as_obs_source(X)
+        src, numeric_u8 = self._as_obs_source(X)
         if src.ndim not in (2, 3):
             raise ValueError(f"X must be 2D or 3D; got {tuple(src.shape)}")
         L = int(src.shape[1])
@@ -654,6 +605,8 @@ class BaseHMM(nn.Module):
             coords = np.arange(L, dtype=int)
         coords = np.asarray(coords, dtype=int)
         device = self._ensure_device_dtype(device)
+        if src.dtype in (np.uint8, torch.uint8) and not numeric_u8:
+            src = CodedU8(src)  # keep the opt-in visible to fit_em
         return self.fit_em(
             src, coords, device=device, max_iter=max_iter, tol=tol, update_start=update_start,
             update_trans=update_trans, update_emission=update_emission, verbose=verbose, **kwargs,
@@ -710,13 +663,13 @@ class BaseHMM(nn.Module):
         sum-all-reduced over NCCL before the (replicated, deterministic) M-step, so every rank
         holds bit-identical parameters.
         """
-        src = self._as_obs_source(X)
+        src, numeric_u8 = self._as_obs_source(X)
         self._check_fit_input(src)
         device = self._ensure_device_dtype(device)
         N, L = int(src.shape[0]), int(src.shape[1])
         self._prepare_fit(src, device)
         bins = self._bins_for(np.asarray(coords, dtype=int), L, device)
-        resident = self._resident_chunks(src, device)
+        resident = self._resident_chunks(src, device, numeric_u8)
         hist: List[float] = []
         workspace = None
         for it in range(1, int(max_iter) + 1):
@@ -748,27 +701,29 @@ class BaseHMM(nn.Module):
             total = torch.zeros((engine.stats_len(tables),), dtype=torch.float64, device=device)
         return total
 
-    def _resident_chunks(self, src, device):
+    def _resident_chunks(self, src, device, numeric_u8: bool = False):
         """Observations for the EM loop: device-resident read chunks (uploaded once, reused by every
         iteration), or -- when the input does not fit in the free device memory -- a generator that
         streams the chunks from the host in every iteration."""
-        if isinstance(src, torch.Tensor) and src.is_cuda:
-            return [src.contiguous()]
         N = int(src.shape[0])
         row_bytes = int(np.prod(src.shape[1:])) * (src.element_size() if isinstance(src, torch.Tensor)
                                                    else src.dtype.itemsize)
         rows = max(1, int(self.device_chunk_bytes // max(row_bytes, 1)))
         bounds = [(lo, min(N, lo + rows)) for lo in range(0, N, rows)]
+        if isinstance(src, torch.Tensor) and src.is_cuda:
+            # already resident: row-block views (no copy) keep the per-launch workspace bounded
+            src = src.contiguous()
+            return [self._to_device(src[lo:hi], device, numeric_u8) for lo, hi in bounds]
         free, _total = torch.cuda.mem_get_info(device)
-        if N * row_bytes <= 0.8 * free:
-            return [self._to_device(src[lo:hi], device) for lo, hi in bounds]
+        if N * row_bytes * (4 if numeric_u8 else 1) <= 0.8 * free:
+            return [self._to_device(src[lo:hi], device, numeric_u8) for lo, hi in bounds]
 
         class _Streamed:
             max_rows = max(hi - lo for lo, hi in bounds)
 
             def __iter__(inner):
                 for lo, hi in bounds:
-                    yield self._to_device(src[lo:hi], device)
+                    yield self._to_device(src[lo:hi], device, numeric_u8)
 
         return _Streamed()
 
@@ -1014,7 +969,7 @@ class BaseHMM(nn.Module):
             adata.uns[uns_key] = []
         appended = list(adata.uns.get(uns_key, []))
 
-        src = self._as_obs_source(X)
+        src, numeric_u8 = self._as_obs_source(X)
         coords = np.asarray(coords, dtype=int)
         var_mask = np.asarray(var_mask, dtype=bool)
         if var_mask.shape[0] != adata.n_vars:
@@ -1112,130 +1067,171 @@ class BaseHMM(nn.Module):
         # DEVICE, chunk by chunk, and land in host memory once -- instead of uint8 / int32 host layers that
         # mask_layers_outside_read_span re-reads, converts and masks on one CPU core (HMM.py:1372-1377).
         fast_final = bool(kernel_ok and mask_to_read_span and feature_sets and fresh_base
-                          and all(gr["clean"] for gr in groups))
+                          and all(gr["clean"] for gr in groups) and len(groups) <= 8)
+        layer_plan = []  # (name, kind, group index, class index, is_float32)
         if fast_final:
             if "reference_start" not in adata.obs or "reference_end" not in adata.obs:
                 raise KeyError("Missing 'reference_start' or 'reference_end' in adata.obs.")
             span_in = _span_inputs(adata, start_key="reference_start", end_key="reference_end",
                                    use_original_var_names=mask_use_original_var_names, device=device)
-            fresh_names = [states_name] + ([post_name] if post_name is not None else [])
-            for gr in groups:
-                fresh_names += [gr["all_layer"], f"{gr['all_layer']}_lengths"]
-                for feat in gr["feats"]:
-                    fresh_names += [f"{prefix}_{feat}", f"{prefix}_{feat}_lengths"]
+            layer_plan.append((states_name, _lib.LAYER_STATES, 0, 0, False))
+            if post_name is not None:
+                layer_plan.append((post_name, _lib.LAYER_POSTERIOR, 0, 0, True))
+            for gi, gr in enumerate(groups):
+                layer_plan.append((gr["all_layer"], _lib.LAYER_ANY, gi, 0, False))
+                layer_plan.append((f"{gr['all_layer']}_lengths", _lib.LAYER_ANY_LEN, gi, 0, False))
+                for ci, feat in enumerate(gr["feats"]):
+                    layer_plan.append((f"{prefix}_{feat}", _lib.LAYER_CLASS, gi, ci, False))
+                    layer_plan.append((f"{prefix}_{feat}_lengths", _lib.LAYER_CLASS_LEN, gi, ci, False))
+            fast_final = len(layer_plan) <= 64
+        if fast_final:
+            fresh_names = [p[0] for p in layer_plan]
             for nm, arr in _alloc_host_layers(
-                    (n_obs, n_vars), {nm: (np.float32 if nm == post_name else np.float64) for nm in fresh_names}).items():
+                    (n_obs, n_vars), {p[0]: (np.float32 if p[4] else np.float64) for p in layer_plan}).items():
                 adata.layers[nm] = arr
-            masked_idx_d = torch.from_numpy(np.ascontiguousarray(masked_idx, dtype=np.int64)).to(device)
-            take_d = torch.from_numpy(np.ascontiguousarray(take, dtype=np.int64)).to(device)
-            nan64 = torch.tensor(float("nan"), dtype=torch.float64, device=device)
-            nan32 = torch.tensor(float("nan"), dtype=torch.float32, device=device)
+            site_of_col = np.full((n_vars,), -1, dtype=np.int32)
+            site_of_col[masked_idx] = take.astype(np.int32)
+            site_of_col_d = torch.from_numpy(site_of_col).to(device)
 
         # ---- decode + feature calling on the device, one chunk of reads at a time ----
+        from .stream import ChunkUploader
+
         tables = self._host_tables()
         bins = self._bins_for(coords, L, device)
         K = self.n_states
         C = int(src.shape[2]) if src.ndim == 3 else 1
         item = src.element_size() if isinstance(src, torch.Tensor) else src.dtype.itemsize
-        per_read = L * (C * item + 4 * K + 2) + n_vars * (5 * max(1, len(groups)) + (26 if fast_final else 0)) + 64
+        if numeric_u8:
+            item += 4
+        n_f64 = sum(1 for p in layer_plan if not p[4])
+        n_f32 = sum(1 for p in layer_plan if p[4])
+        stage_row = n_vars * (8 * n_f64 + 4 * n_f32)
+        per_read = L * (2 * C * item + 4 * K + 2) + n_vars * (5 * max(1, len(groups)) + 2) + 2 * stage_row + 64
         rows = max(1, int(self.device_chunk_bytes // per_read))
-        for lo in range(0, N, rows):
-            hi = min(N, lo + rows)
-            obs = self._to_device(src[lo:hi], device)
-            gamma_d, states_d, _ = engine.posterior(tables, obs, bins, want_gamma=True,
-                                                    want_states=not use_viterbi)
-            if use_viterbi:
-                states_d = engine.viterbi(tables, obs, bins)
-            del obs
+        if fast_final:
+            rows = max(1, min(rows, int((384 << 20) // max(stage_row, 1))))
+        rows = min(rows, max(N, 1))
+        cur = torch.cuda.current_stream(device)
+        uploader = ChunkUploader(src, rows, device)
+        entry = torch.cuda.Event()
+        entry.record(cur)
+        uploader.wait_entry(entry)
+        ev_cmp = [None, None]
+        ev_out = [None, None]
+        if fast_final:
+            s_out = torch.cuda.Stream(device)
+            s_out.wait_event(entry)
+            stage64 = [torch.empty((n_f64, rows, n_vars), dtype=torch.float64, device=device) for _ in range(2)]
+            stage32 = [torch.empty((max(n_f32, 1), rows, n_vars), dtype=torch.float32, device=device) for _ in range(2)]
+        try:
+            for ck, lo in enumerate(range(0, N, rows)):
+                hi = min(N, lo + rows)
+                b = ck % 2
+                obs = uploader.upload(ck, lo, hi, ev_cmp[b])
+                if numeric_u8 and obs.dtype == torch.uint8:
+                    obs = obs.to(torch.float32)
+                gamma_d, states_d, _ = engine.posterior(tables, obs, bins, want_gamma=True,
+                                                        want_states=not use_viterbi)
+                if use_viterbi:
+                    states_d = engine.viterbi(tables, obs, bins)
+                del obs
+                if not fast_final:
+                    states_h = states_d.cpu().numpy()
+                    adata.layers[states_name][lo:hi, masked_idx] = states_h[:, take]
+                    if post_name is not None:
+                        post_h = gamma_d[:, :, t_post].contiguous().cpu().numpy()
+                        adata.layers[post_name][lo:hi, masked_idx] = post_h[:, take]
+                packed = []
+                for gr in groups:
+                    all_layer, feats, ranges, target_idx = gr["all_layer"], gr["feats"], gr["ranges"], gr["target"]
+                    if kernel_ok:
+                        if use_viterbi:
+                            cls_d, len_d, _ = engine.call_features(
+                                states=states_d, post=None, target=target_idx, threshold=0.0, coords=coords_d,
+                                grid_left=left_d, grid_right=right_d, n_grid=n_vars, ranges=ranges)
+                        else:
+                            post_d = gamma_d[:, :, target_idx].contiguous()
+                            cls_d, len_d, _ = engine.call_features(
+                                states=None, post=post_d, target=target_idx, threshold=float(prob_threshold),
+                                coords=coords_d, grid_left=left_d, grid_right=right_d, n_grid=n_vars, ranges=ranges)
+                        if fast_final:
+                            packed.append((cls_d, len_d, False))
+                            continue
+                        cls_h = cls_d.cpu().numpy()
+                        len_h = len_d.cpu().numpy()
+                        any_hit = cls_h > 0
+                        if gr["clean"]:
+                            adata.layers[all_layer][lo:hi] = any_hit.astype(np.uint8)
+                            adata.layers[f"{all_layer}_lengths"][lo:hi] = np.where(any_hit, len_h, 0).astype(np.int32)
+                            for ci, feat in enumerate(feats):
+                                hit = cls_h == (ci + 1)
+                                adata.layers[f"{prefix}_{feat}"][lo:hi] = hit.astype(np.uint8)
+                                adata.layers[f"{prefix}_{feat}_lengths"][lo:hi] = np.where(hit, len_h, 0).astype(np.int32)
+                        else:
+                            # layers carried over from an earlier annotation: OR the new runs in and
+                            # recompute run lengths on the union (HMM.py:1348-1370)
+                            lay = np.asarray(adata.layers[all_layer])
+                            lay[lo:hi][any_hit] = 1
+                            adata.layers[all_layer] = lay
+                            adata.layers[f"{all_layer}_lengths"][lo:hi] = _run_lengths_np(lay[lo:hi])
+                            for ci, feat in enumerate(feats):
+                                lay = np.asarray(adata.layers[f"{prefix}_{feat}"])
+                                lay[lo:hi][cls_h == (ci + 1)] = 1
+                                adata.layers[f"{prefix}_{feat}"] = lay
+                                adata.layers[f"{prefix}_{feat}_lengths"][lo:hi] = _run_lengths_np(lay[lo:hi])
+                    else:
+                        membership = (
+                            (states_h == target_idx) if use_viterbi
+                            else (gamma_d[:, :, target_idx].contiguous().cpu().numpy().astype(np.float64)
+                                  >= float(prob_threshold))
+                        )
+                        self._fill_features_host(adata, prefix, gr["name"], feats, ranges, membership, coords,
+                                                 full_coords, bool(span_fill and full_int), masked_idx,
+                                                 masked_coords_good, lo)
+                if fast_final:
+                    # ONE kernel writes every final layer of the chunk (final dtype, NaN outside the read span)
+                    # into the device staging slot; the copy engine moves each layer block to its host array
+                    n_chunk = hi - lo
+                    if "covered" in span_in:
+                        cov_d = torch.from_numpy(np.ascontiguousarray(span_in["covered"][lo:hi])).to(device)
+                        valid_u8 = engine.span_mask(n_chunk, n_vars, device, covered=cov_d)
+                    else:
+                        valid_u8 = engine.span_mask(n_chunk, n_vars, device, coords=span_in["coords"],
+                                                    start=span_in["start"][lo:hi].contiguous(),
+                                                    end=span_in["end"][lo:hi].contiguous())
+                    if ev_out[b] is not None:
+                        cur.wait_event(ev_out[b])
+                    outs = []
+                    i64 = i32 = 0
+                    for (nm, kind, gi, ci, is32) in layer_plan:
+                        if is32:
+                            outs.append(stage32[b][i32, :n_chunk])
+                            i32 += 1
+                        else:
+                            outs.append(stage64[b][i64, :n_chunk])
+                            i64 += 1
+                    engine.expand_layers(
+                        n_chunk, n_vars, L, states=states_d,
+                        post=gamma_d[:, :, t_post] if post_name is not None else None, post_stride=K,
+                        site_of_col=site_of_col_d, valid=valid_u8, groups=packed,
+                        layers=[(kind, gi, ci, out) for (nm, kind, gi, ci, is32), out in zip(layer_plan, outs)])
+                    ev_cmp[b] = torch.cuda.Event()
+                    ev_cmp[b].record(cur)
+                    s_out.wait_event(ev_cmp[b])
+                    for (nm, *_rest), out in zip(layer_plan, outs):
+                        engine.copy_to_host_async(adata.layers[nm][lo:hi], out, s_out)
+                    ev_out[b] = torch.cuda.Event()
+                    ev_out[b].record(s_out)
+                    del packed, valid_u8
+                else:
+                    ev_cmp[b] = torch.cuda.Event()
+                    ev_cmp[b].record(cur)
+                del gamma_d, states_d
+        finally:
+            uploader.finish()
             if fast_final:
-                n_chunk = hi - lo
-                if "covered" in span_in:
-                    valid_u8 = engine.span_mask(n_chunk, n_vars, device, covered=span_in["covered"][lo:hi].contiguous())
-                else:
-                    valid_u8 = engine.span_mask(n_chunk, n_vars, device, coords=span_in["coords"],
-                                                start=span_in["start"][lo:hi].contiguous(),
-                                                end=span_in["end"][lo:hi].contiguous())
-                valid_b = valid_u8 != 0
-                del valid_u8
-
-                def put(name, values, is_post=False):
-                    """final dtype + NaN outside the read span on the device, one copy to the host layer"""
-                    if is_post:
-                        out = torch.where(valid_b, values.to(torch.float32), nan32)
-                    else:
-                        out = torch.where(valid_b, values.to(torch.float64), nan64)
-                    _device_to_host_layer(adata.layers[name][lo:hi], out)
-
-                full_s = torch.full((n_chunk, n_vars), -1, dtype=torch.int8, device=device)
-                full_s[:, masked_idx_d] = states_d.index_select(1, take_d)
-                put(states_name, full_s)
-                del full_s
-                if post_name is not None:
-                    full_p = torch.zeros((n_chunk, n_vars), dtype=torch.float32, device=device)
-                    full_p[:, masked_idx_d] = gamma_d[:, :, t_post].index_select(1, take_d)
-                    put(post_name, full_p, is_post=True)
-                    del full_p
-            else:
-                states_h = states_d.cpu().numpy()
-                adata.layers[states_name][lo:hi, masked_idx] = states_h[:, take]
-                if post_name is not None:
-                    post_h = gamma_d[:, :, t_post].contiguous().cpu().numpy()
-                    adata.layers[post_name][lo:hi, masked_idx] = post_h[:, take]
-            for gr in groups:
-                all_layer, feats, ranges, target_idx = gr["all_layer"], gr["feats"], gr["ranges"], gr["target"]
-                if kernel_ok:
-                    if use_viterbi:
-                        cls_d, len_d, _ = engine.call_features(
-                            states=states_d, post=None, target=target_idx, threshold=0.0, coords=coords_d,
-                            grid_left=left_d, grid_right=right_d, n_grid=n_vars, ranges=ranges)
-                    else:
-                        post_d = gamma_d[:, :, target_idx].contiguous()
-                        cls_d, len_d, _ = engine.call_features(
-                            states=None, post=post_d, target=target_idx, threshold=float(prob_threshold),
-                            coords=coords_d, grid_left=left_d, grid_right=right_d, n_grid=n_vars, ranges=ranges)
-                    if fast_final:
-                        any_hit_d = cls_d > 0
-                        zero_d = torch.zeros((), dtype=len_d.dtype, device=device)
-                        put(all_layer, any_hit_d)
-                        put(f"{all_layer}_lengths", torch.where(any_hit_d, len_d, zero_d))
-                        for ci, feat in enumerate(feats):
-                            hit_d = cls_d == (ci + 1)
-                            put(f"{prefix}_{feat}", hit_d)
-                            put(f"{prefix}_{feat}_lengths", torch.where(hit_d, len_d, zero_d))
-                        del cls_d, len_d
-                        continue
-                    cls_h = cls_d.cpu().numpy()
-                    len_h = len_d.cpu().numpy()
-                    any_hit = cls_h > 0
-                    if gr["clean"]:
-                        adata.layers[all_layer][lo:hi] = any_hit.astype(np.uint8)
-                        adata.layers[f"{all_layer}_lengths"][lo:hi] = np.where(any_hit, len_h, 0).astype(np.int32)
-                        for ci, feat in enumerate(feats):
-                            hit = cls_h == (ci + 1)
-                            adata.layers[f"{prefix}_{feat}"][lo:hi] = hit.astype(np.uint8)
-                            adata.layers[f"{prefix}_{feat}_lengths"][lo:hi] = np.where(hit, len_h, 0).astype(np.int32)
-                    else:
-                        # layers carried over from an earlier annotation: OR the new runs in and
-                        # recompute run lengths on the union (HMM.py:1348-1370)
-                        lay = np.asarray(adata.layers[all_layer])
-                        lay[lo:hi][any_hit] = 1
-                        adata.layers[all_layer] = lay
-                        adata.layers[f"{all_layer}_lengths"][lo:hi] = _run_lengths_np(lay[lo:hi])
-                        for ci, feat in enumerate(feats):
-                            lay = np.asarray(adata.layers[f"{prefix}_{feat}"])
-                            lay[lo:hi][cls_h == (ci + 1)] = 1
-                            adata.layers[f"{prefix}_{feat}"] = lay
-                            adata.layers[f"{prefix}_{feat}_lengths"][lo:hi] = _run_lengths_np(lay[lo:hi])
-                else:
-                    membership = (
-                        (states_h == target_idx) if use_viterbi
-                        else (gamma_d[:, :, target_idx].contiguous().cpu().numpy().astype(np.float64)
-                              >= float(prob_threshold))
-                    )
-                    self._fill_features_host(adata, prefix, gr["name"], feats, ranges, membership, coords,
-                                             full_coords, bool(span_fill and full_int), masked_idx,
-                                             masked_coords_good, lo)
-            del gamma_d, states_d
+                s_out.synchronize()
+            cur.synchronize()
 
         if not feature_sets:
             # no feature sets: only states / posterior are written and, like the reference, no
@@ -1288,10 +1284,12 @@ class BaseHMM(nn.Module):
                         continue
                     adata.layers[f"{prefix}_{chosen}"][i, cols] = 1
                     adata.layers[all_layer][i, cols] = 1
-        adata.layers[f"{all_layer}_lengths"] = _run_lengths_np(np.asarray(adata.layers[all_layer]))
+        # run lengths of the rows this chunk touched only (reads are independent)
+        r0, r1 = row0, row0 + membership.shape[0]
+        adata.layers[f"{all_layer}_lengths"][r0:r1] = _run_lengths_np(np.asarray(adata.layers[all_layer])[r0:r1])
         for feat in feats:
             nm = f"{prefix}_{feat}"
-            adata.layers[f"{nm}_lengths"] = _run_lengths_np(np.asarray(adata.layers[nm]))
+            adata.layers[f"{nm}_lengths"][r0:r1] = _run_lengths_np(np.asarray(adata.layers[nm])[r0:r1])
 
     def _ensure_final_layer_and_assign(self, final_adata, layer_name: str, subset_idx_mask: np.ndarray, sub_data):
         """Row-copy helper used by the legacy workflow (HMM.py:1385-1403)."""

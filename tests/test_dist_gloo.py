@@ -26,7 +26,7 @@ def _oracle_estep_patch(model, X_local, coords):
     model._estep_local = _estep_local
     model._ensure_device_dtype = lambda device=None: torch.device("cpu")
     model._bins_for = lambda coords, L, device: None
-    model._resident_chunks = lambda src, device: [src]
+    model._resident_chunks = lambda src, device, numeric_u8=False: [src]
     import smftools_b200.hmm as H
 
     H.engine.estep_workspace = lambda tables, device, n_reads=1, n_pos=1: torch.zeros(1, dtype=torch.float64)
