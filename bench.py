@@ -29,10 +29,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ALGO_BYTES = {  # algorithmic bytes per read-position: obs f32 in + gamma f32*K + state i8
-    "posterior": lambda K, C: 4 * C + 4 * K + 1,
-    "viterbi": lambda K, C: 4 * C + 1,
-    "estep": lambda K, C: 4 * C,
+ALGO_BYTES = {  # algorithmic bytes per read-position: obs (es bytes) in + gamma f32*K + state i8
+    "posterior": lambda K, C, es=4: es * C + 4 * K + 1,
+    "viterbi": lambda K, C, es=4: es * C + 1,
+    "estep": lambda K, C, es=4: es * C,
 }
 
 WORKLOADS = {
@@ -128,10 +128,11 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def device_reads(N, L, K, prob, seed, device):
+def device_reads(N, L, K, prob, seed, device, coded_u8=False):
     """Synthetic SMF-like reads generated ON the device (fp32, NaN = missing): K-state block
     structure with the survey's per-state emission means, Bernoulli calls or k/255-quantised
-    probabilities, 30 % iid NaN plus read-span truncation."""
+    probabilities, 30 % iid NaN plus read-span truncation.  ``coded_u8``: binary calls as the kernels'
+    compact uint8 code (0 / 1 / 255 = missing) instead of fp32."""
     import torch
 
     gen = torch.Generator(device=device)
@@ -139,7 +140,7 @@ def device_reads(N, L, K, prob, seed, device):
     em = torch.tensor([0.85, 0.08, 0.35, 0.60][:K], device=device)
     blk = 40
     nb = (L + blk - 1) // blk
-    out = torch.empty((N, L), dtype=torch.float32, device=device)
+    out = torch.empty((N, L), dtype=torch.uint8 if coded_u8 else torch.float32, device=device)
     step = max(1, min(N, (1 << 28) // max(L, 1)))
     for lo in range(0, N, step):
         hi = min(N, lo + step)
@@ -163,7 +164,7 @@ def device_reads(N, L, K, prob, seed, device):
         hi_t = L - torch.randint(0, max(1, L // 10), (n, 1), device=device, generator=gen)
         pos = torch.arange(L, device=device)[None, :]
         x[(pos < lo_t) | (pos >= hi_t)] = float("nan")
-        out[lo:hi] = x
+        out[lo:hi] = torch.where(torch.isnan(x), torch.full_like(x, 255.0), x).to(torch.uint8) if coded_u8 else x
         del st, keep, p, u, x
     return out
 
@@ -280,6 +281,361 @@ def run_reference(args, wl):
 # --------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------
+PARITY_TOL = {"gamma_abs": 1e-5, "viterbi_margin": 1e-6, "stats_rel": 2e-6}
+
+
+def _dist_ctx():
+    import torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    return world, rank, local, torch.device("cuda", local)
+
+
+def _max_over_ranks(ms, device, world):
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _barrier(world):
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+
+
+def _feature_setup(L, device):
+    """Sites every ~4 bp on a grid of 4*L columns; default footprint size classes."""
+    import torch
+
+    coords_h = np.sort(np.random.default_rng(5).choice(np.arange(4 * L), size=L, replace=False)).astype(np.int64)
+    full_h = np.arange(4 * L, dtype=np.int64)
+    return dict(
+        coords_h=coords_h, full_h=full_h,
+        coords=torch.from_numpy(coords_h).to(device),
+        left=torch.from_numpy(np.searchsorted(full_h, coords_h, side="left").astype(np.int32)).to(device),
+        right=torch.from_numpy(np.searchsorted(full_h, coords_h, side="right").astype(np.int32)).to(device),
+        V=4 * L, ranges=[(6, 40), (40, 100), (100, 200), (200, float("inf"))], target=1)
+
+
+def parity_record(op, K, obs_prefix, tables, feat=None):
+    """Outside every timed region: the kernels' results on a read prefix against the CPU oracle
+    (test infrastructure; the only place bench.py's GPU arm touches oracle/)."""
+    import torch
+
+    from oracle import hmm_oracle as O
+    from smftools_b200 import engine
+
+    t0 = time.perf_counter()
+    p = O.synth_params(K)
+    n, L = int(obs_prefix.shape[0]), int(obs_prefix.shape[1])
+    if obs_prefix.dtype == torch.uint8:
+        xh = obs_prefix.cpu().numpy().astype(np.float64)
+        xh[xh > 1] = np.nan
+    else:
+        xh = obs_prefix.cpu().numpy().astype(np.float64)
+    rec = {"reads": n, "positions": L, "against": "oracle/hmm_oracle.py (numpy fp64 port pinned to the reference)"}
+    if op == "posterior":
+        g, s, _ = engine.posterior(tables, obs_prefix, None)
+        g_ref, _ = O.posterior(xh, p)
+        err = float(np.abs(g.cpu().numpy() - g_ref).max())
+        top2 = np.sort(g_ref, axis=2)
+        close = (top2[:, :, -1] - top2[:, :, -2]) < 2e-5
+        bad = int(((s.cpu().numpy() != g_ref.argmax(axis=2)) & ~close).sum())
+        rec.update({"max_abs_dgamma": err, "tol": PARITY_TOL["gamma_abs"], "state_mismatches_outside_ties": bad,
+                    "ok": bool(err <= PARITY_TOL["gamma_abs"] and bad == 0)})
+    elif op == "viterbi":
+        sv = engine.viterbi(tables, obs_prefix, None).cpu().numpy().astype(np.int64)
+        ref, margin = O.viterbi(xh, p, return_margins=True)
+        same = (sv == ref).all(axis=1)
+        viol = int((~same & ~(margin < PARITY_TOL["viterbi_margin"])).sum())
+        rec.update({"reads_identical": int(same.sum()), "reads_differing_within_1e-6_margin": int((~same).sum()) - viol,
+                    "violations": viol, "ok": viol == 0})
+        if feat is not None:
+            ivals = engine.call_features(states=torch.from_numpy(sv.astype(np.int8)).to(obs_prefix.device), post=None,
+                                         target=feat["target"], threshold=0.0, coords=feat["coords"],
+                                         grid_left=feat["left"], grid_right=feat["right"], n_grid=feat["V"],
+                                         ranges=feat["ranges"], want_dense=False, max_intervals=n * (L // 2 + 1))[2]
+            got = sorted(map(tuple, ivals.cpu().numpy().tolist()))
+            want = []
+            for i in range(n):
+                for (a, b) in O.runs_from_bool(sv[i] == feat["target"]):
+                    glen = int(feat["coords_h"][b - 1]) - int(feat["coords_h"][a]) + 1
+                    c = O.pick_class(feat["ranges"], glen)
+                    if c >= 0:
+                        want.append((i, int(np.searchsorted(feat["full_h"], feat["coords_h"][a], side="left")),
+                                     int(np.searchsorted(feat["full_h"], feat["coords_h"][b - 1], side="right")), c))
+            rec["intervals"] = len(got)
+            rec["intervals_identical"] = bool(got == sorted(want))
+            rec["ok"] = bool(rec["ok"] and rec["intervals_identical"])
+    else:
+        st = engine.estep(tables, obs_prefix, None).cpu().numpy()
+        ref = O.stats_vector(O.estep(xh, p))
+        rel = float((np.abs(st - ref) / np.maximum(np.abs(ref), 1.0)).max())
+        rec.update({"max_rel_dstats": rel, "tol": PARITY_TOL["stats_rel"], "ok": bool(rel <= PARITY_TOL["stats_rel"])})
+    rec["seconds"] = round(time.perf_counter() - t0, 2)
+    return rec
+
+
+def roofline_of(op, K, es, positions, kernel_ms, workload=None):
+    peak, peak_src = measured_peak()
+    algo = ALGO_BYTES[op](K, 1, es)
+    achieved = algo * positions / (kernel_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": ncu_traffic(workload) if workload else None, "peak_source": peak_src,
+            "algorithmic_bytes_per_read_position": algo, "kernel_ms": kernel_ms}
+
+
+def stream_workload(name, ctx, steps_cap=None):
+    """A BASELINE shape at its FULL size, streamed through the device in resident chunks dealt to the
+    ranks; generation is outside the timed region (CUDA events around each chunk's kernels)."""
+    import torch
+
+    from smftools_b200 import engine
+
+    world, rank, local, device = ctx
+    spec = FULL_WORKLOADS[name]
+    K, L, op, prob, es = spec["K"], spec["L"], spec["op"], spec["prob"], spec.get("es", 4)
+    chunk, n_chunks = spec["chunk"], spec["chunks"]
+    model = make_model(K, device)
+    tables = model._host_tables()
+    mine = [c for c in range(n_chunks) if c % world == rank]
+    gamma = torch.empty((chunk, L, K), dtype=torch.float32, device=device) if op == "posterior" else None
+    states = torch.empty((chunk, L), dtype=torch.int8, device=device) if op in ("posterior", "viterbi") else None
+    ws = stats = feat = None
+    if op == "viterbi":
+        ws = torch.empty((chunk * L,), dtype=torch.uint8, device=device)
+        feat = _feature_setup(L, device)
+    if op == "estep":
+        ws = engine.estep_workspace(tables, device, chunk, L)
+        stats = torch.empty((engine.stats_len(tables),), dtype=torch.float64, device=device)
+    launches = 0
+    n_intervals = 0
+
+    def run(obs):
+        nonlocal launches, n_intervals
+        if op == "posterior":
+            engine.posterior(tables, obs, None, out_gamma=gamma, out_states=states)
+            launches += 1
+        elif op == "viterbi":
+            engine.viterbi(tables, obs, None, out_states=states, workspace=ws)
+            iv = engine.call_features(states=states, post=None, target=feat["target"], threshold=0.0,
+                                      coords=feat["coords"], grid_left=feat["left"], grid_right=feat["right"],
+                                      n_grid=feat["V"], ranges=feat["ranges"], want_dense=False,
+                                      max_intervals=int(chunk) * 64)[2]
+            n_intervals += int(iv.shape[0])
+            launches += 2
+        else:
+            engine.estep(tables, obs, None, out_stats=stats, workspace=ws)
+            launches += 3
+
+    total_ms = 0.0
+    first = None
+    for ci, c in enumerate(mine):
+        obs = device_reads(chunk, L, K, prob, 7000 + 100 * c + spec.get("seed", 0), device, coded_u8=(es == 1))
+        if first is None:
+            first = obs[:spec.get("parity_reads", 128)].clone()
+            for _ in range(3):  # warm-up on the first chunk
+                run(obs)
+            launches = 0
+            n_intervals = 0
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        run(obs)
+        b.record()
+        torch.cuda.synchronize()
+        total_ms += a.elapsed_time(b)
+        del obs
+    ms = _max_over_ranks(total_ms, device, world)
+    positions = float(chunk) * L * n_chunks
+    rec = None
+    if rank == 0:
+        per_rank_positions = float(chunk) * L * len(mine)
+        rec = {"name": name, "workload": spec["desc"], "op": op, "K": K, "positions": L, "reads_total": chunk * n_chunks,
+               "chunks": n_chunks, "reads_per_chunk": chunk, "obs": "u8 coded" if es == 1 else "f32 NaN-coded",
+               "value": positions / (ms * 1e-3), "unit": "read-positions/s", "ms_total": ms,
+               "gpu_launches_rank0": launches,
+               "roofline": roofline_of(op, K, es, per_rank_positions, total_ms)}
+        if op == "viterbi":
+            rec["intervals_rank0"] = n_intervals
+        rec["parity"] = parity_record(op, K, first, tables, feat)
+    del gamma, states, ws
+    torch.cuda.empty_cache()
+    return rec
+
+
+FULL_WORKLOADS = {
+    "c3p": dict(K=2, L=10_000, op="posterior", prob=False, chunk=65_536, chunks=16,
+                desc="headline target: posterior decode of 1M (16 x 65,536) reads x 10 kb, K=2 binary, f32 obs"),
+    "c3p_k3": dict(K=3, L=10_000, op="posterior", prob=True, chunk=65_536, chunks=16,
+                   desc="posterior decode of 1M (16 x 65,536) reads x 10 kb, K=3 m6A probabilistic, f32 obs"),
+    "c3v": dict(K=3, L=10_000, op="viterbi", prob=True, chunk=262_144, chunks=4, parity_reads=96,
+                desc="BASELINE configs[2]: 1M (4 x 262,144) reads x 10 kb m6A probabilistic, 3-state Viterbi + "
+                     "footprint interval calling"),
+    "c4": dict(K=4, L=8_000, op="estep", prob=False, chunk=262_144, chunks=2, parity_reads=96,
+               desc="BASELINE configs[3] kernel: 4-state Baum-Welch E-step, 2 x 262,144 reads x 8 kb, f32 obs"),
+    "c4_u8": dict(K=4, L=8_000, op="estep", prob=False, chunk=262_144, chunks=2, es=1, parity_reads=96,
+                  desc="BASELINE configs[3] kernel: 4-state Baum-Welch E-step, 2 x 262,144 reads x 8 kb, u8 coded obs"),
+}
+
+
+def fit_strong_scaling(args, ctx):
+    """BASELINE configs[3] as north_star states it: 4-state HMM, 8 kb reads, 20 Baum-Welch iterations over
+    ``--bw-reads`` (4 M) reads IN TOTAL, sharded N ways (strong scaling), through ``model.fit`` with the
+    NCCL all-reduce of the 29-double statistics vector, the host M-step and the convergence test."""
+    import torch
+
+    import smftools_b200 as S
+    from smftools_b200.dist import enable_distributed_fit, shard_bounds
+
+    world, rank, local, device = ctx
+    K, L, total = 4, 8_000, int(args.bw_reads)
+    lo, hi = shard_bounds(total, rank, world)
+    n_local = hi - lo
+    obs = device_reads(n_local, L, K, False, 4000 + rank, device, coded_u8=True)
+    torch.cuda.synchronize()
+
+    def fresh_model():
+        m = S.create_hmm({"hmm_n_states": K, "hmm_init_emission_probs": [0.85, 0.08, 0.35, 0.60]}, arch="single")
+        if world > 1:
+            enable_distributed_fit(m)
+        return m
+
+    m = fresh_model()
+    m.fit(S.CodedU8(obs), max_iter=2, tol=0.0)  # warm-up (allocations, NCCL channels)
+    m = fresh_model()
+    m.fit_profile = []
+    iters = int(args.bw_iters)
+    _barrier(world)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    a.record()
+    hist = m.fit(S.CodedU8(obs), max_iter=iters, tol=0.0)
+    b.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms = _max_over_ranks(a.elapsed_time(b), device, world)
+    wall = _max_over_ranks(wall * 1e3, device, world)
+    rec = None
+    if rank == 0:
+        prof = m.fit_profile
+        mean = lambda k: float(statistics.mean(p[k] for p in prof)) if prof else None  # noqa: E731
+        rec = {
+            "config": f"BASELINE configs[3]: K=4, {total} reads x {L} positions in total, sharded over {world} GPU(s) "
+                      f"({n_local} on rank 0), u8 coded obs, {iters} iterations through model.fit (tol=0)",
+            "scaling": "strong", "value": float(total) * L * len(hist) / (ms * 1e-3),
+            "unit": "read-positions/s (all iterations)", "iterations": len(hist), "ms_total": ms, "wall_ms_total": wall,
+            "ms_per_iter": ms / max(len(hist), 1),
+            "split_ms_per_iter": {"estep_kernels": mean("estep_ms"), "allreduce": mean("allreduce_ms"),
+                                  "host_mstep_tables": mean("host_mstep_ms")},
+            "collective": (f"nccl all_reduce(sum) of {K + K * K + 2 * K + 1} fp64 per iteration" if world > 1 else "none"),
+            "loglik_first_last": [hist[0], hist[-1]], "loglik_monotone": bool(all(b2 >= a2 - 1e-6 * abs(a2) for a2, b2 in zip(hist, hist[1:]))),
+            "reads_total": total, "reads_rank0": n_local,
+        }
+    del obs
+    torch.cuda.empty_cache()
+    return rec
+
+
+def host_link_probe(ctx, seconds=2.0, nbytes=1 << 30):
+    """Pinned H2D, D2H and concurrent both-way copies on every rank at once: the host-link ceiling the
+    end-to-end numbers are bounded by (GB/s summed over ranks)."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank, local, device = ctx
+    h_a = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    h_b = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d_a = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    d_b = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    s1, s2 = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    out = {}
+    for kind in ("h2d", "d2h", "both"):
+        _barrier(world)
+        reps = 0
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < seconds:
+            if kind in ("h2d", "both"):
+                with torch.cuda.stream(s1):
+                    d_a.copy_(h_a, non_blocking=True)
+            if kind in ("d2h", "both"):
+                with torch.cuda.stream(s2):
+                    h_b.copy_(d_b, non_blocking=True)
+            s1.synchronize()
+            s2.synchronize()
+            reps += 1
+        rate = nbytes * reps / (time.perf_counter() - t0) / 1e9
+        t = torch.tensor([rate], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t)
+        out[f"{kind}_gbs" if kind != "both" else "bidir_gbs_per_direction"] = float(t.item())
+    out["note"] = f"pinned {nbytes >> 20} MiB copies for {seconds:.0f} s per pattern, all {world} rank(s) at once, summed"
+    return out
+
+
+def e2e_legs(args, ctx, model, obs, N, L, K):
+    """End to end through the public API with HOST buffers, copies inside the timed region.
+    ``e2e`` is the reference signature itself: ``decode(X float64 pageable numpy)`` returning fresh
+    ``(int64 states, float64 posteriors)`` host arrays (HMM.py:673-720).  ``e2e_compact`` is the opt-in
+    extension (float32 in, int8 + float32 out into caller-provided pinned buffers)."""
+    import torch
+
+    world, rank, local, device = ctx
+    steps = max(1, min(args.steps, 3))
+    n_e2e = min(N, 32_768)
+    X64 = obs[:n_e2e].cpu().numpy().astype(np.float64)  # ordinary pageable numpy, like the reference's callers hold
+    res = model.decode(X64, decode="marginal")  # warm-up: fills the page-locked result pool
+    del res
+    _barrier(world)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        st, g = model.decode(X64, decode="marginal")
+        del st, g
+    torch.cuda.synchronize()
+    dt = _max_over_ranks(time.perf_counter() - t0, device, world)
+    e2e = {
+        "value": world * n_e2e * L * steps / dt, "unit": "read-positions/s",
+        "h2d_bytes_per_step": int(n_e2e * L * 8), "d2h_bytes_per_step": int(n_e2e * L * (8 * K + 8)),
+        "steps": steps, "reads_per_step": n_e2e,
+        "api": "SingleBernoulliHMM.decode(X_host_f64_pageable, decode='marginal') -> fresh (int64 states, float64 gamma) "
+               "numpy arrays: the reference signature, nothing pre-allocated by the caller",
+        "d2h_gbs_per_gpu": n_e2e * L * (8 * K + 8) * steps / dt / 1e9,
+    }
+    del X64
+    host_in = torch.empty((n_e2e, L), dtype=torch.float32, pin_memory=True)
+    host_in.copy_(obs[:n_e2e])
+    out_states = torch.empty((n_e2e, L), dtype=torch.int8, pin_memory=True)
+    out_gamma = torch.empty((n_e2e, L, K), dtype=torch.float32, pin_memory=True)
+    X_host = host_in.numpy()
+    outs = (out_states.numpy(), out_gamma.numpy())
+    model.decode(X_host, decode="marginal", compact=True, out=outs)
+    _barrier(world)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        model.decode(X_host, decode="marginal", compact=True, out=outs)
+    torch.cuda.synchronize()
+    dt = _max_over_ranks(time.perf_counter() - t0, device, world)
+    compact = {
+        "value": world * n_e2e * L * steps / dt, "unit": "read-positions/s",
+        "h2d_bytes_per_step": int(n_e2e * L * 4), "d2h_bytes_per_step": int(n_e2e * L * (4 * K + 1)),
+        "steps": steps, "reads_per_step": n_e2e,
+        "api": "extension: decode(X_host_f32_pinned, compact=True, out=pinned (int8, float32) buffers)",
+    }
+    del host_in, out_states, out_gamma
+    return e2e, compact
+
+
 def run_groups(args, wl):
     """Config #5: many (model, N_g, L_g) groups, each its own call sequence (fit 5 iterations with the
     host M-step in the loop, then posterior decode); groups are dealt round-robin to the ranks."""
@@ -288,11 +644,7 @@ def run_groups(args, wl):
 
     import smftools_b200 as S
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
+    world, rank, local, device = _dist_ctx()
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     rng = np.random.default_rng(17)
@@ -312,9 +664,7 @@ def run_groups(args, wl):
 
     for _ in range(max(1, min(args.warmup, 2))):
         one_pass()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    _barrier(world)
     steps = max(1, min(args.steps, 3))
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
@@ -322,10 +672,7 @@ def run_groups(args, wl):
         one_pass()
     b.record()
     torch.cuda.synchronize()
-    t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item()) / steps
+    ms = _max_over_ranks(a.elapsed_time(b), device, world) / steps
     rp = float(sum(N * int(lengths[g]) * 6 for g in range(16)))  # 5 E-steps + 1 decode per position
     if rank == 0:
         emit({
@@ -349,18 +696,15 @@ def run_ours(args, wl):
     if wl["op"] == "groups":
         return run_groups(args, wl)
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    numa_node = None
+    ctx = _dist_ctx()
+    world, rank, local, device = ctx
+    numa = None
     if world > 1:
         # several ranks stream through host memory at once (e2e leg): keep each rank's host buffers and
-        # copy threads on the NUMA node of its GPU
+        # copy threads on the CPUs local to its GPU
         from smftools_b200.dist import bind_to_gpu_numa_node
 
-        numa_node = bind_to_gpu_numa_node(local)
+        numa = bind_to_gpu_numa_node(local)
         dist.init_process_group("nccl", device_id=device)
     N, L, K, op = wl["N"], wl["L"], wl["K"], wl["op"]
     C = 1
@@ -377,19 +721,7 @@ def run_ours(args, wl):
     if op == "estep":
         ws = engine.estep_workspace(tables, device, N, L)
         stats = torch.empty((engine.stats_len(tables),), dtype=torch.float64, device=device)
-
-    feat = None
-    if op == "viterbi":
-        # BASELINE configs[2]: Viterbi + footprint interval calling on the decoded states.  Sites every
-        # ~4 bp on a grid of 4*L columns; default footprint size classes; compacted interval records.
-        coords_h = np.sort(np.random.default_rng(5).choice(np.arange(4 * L), size=L, replace=False)).astype(np.int64)
-        full_h = np.arange(4 * L, dtype=np.int64)
-        feat = dict(
-            coords=torch.from_numpy(coords_h).to(device),
-            left=torch.from_numpy(np.searchsorted(full_h, coords_h, side="left").astype(np.int32)).to(device),
-            right=torch.from_numpy(np.searchsorted(full_h, coords_h, side="right").astype(np.int32)).to(device),
-            V=4 * L, ranges=[(6, 40), (40, 100), (100, 200), (200, float("inf"))], target=1,
-            max_intervals=int(N) * 64)
+    feat = _feature_setup(L, device) if op == "viterbi" else None
 
     launches = {"n": 0}
     # E-step launches per call: two-kernel path (walk + sweeps + reduce) for K = 4 and long K = 3 batches
@@ -405,7 +737,7 @@ def run_ours(args, wl):
             engine.viterbi(tables, obs, None, out_states=states, workspace=ws)
             engine.call_features(states=states, post=None, target=feat["target"], threshold=0.0, coords=feat["coords"],
                                  grid_left=feat["left"], grid_right=feat["right"], n_grid=feat["V"],
-                                 ranges=feat["ranges"], want_dense=False, max_intervals=feat["max_intervals"])
+                                 ranges=feat["ranges"], want_dense=False, max_intervals=int(N) * 64)
             launches["n"] += 2
         else:
             engine.estep(tables, obs, None, out_stats=stats, workspace=ws)
@@ -413,14 +745,9 @@ def run_ours(args, wl):
             if world > 1:
                 dist.all_reduce(stats)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     for _ in range(max(3, args.warmup)):
         step()
-    barrier()
+    _barrier(world)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -429,92 +756,63 @@ def run_ours(args, wl):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
-    barrier()
+    _barrier(world)
     t_start.record(stream)
     for i in range(args.steps):
         ev[i][0].record(stream)
         step()
         ev[i][1].record(stream)
     t_end.record(stream)
-    barrier()
+    _barrier(world)
     total_ms = t_start.elapsed_time(t_end)
     kernel_ms = [a.elapsed_time(b) for a, b in ev]
     clocks = sampler.stop() if rank == 0 else None
     n_launch = launches["n"]
-
-    tmax = torch.tensor([total_ms], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    total_ms = float(tmax.item())
+    total_ms = _max_over_ranks(total_ms, device, world)
     ms_per_step = total_ms / args.steps
     value = world * N * L / (ms_per_step * 1e-3)
 
-    # ---- end-to-end through the public API with HOST buffers (pinned), copies inside the timed region ----
-    e2e = None
+    # ---- parity of this very process's kernels on a read prefix (outside the timed region) ----
+    parity = parity_record(op, K, obs[:256 if L <= 5000 else 128].clone(), tables, feat) if rank == 0 else None
+
+    # ---- end to end through the public API with HOST buffers ----
+    e2e = e2e_compact = None
     if op == "posterior" and not args.no_e2e:
-        e2e_steps = max(1, min(args.steps, 3))
-        n_e2e = min(N, 32_768)
-        host_in = torch.empty((n_e2e, L), dtype=torch.float32, pin_memory=True)
-        host_in.copy_(obs[:n_e2e])
-        out_states = torch.empty((n_e2e, L), dtype=torch.int8, pin_memory=True)
-        out_gamma = torch.empty((n_e2e, L, K), dtype=torch.float32, pin_memory=True)
-        X_host = host_in.numpy()
-        outs = (out_states.numpy(), out_gamma.numpy())
-        model.decode(X_host, decode="marginal", compact=True, out=outs)  # warm-up
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            model.decode(X_host, decode="marginal", compact=True, out=outs)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        t = torch.tensor([dt], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-        e2e = {
-            "value": world * n_e2e * L * e2e_steps / dt, "unit": "read-positions/s",
-            "h2d_bytes_per_step": int(n_e2e * L * 4), "d2h_bytes_per_step": int(n_e2e * L * (4 * K + 1)),
-            "steps": e2e_steps, "reads_per_step": n_e2e,
-            "api": "SingleBernoulliHMM.decode(X_host_f32, decode='marginal', compact=True, out=pinned buffers)",
-            "numa_node_rank0": numa_node,
-        }
-        del host_in, out_states, out_gamma
+        e2e, e2e_compact = e2e_legs(args, ctx, model, obs, N, L, K)
+    del gamma, states, ws
+    obs_keep = obs if (world == 1 and not args.no_cpu) else None
+    del obs
+    torch.cuda.empty_cache()
 
-    # ---- Baum-Welch iteration (E-step kernel + NCCL all-reduce of the statistics + host M-step) ----
-    bw = None
-    if op == "posterior" and not args.no_bw:
-        n_bw = N
-        wsb = engine.estep_workspace(tables, device, n_bw, L)
-        stats = torch.empty((engine.stats_len(tables),), dtype=torch.float64, device=device)
+    link = None
+    if not args.no_e2e:
+        link = host_link_probe(ctx)
+        if e2e is not None and rank == 0:
+            e2e["fraction_of_host_link_d2h"] = (e2e["d2h_gbs_per_gpu"] * world) / max(link["bidir_gbs_per_direction"], 1e-9)
+            e2e["limiter"] = ("device->host link: every read-position returns 8*K + 8 = %d bytes (int64 state + float64 "
+                              "posteriors) against %.1f GB/s of measured pinned D2H under two-way traffic" %
+                              (8 * K + 8, link["bidir_gbs_per_direction"]))
+            e2e["numa_binding_rank0"] = numa
 
-        def bw_iter():
-            engine.estep(tables, obs[:n_bw], None, out_stats=stats, workspace=wsb)
-            if world > 1:
-                dist.all_reduce(stats)
-            return stats.cpu()  # the M-step / convergence test needs the statistics on the host every iteration
+    # ---- Baum-Welch: BASELINE configs[3], strong scaling ----
+    bw = fit_strong_scaling(args, ctx) if not args.no_bw else None
 
-        for _ in range(3):
-            bw_iter()
-        barrier()
-        iters = max(3, min(args.steps, 10))
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        for _ in range(iters):
-            bw_iter()
-        b.record(stream)
-        barrier()
-        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item()) / iters
-        bw = {"value": world * n_bw * L / (ms * 1e-3), "unit": "read-positions/s per EM iteration", "ms_per_iter": ms,
-              "reads_per_gpu": n_bw, "K": K, "collective": "nccl all_reduce fp64 x %d" % stats.numel() if world > 1 else "none"}
+    # ---- the other BASELINE shapes at full size ----
+    extra = []
+    if args.workload == "c2" and not args.no_extra:
+        for name in ("c3p", "c3p_k3", "c3v", "c4", "c4_u8"):
+            rec = stream_workload(name, ctx)
+            if rec is not None:
+                extra.append(rec)
 
     if rank == 0:
-        peak, peak_src = measured_peak()
-        algo = ALGO_BYTES[op](K, C)
         k_ms = statistics.mean(kernel_ms)
-        achieved = algo * N * L / (k_ms * 1e-3) / 1e9
+        roof = roofline_of(op, K, 4, float(N) * L, k_ms, args.workload)
+        roof["kernel"] = {"posterior": "smf::fb2_kernel<K, CH, STATS=false, ...> (one launch per step)",
+                          "viterbi": "smf::viterbi_kernel (+ smf::call_intervals_kernel)",
+                          "estep": ("smf::walk_kernel + smf::estep_sweep_kernel (+ reduce_partials_kernel)"
+                                    if two_kernel else
+                                    "smf::fb2_kernel<K, CH, STATS=true, ...> (+ reduce_partials_kernel)")}[op]
         line = {
             "metric": "HMM read-positions/sec", "value": value, "unit": "read-positions/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -523,18 +821,16 @@ def run_ours(args, wl):
                        "l2": f"inputs {N * L * 4 / 1e9:.2f} GB + outputs per step, far larger than the 126 MB L2 (no flush needed)"},
             "clocks": clocks,
             "e2e": e2e,
+            "e2e_compact": e2e_compact,
+            "host_link": link,
             "gpu_launches": n_launch,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
-                         "algorithmic_bytes_per_read_position": algo, "kernel_ms": k_ms,
-                         "kernel": {"posterior": "smf::fb2_kernel<K, CH, STATS=false, ...> (one launch per step)",
-                                    "viterbi": "smf::viterbi_kernel (+ smf::call_intervals_kernel)",
-                                    "estep": ("smf::walk_kernel + smf::estep_sweep_kernel (+ reduce_partials_kernel)"
-                                              if two_kernel else
-                                              "smf::fb2_kernel<K, CH, STATS=true, ...> (+ reduce_partials_kernel)")}[op]},
+            "roofline": roof,
+            "parity": parity,
             "baum_welch": bw,
+            "workloads": extra,
         }
-        if world == 1 and not args.no_cpu:
+        if obs_keep is not None:
+            del obs_keep
             line["cpu_baseline"] = cpu_baseline(wl)
         else:
             line["cpu_baseline"] = None
@@ -575,7 +871,10 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-bw", action="store_true", help="skip the Baum-Welch leg")
-    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end legs and the host-link probe")
+    ap.add_argument("--no-extra", action="store_true", help="skip the full-size runs of the other BASELINE shapes")
+    ap.add_argument("--bw-reads", type=int, default=4_000_000, help="total reads of the configs[3] fit (sharded over the GPUs)")
+    ap.add_argument("--bw-iters", type=int, default=20, help="Baum-Welch iterations of the configs[3] fit")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

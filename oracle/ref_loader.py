@@ -45,6 +45,45 @@ def load_reference_hmm():
     return mod
 
 
+class _PermissiveStub(types.ModuleType):
+    """Stand-in for a module the reference imports at load time but this image lacks (anndata-backed
+    ``smftools.readwrite``, matplotlib): attribute lookups succeed, calling anything raises."""
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+
+        def _stub(*args, **kwargs):
+            raise RuntimeError(f"stubbed {self.__name__}.{name} was called")
+
+        _stub.__name__ = name
+        return _stub
+
+
+def load_reference_cli():
+    """Return the reference's ``(smftools.cli.hmm_adata, smftools.tools.partitioned_hmm)`` modules,
+    unmodified, with the absent I/O / plotting dependencies stubbed.  The functions on and
+    next to the hot path (``HMMTrainer``, ``build_single_channel``, ``build_multi_channel_union``,
+    ``_mask_uncovered_model_input``, ``_apply_merges``, the layer reductions) only need numpy / pandas."""
+    load_reference_hmm()
+    root = os.path.join(REFERENCE_SRC, "smftools")
+    if "smftools.readwrite" not in sys.modules:
+        sys.modules["smftools.readwrite"] = _PermissiveStub("smftools.readwrite")
+    for nm in ("matplotlib", "matplotlib.colors", "matplotlib.pyplot"):
+        try:
+            importlib.import_module(nm)
+        except Exception:
+            sys.modules[nm] = _PermissiveStub(nm)
+    for sub in ("cli", "tools", "informatics", "plotting", "analysis", "preprocessing"):
+        name = f"smftools.{sub}"
+        if name not in sys.modules:
+            pkg = types.ModuleType(name)
+            pkg.__path__ = [os.path.join(root, sub)]
+            sys.modules[name] = pkg
+    return (importlib.import_module("smftools.cli.hmm_adata"),
+            importlib.import_module("smftools.tools.partitioned_hmm"))
+
+
 class DuckAnnData:
     """Minimal stand-in for AnnData (the reference only touches these attributes)."""
 

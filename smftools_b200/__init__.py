@@ -5,6 +5,7 @@ Public surface mirrors ``smftools.hmm.HMM`` of the reference (see ``smftools_b20
 from .hmm import (  # noqa: F401
     HMM,
     BaseHMM,
+    CodedU8,
     DistanceBinnedSingleBernoulliHMM,
     MultiBernoulliHMM,
     SingleBernoulliHMM,

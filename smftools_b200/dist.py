@@ -42,41 +42,70 @@ def broadcast_parameters(model, src: int = 0, process_group=None):
     return model
 
 
-def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
-    """Pin this process to the CPUs of the NUMA node its GPU hangs off (Linux sysfs), so that pinned /
-    pageable host buffers allocated afterwards are first-touched on that node and host<->device copies
-    of several ranks do not all cross the same socket link.  Returns the node, or None when the
-    topology cannot be read (then nothing is changed)."""
-    try:
-        bdf = torch.cuda.get_device_properties(device_index).pci_bus_id  # e.g. "0000:1B:00.0"
-    except Exception:
-        try:
-            import ctypes
+def _parse_cpulist(text: str) -> set:
+    cpus = set()
+    for part in text.strip().split(","):
+        if "-" in part:
+            a, b = part.split("-")
+            cpus.update(range(int(a), int(b) + 1))
+        elif part:
+            cpus.add(int(part))
+    return cpus
 
-            buf = ctypes.create_string_buffer(32)
-            rt = ctypes.CDLL("libcudart.so")
-            if rt.cudaDeviceGetPCIBusId(buf, 32, int(device_index)) != 0:
-                return None
-            bdf = buf.value.decode()
-        except Exception:
-            return None
+
+def gpu_cpu_affinity(device_index: int) -> Optional[set]:
+    """CPUs the driver reports as local to the GPU (NVML ``nvmlDeviceGetCpuAffinity``, the same source as
+    ``nvidia-smi topo -m``); None when NVML is unavailable."""
     try:
-        with open(f"/sys/bus/pci/devices/{str(bdf).lower()}/numa_node") as fh:
-            node = int(fh.read().strip())
-        if node < 0:
-            return None
-        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
-            cpus = set()
-            for part in fh.read().strip().split(","):
-                if "-" in part:
-                    a, b = part.split("-")
-                    cpus.update(range(int(a), int(b) + 1))
-                elif part:
-                    cpus.add(int(part))
-        allowed = cpus & set(os.sched_getaffinity(0))
-        if not allowed:
-            return None
-        os.sched_setaffinity(0, allowed)
-        return node
-    except (OSError, ValueError, AttributeError):
+        import pynvml
+
+        pynvml.nvmlInit()
+        try:
+            uuid = torch.cuda.get_device_properties(device_index).uuid
+            try:
+                handle = pynvml.nvmlDeviceGetHandleByUUID(f"GPU-{uuid}".encode())
+            except Exception:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            ncpu = os.cpu_count() or 1
+            words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+            cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+            return cpus or None
+        finally:
+            pynvml.nvmlShutdown()
+    except Exception:
         return None
+
+
+def bind_to_gpu_numa_node(device_index: int) -> Optional[dict]:
+    """Pin this process to the CPUs local to its GPU, so that host buffers allocated afterwards are
+    first-touched on that NUMA node and the host<->device copies of several ranks do not all cross the
+    same socket link.  Sources, in order: the PCI device's ``numa_node`` in sysfs, then NVML's CPU affinity
+    of the GPU.  Returns ``{"source", "node", "cpus", "changed"}`` (``changed`` False when the affinity
+    already equals the allowed set, e.g. on a single-node VM), or None when no topology is exposed."""
+    allowed_now = set(os.sched_getaffinity(0))
+    info = None
+    try:
+        bdf = str(torch.cuda.get_device_properties(device_index).pci_bus_id).lower()
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as fh:
+            node = int(fh.read().strip())
+        if node >= 0:
+            with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+                info = {"source": "sysfs", "node": node, "cpus": _parse_cpulist(fh.read())}
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        info = None
+    if info is None:
+        cpus = gpu_cpu_affinity(device_index)
+        if cpus:
+            info = {"source": "nvml", "node": None, "cpus": cpus}
+    if info is None:
+        return None
+    target = info["cpus"] & allowed_now
+    if not target:
+        return None
+    changed = target != allowed_now
+    if changed:
+        try:
+            os.sched_setaffinity(0, target)
+        except OSError:
+            return None
+    return {"source": info["source"], "node": info["node"], "cpus": len(target), "changed": changed}

@@ -16,6 +16,16 @@ from . import _lib
 _OBS_DTYPES = {torch.float32: _lib.OBS_F32, torch.float64: _lib.OBS_F64, torch.uint8: _lib.OBS_U8}
 
 
+class IntervalOverflow(ValueError):
+    """``call_features`` found more runs than ``max_intervals``; ``needed`` is the size to retry with."""
+
+    def __init__(self, needed: int, capacity: int):
+        super().__init__(f"smf_hmm_call_features found {needed} intervals but the record buffer holds {capacity}; "
+                         f"call again with max_intervals >= {needed}")
+        self.needed = int(needed)
+        self.capacity = int(capacity)
+
+
 def _require_cuda(t: torch.Tensor, name: str) -> None:
     if not t.is_cuda:
         raise RuntimeError(
@@ -190,6 +200,8 @@ def call_features(
     """Feature calling (``smf_hmm_call_features``).
 
     Returns (class_out uint8 [N,V], run_len int32 [N,V] | None, intervals int32 [n,4] | None).
+    Raises ``IntervalOverflow`` (a ``ValueError`` carrying the needed capacity) when more runs were found
+    than ``max_intervals`` records fit.
     """
     lib = _lib.load()
     src = states if states is not None else post
@@ -222,8 +234,12 @@ def call_features(
                                        _stream_ptr(dev))
     _lib.check(rc, "smf_hmm_call_features")
     if ivals is not None:
-        n = min(int(cnt.item()), max_intervals)
-        ivals = ivals[:n]
+        found = int(cnt.item())
+        if found > max_intervals:
+            # the kernel counted every run but could only store max_intervals of them: never hand back a
+            # silently truncated (and, being atomically appended, arbitrary) subset
+            raise IntervalOverflow(found, max_intervals)
+        ivals = ivals[:found]
     return cls, rlen, ivals
 
 

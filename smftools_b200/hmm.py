@@ -15,6 +15,7 @@ formed on the host, with the same torch ops (and therefore the same rounding) as
 from __future__ import annotations
 
 import os
+import time
 
 import ast
 import json
@@ -672,22 +673,39 @@ class BaseHMM(nn.Module):
         resident = self._resident_chunks(src, device, numeric_u8)
         hist: List[float] = []
         workspace = None
+        # optional per-iteration timing split (bench.py): set ``model.fit_profile = []`` before calling fit
+        prof = getattr(self, "fit_profile", None)
+        marks = []
         for it in range(1, int(max_iter) + 1):
             tables = self._host_tables()
             if workspace is None:
                 # sized for the largest resident chunk (includes the two-kernel path's boundary vectors)
                 workspace = engine.estep_workspace(tables, device, getattr(resident, "max_rows", None) or max(
                     (int(o.shape[0]) for o in resident), default=1), L)
+            if prof is not None:
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                ev[0].record()
             total = self._estep_local(tables, resident, bins, workspace, device)
+            if prof is not None:
+                ev[1].record()
             total = self._allreduce_stats(total)
+            if prof is not None:
+                ev[2].record()
             stats = total.cpu()
+            t_host = time.perf_counter()
             hist.append(float(stats[-1].item()))
             self._m_step(stats, update_start=update_start, update_trans=update_trans,
                          update_emission=update_emission)
+            if prof is not None:
+                marks.append((ev, time.perf_counter() - t_host))
             if verbose:
                 print(f"[{type(self).__name__}.fit] iter={it} ll_proxy={hist[-1]:.6f}")
             if len(hist) > 1 and abs(hist[-1] - hist[-2]) < float(tol) * max(abs(hist[-1]), 1.0):
                 break
+        if prof is not None:
+            for ev, host_s in marks:
+                prof.append({"estep_ms": ev[0].elapsed_time(ev[1]), "allreduce_ms": ev[1].elapsed_time(ev[2]),
+                             "host_mstep_ms": 1e3 * host_s})
         return hist
 
     def _estep_local(self, tables, resident, bins, workspace, device) -> torch.Tensor:

@@ -146,11 +146,33 @@ def test_u8_binary_input_equals_float_input():
     p = O.synth_params(K)
     m = model_from_params(p)
     st_f, g_f = m.decode(X32, decode="marginal", compact=True)
-    st_u, g_u = m.decode(code, decode="marginal", compact=True)
+    import smftools_b200 as S
+
+    st_u, g_u = m.decode(S.CodedU8(code), decode="marginal", compact=True)
     assert np.array_equal(g_f, g_u) and np.array_equal(st_f, st_u)
     sv_f, _ = m.decode(X32, decode="viterbi", compact=True)
-    sv_u, _ = m.decode(code, decode="viterbi", compact=True)
+    sv_u, _ = m.decode(S.CodedU8(code), decode="viterbi", compact=True)
     assert np.array_equal(sv_f, sv_u)
+    hist_f = m.fit(X32, max_iter=2, tol=0.0)
+    m2 = model_from_params(p)
+    hist_u = m2.fit(S.CodedU8(code), max_iter=2, tol=0.0)
+    assert np.allclose(hist_f, hist_u, rtol=1e-9)
+
+
+def test_plain_uint8_input_keeps_its_numeric_meaning():
+    """A plain uint8 matrix means what ``np.asarray(X, dtype=float)`` means in the reference (HMM.py:694):
+    the byte value is the observation.  Only ``CodedU8`` opts into the 0 / 1 / missing code."""
+    N, L, K = 64, 301, 2
+    X32 = np.nan_to_num(O.synth_reads(N, L, K, 6, prob=False, nan_rate=0.0), nan=0.0)
+    Xb = X32.astype(np.uint8)
+    Xb[:, ::7] = 2  # a value that is neither 0 nor 1: numeric 2.0, not "missing"
+    p = O.synth_params(K)
+    m = model_from_params(p)
+    st_u, g_u = m.decode(Xb, decode="marginal")
+    g_ref, _ = O.posterior(Xb.astype(np.float64), p)
+    assert np.abs(g_u - g_ref).max() <= GAMMA_TOL
+    st_f, g_f = m.decode(Xb.astype(np.float64), decode="marginal")
+    assert np.array_equal(g_u, g_f) and np.array_equal(st_u, st_f)
 
 
 def test_reference_property_tests_hold_for_the_cuda_models():
