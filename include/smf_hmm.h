@@ -91,6 +91,10 @@ const char* smf_hmm_strerror(int code);
  *   "short"  -1 (default) posterior decode and E-step of short reads (posterior: up to ~275 / 400 / 200
  *            positions for K = 2 / 3 / 4; E-step: ~450 / 450 / 300) run on the several-reads-per-warp
  *            kernel; 0 never / 1 whenever the read fits it (<= 1056 positions).
+ *   "seq"    -1 (default) the E-step of large batches (K = 2: >= 98,304 reads, K = 3, 4: >= 49,152; uint8-coded
+ *            rows of a multiple of 16 positions, or float rows of a multiple of 4) runs on the
+ *            one-thread-per-read kernels (checkpointed forward pass + one backward pass); 0 never /
+ *            1 whenever the batch is eligible.  smf_hmm_workspace_bytes() follows the setting.
  * Returns SMF_ERR_BAD_ARG for an unknown key or value.
  */
 int smf_hmm_set_option(const char* key, int value);

@@ -18,6 +18,7 @@
 #include "launch.h"
 #include "smf_hmm.h"
 #include "post_sweep_kernel.cuh"
+#include "seq_kernel.cuh"
 #include "short_kernel.cuh"
 #include "sweep_kernel.cuh"
 #include "walk_kernel.cuh"
@@ -465,6 +466,40 @@ static int launch_walk_path(bool stats, const smf_hmm_tables* t, int obs_dtype, 
                   : launch_fb2w_k4(plan.chunk, stats, obs_dtype, out, t, a, plan, di, nblocks, stream);
 }
 
+// ---------------------------------------------------------------------------------------
+// sequential E-step (seq_kernel.cuh): one thread per read, three recursions per position
+// ---------------------------------------------------------------------------------------
+// -1 = measured policy, 0 = never, 1 = whenever the batch is eligible.  SMF_SEQ / smf_hmm_set_option("seq", v).
+static std::atomic<int> g_seq_mode{[] { const char* e = getenv("SMF_SEQ"); return e ? atoi(e) : -1; }()};
+// Reads per launch from which the reads alone fill the machine (148 SMs x 4-5 CTAs x 128 threads); measured
+// break-even against the chunk-parallel kernels in profiles/r02_seq_estep.txt.
+static int64_t seq_min_reads(int K) {
+  static const int env = [] { const char* e = getenv("SMF_SEQ_MIN_READS"); return e ? atoi(e) : 0; }();
+  if (env > 0) return env;
+  return K == 2 ? 98304 : 49152;
+}
+// shape-only test (used for workspace sizing); the launch additionally needs an eligible dtype / alignment
+static bool seq_shape_eligible(const smf_hmm_tables* t, int64_t N, int64_t L) {
+  const int mode = g_seq_mode;
+  if (mode == 0 || g_force_generic) return false;
+  if (t->n_channels != 1 || t->n_bins != 1) return false;
+  if (L < 2 || L > (1 << 24) || (L & 3)) return false;
+  if (rescale_cadence(t) != 4) return false;
+  if (mode == 1) return true;
+  return N >= seq_min_reads(t->n_states);
+}
+static bool seq_launch_eligible(const smf_hmm_tables* t, int64_t N, int64_t L, int obs_dtype, const void* obs) {
+  if (!seq_shape_eligible(t, N, L)) return false;
+  if (reinterpret_cast<uintptr_t>(obs) & 15u) return false;
+  if (obs_dtype == SMF_OBS_U8) return (L & 15) == 0;  // rows are whole 16-byte groups
+  if (obs_dtype == SMF_OBS_F32) return (L & 3) == 0;
+  return false;
+}
+static size_t seq_ws_bytes(int K, int64_t N, int64_t L) {
+  const size_t tact = (size_t)((L + kSeqCH - 1) / kSeqCH);
+  return tact * (size_t)N * SeqVec<4>::KP * sizeof(float) + (size_t)N * sizeof(double) + 64;
+}
+
 static inline int obs_elem_size(int dt) { return dt == SMF_OBS_F32 ? 4 : (dt == SMF_OBS_F64 ? 8 : 1); }
 
 // ---------------------------------------------------------------------------------------
@@ -692,6 +727,11 @@ int smf_hmm_set_option(const char* key, int value) {
     g_short_mode = value;
     return SMF_OK;
   }
+  if (strcmp(key, "seq") == 0) {
+    if (value < -1 || value > 1) return SMF_ERR_BAD_ARG;
+    g_seq_mode = value;
+    return SMF_OK;
+  }
   return SMF_ERR_BAD_ARG;
 }
 
@@ -707,8 +747,13 @@ size_t smf_hmm_workspace_bytes(int op, const smf_hmm_tables* tab, int64_t n_read
     case SMF_OP_ESTEP: {
       if (check_tables(tab) != SMF_OK) return 0;
       size_t b = (size_t)kMaxEstepBlocks * (size_t)stats_len(tab) * sizeof(double);
-      if (walk_eligible(tab, n_reads, n_pos, true)) b += walk_ws_bytes(tab->n_states, n_reads, n_pos);
-      return b;
+      size_t extra = 0;
+      if (walk_eligible(tab, n_reads, n_pos, true)) extra = walk_ws_bytes(tab->n_states, n_reads, n_pos);
+      if (seq_shape_eligible(tab, n_reads, n_pos)) {
+        const size_t sq = seq_ws_bytes(tab->n_states, n_reads, n_pos);
+        if (sq > extra) extra = sq;
+      }
+      return b + extra;
     }
     case SMF_OP_POSTERIOR:
       if (check_tables(tab) != SMF_OK) return 0;
@@ -918,6 +963,28 @@ int smf_hmm_estep(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int
         reduce_partials_kernel<<<(S + 127) / 128, 128, 0, st>>>(sa.partials, nb2, S, stats);
         return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
       }
+    }
+    if (seq_launch_eligible(tab, n_reads, n_pos, obs_dtype, obs)) {
+      // large batch: one thread per read, checkpointed forward pass + one backward pass with statistics
+      char* wws = reinterpret_cast<char*>(workspace) + (size_t)kMaxEstepBlocks * (size_t)S * sizeof(double);
+      SeqArgs q;
+      memset(&q, 0, sizeof(q));
+      q.obs = obs;
+      q.N = n_reads;
+      q.L = (int)n_pos;
+      q.Tact = (int)((n_pos + kSeqCH - 1) / kSeqCH);
+      q.ll = reinterpret_cast<double*>(wws);
+      q.ckpt = reinterpret_cast<float*>(wws + (((size_t)n_reads * sizeof(double) + 63) & ~(size_t)63));
+      q.partials = reinterpret_cast<double*>(workspace);
+      q.S = S;
+      q.flush_chunks = 8;
+      int nb2 = kMaxEstepBlocks;
+      rc = (tab->n_states == 2)   ? launch_seq_estep_k2(obs_dtype, tab, q, di, &nb2, st)
+           : (tab->n_states == 3) ? launch_seq_estep_k3(obs_dtype, tab, q, di, &nb2, st)
+                                  : launch_seq_estep_k4(obs_dtype, tab, q, di, &nb2, st);
+      if (rc != SMF_OK) return rc;
+      reduce_partials_kernel<<<(S + 127) / 128, 128, 0, st>>>(q.partials, nb2, S, stats);
+      return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
     }
     Fb2Args b;
     memset(&b, 0, sizeof(b));

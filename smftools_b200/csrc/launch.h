@@ -132,9 +132,16 @@ int launch_fb2y_k2(int chunk, int obs_dtype, int out_mode, const smf_hmm_tables*
 int launch_fb2x_k3(int chunk, int obs_dtype, int out_mode, const smf_hmm_tables* t, Fb2Args& a, const Fb2Plan& plan,
                    const DeviceInfo& di, int* nblocks, cudaStream_t s);
 struct WalkArgs;
+struct SeqArgs;
 struct SweepArgs;
 struct ShortArgs;
 struct PostSweepArgs;
+int launch_seq_estep_k2(int obs_dtype, const smf_hmm_tables* t, const SeqArgs& a, const DeviceInfo& di, int* nblocks,
+                        cudaStream_t s);
+int launch_seq_estep_k3(int obs_dtype, const smf_hmm_tables* t, const SeqArgs& a, const DeviceInfo& di, int* nblocks,
+                        cudaStream_t s);
+int launch_seq_estep_k4(int obs_dtype, const smf_hmm_tables* t, const SeqArgs& a, const DeviceInfo& di, int* nblocks,
+                        cudaStream_t s);
 int launch_walk_k2(int obs_dtype, const smf_hmm_tables* t, const WalkArgs& a, cudaStream_t s);
 int launch_post_sweep_k2(int obs_dtype, const smf_hmm_tables* t, PostSweepArgs& a, const DeviceInfo& di, cudaStream_t s);
 int launch_post_sweep_k3(int obs_dtype, const smf_hmm_tables* t, PostSweepArgs& a, const DeviceInfo& di, cudaStream_t s);
