@@ -115,7 +115,9 @@ def test_trainer_call_sequence_ends_in_identical_annotation(arch, tmp_path):
     path = os.path.join(tmp_path, "PER_s_ref_GpC.pt")
     torch.save(payload, path)
     # HMMTrainer._load (:510-524)
-    payload = torch.load(path, map_location="cpu")
+    # (torch >= 2.6 defaults to weights_only=True, which rejects the numpy integers of the override list -- with
+    # the reference's own class too, see the CPU test above; load the way the reference's torch did)
+    payload = torch.load(path, map_location="cpu", weights_only=False)
     device = torch.device("cuda")
     m = S.create_hmm(cfg, arch=payload["hmm_arch"], override=payload.get("override", None), device=device)
     sd = payload["state_dict"]
