@@ -275,6 +275,53 @@ int smf_hmm_expand_layers(int64_t n_reads, int64_t n_grid, int64_t n_pos, const 
                           const uint8_t* valid, const smf_hmm_layer_group* groups_host, int n_groups,
                           const smf_hmm_layer_desc* layers_host, int n_layers, void* stream);
 
+/*
+ * Model-input builder (the step before the path).  Replaces build_single_channel /
+ * build_multi_channel_union (cli/hmm_adata.py:251-319: the site columns of the per-position matrix, on the
+ * union grid for several methylation channels, NaN where a channel has no site) and
+ * _mask_uncovered_model_input (tools/partitioned_hmm.py:170-188: missing where covered_base_mask is False),
+ * fused, producing the kernels' observation layout directly:
+ *   layer         device [N, V] of layer_dtype (SMF_OBS_F32 / F64 with NaN = missing, or SMF_OBS_U8 code)
+ *   cols          device int32 [L, C]: grid column of (position, channel), -1 = no site of that channel
+ *   covered       device uint8 [N, n_cov_grid] or NULL; covered_cols device int32 [L] = its column for position l
+ *   out           device [N, L, C]: uint8 code 0 / 1 / 255 (out_dtype SMF_OBS_U8) or float, NaN = missing
+ *   flag          device int (zeroed by the caller), may be NULL: set to 1 when the output type cannot carry a
+ *                 value exactly -- a call other than 0 / 1 / NaN for the uint8 code (the host mirror then
+ *                 asks for float output), or a float64 value that float32 does not represent
+ */
+int smf_hmm_build_obs(const void* layer, int layer_dtype, int64_t n_reads, int64_t n_grid,
+                      const int32_t* cols, int64_t n_pos, int n_channels, const uint8_t* covered,
+                      int64_t n_cov_grid, const int32_t* covered_cols, void* out, int out_dtype, int* flag,
+                      void* stream);
+
+/*
+ * ---- layer reductions from the packed results (what the reference's consumers re-derive from the dense layers)
+ *
+ * Membership of a cell: class_out > 0 (or == select_class + 1), resp. for packed merge-chain codes the 0x40 bit
+ * (or (code & 15) == select_class + 1); a cell counts only where `valid` != 0 (NULL = everywhere) and, for packed
+ * codes, where the 0x80 bit is set -- exactly the cells that are finite in the reference's float64 layers.
+ */
+
+/* Per-column sums over the reads: colsum[0][v] = cells of the aggregate layer that are > 0, colsum[c + 1][v] = of
+ * size class c, colvalid[v] = finite cells (outputs are zeroed by the call).  Their totals are the "modified" /
+ * "valid" counts of tools/partitioned_hmm.py:519-529; colsum / colvalid is np.nanmean(axis=0) of
+ * hmm/call_hmm_peaks.py:151.  n_classes <= 15. */
+int smf_hmm_layer_colsums(const uint8_t* cls_or_code, int packed, const uint8_t* valid, int64_t n_reads,
+                          int64_t n_grid, int n_classes, uint64_t* colsum /*[n_classes + 1, V]*/,
+                          uint64_t* colvalid /*[V]*/, void* stream);
+
+/* means[v] = colsum[v] / colvalid[v] (0 where no read covers v: nan_to_num) and metric = the 'same'-mode rolling
+ * mean np.convolve(means, ones(w) / w, "same") (hmm/call_hmm_peaks.py:151-158). */
+int smf_hmm_column_metric(const uint64_t* colsum, const uint64_t* colvalid, int64_t n_grid, int rolling_window,
+                          double* means, double* metric, void* stream);
+
+/* Runs-per-read and run-size histograms of one binary layer (tools/partitioned_hmm.py:572-585, 618-630):
+ * count_hist[k] = reads with k runs (k <= V / 2 + 1), size_hist[s] = runs of s grid columns (s <= V); zeroed by the
+ * call.  select_class = -1 for the aggregate / merged layer. */
+int smf_hmm_run_histograms(const uint8_t* cls_or_code, int packed, int select_class, const uint8_t* valid,
+                           int64_t n_reads, int64_t n_grid, uint64_t* count_hist /*[V / 2 + 2]*/,
+                           uint64_t* size_hist /*[V + 1]*/, void* stream);
+
 /* Page-lock / release caller-owned host memory (cudaHostRegister, portable) so that copies into it run
  * at link speed and asynchronously; plain async copy on `stream`. */
 #define SMF_COPY_H2D 0

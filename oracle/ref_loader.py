@@ -87,7 +87,7 @@ def load_reference_cli():
 class DuckAnnData:
     """Minimal stand-in for AnnData (the reference only touches these attributes)."""
 
-    def __init__(self, n_obs, var_names, obs=None, var=None):
+    def __init__(self, n_obs, var_names, obs=None, var=None, X=None):
         import pandas as pd
 
         self.var_names = pd.Index([str(v) for v in var_names])
@@ -99,3 +99,19 @@ class DuckAnnData:
         self.obs = obs if obs is not None else pd.DataFrame(index=[f"r{i}" for i in range(n_obs)])
         self.var = var if var is not None else pd.DataFrame(index=self.var_names)
         self.obs_names = self.obs.index
+        self.X = X
+
+    def __getitem__(self, key):
+        """``adata[:, column_mask]`` -- the only slicing the input builders use (cli/hmm_adata.py:184, 273)."""
+        import numpy as np
+
+        rows, cols = key
+        if not (isinstance(rows, slice) and rows == slice(None)):
+            raise NotImplementedError("DuckAnnData only slices columns")
+        cols = np.asarray(cols)
+        idx = np.flatnonzero(cols) if cols.dtype == bool else cols.astype(int)
+        sub = DuckAnnData(self.n_obs, self.var_names[idx], obs=self.obs, var=self.var.iloc[idx],
+                          X=None if self.X is None else np.asarray(self.X)[:, idx])
+        sub.layers = {k: np.asarray(v)[:, idx] for k, v in self.layers.items()}
+        sub.uns = self.uns
+        return sub

@@ -18,4 +18,12 @@ from .hmm import (  # noqa: F401
 
 from .merges import apply_merges, expand_merge_chain, expand_merge_chain_device, merge_chain_packed  # noqa: F401,E402
 
-__version__ = "0.1.0"
+from .inputs import (  # noqa: F401,E402
+    build_multi_channel_union,
+    build_single_channel,
+    mask_uncovered_model_input,
+    prepare_model_input,
+    resolve_pos_mask_for_methbase,
+)
+
+__version__ = "0.2.0"

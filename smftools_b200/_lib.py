@@ -41,6 +41,10 @@ EXPORTS = (
     "smf_hmm_span_mask",
     "smf_hmm_widen_decode",
     "smf_hmm_expand_layers",
+    "smf_hmm_build_obs",
+    "smf_hmm_layer_colsums",
+    "smf_hmm_column_metric",
+    "smf_hmm_run_histograms",
     "smf_hmm_host_register",
     "smf_hmm_host_unregister",
     "smf_hmm_host_is_pinned",
@@ -170,6 +174,15 @@ def load():
     lib.smf_hmm_expand_layers.restype = c_int
     lib.smf_hmm_expand_layers.argtypes = [c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                           POINTER(LayerGroup), c_int, POINTER(LayerDesc), c_int, c_void_p]
+    lib.smf_hmm_layer_colsums.restype = c_int
+    lib.smf_hmm_layer_colsums.argtypes = [c_void_p, c_int, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]
+    lib.smf_hmm_column_metric.restype = c_int
+    lib.smf_hmm_column_metric.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]
+    lib.smf_hmm_run_histograms.restype = c_int
+    lib.smf_hmm_run_histograms.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]
+    lib.smf_hmm_build_obs.restype = c_int
+    lib.smf_hmm_build_obs.argtypes = [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p, c_int64,
+                                      c_void_p, c_void_p, c_int, c_void_p, c_void_p]
     lib.smf_hmm_host_register.restype = c_int
     lib.smf_hmm_host_register.argtypes = [c_void_p, c_size_t]
     lib.smf_hmm_host_unregister.restype = c_int

@@ -124,6 +124,61 @@ __global__ void __launch_bounds__(256) widen_decode_kernel(const int8_t* __restr
   }
 }
 
+
+// ---- model-input builder (N2): gather the site columns of a per-position layer into the kernels' -----
+// observation layout, apply the coverage mask, and code binary calls as uint8 (0 / 1 / 255 = missing).
+struct BuildArgs {
+  const void* layer;   // [N, V]
+  int layer_dtype;     // SMF_OBS_F32 / F64 (NaN = missing) / U8 (0, 1, other = missing)
+  long long N;
+  int V, L, C;
+  const int32_t* cols;          // [L, C] grid column of (position, channel), -1 = the channel has no site there
+  const uint8_t* covered;       // [N, VC] or nullptr
+  int VC;                       // columns of the coverage matrix
+  const int32_t* covered_cols;  // [L] grid column whose coverage applies to position l
+  void* out;                    // [N, L, C] uint8 code or float
+  int out_dtype;                // SMF_OBS_U8 / SMF_OBS_F32
+  int* nonbinary;               // set to 1 when a value other than 0 / 1 / NaN was met (uint8 output only)
+};
+
+__global__ void __launch_bounds__(256) build_obs_kernel(const __grid_constant__ BuildArgs a) {
+  const long long per_read = (long long)a.L * a.C;
+  const long long total = a.N * per_read;
+  bool odd = false;
+  for (long long idx = blockIdx.x * 256LL + threadIdx.x; idx < total; idx += gridDim.x * 256LL) {
+    const long long n = idx / per_read;
+    const int lc = (int)(idx - n * per_read);
+    const int l = lc / a.C;
+    const int col = a.cols[lc];
+    float v = __int_as_float(0x7fc00000);
+    bool exact = true;  // value representable in the output without changing its meaning
+    if (col >= 0 && !(a.covered != nullptr && a.covered[n * a.VC + a.covered_cols[l]] == 0)) {
+      const long long src = n * a.V + col;
+      if (a.layer_dtype == SMF_OBS_F32) {
+        v = reinterpret_cast<const float*>(a.layer)[src];
+      } else if (a.layer_dtype == SMF_OBS_F64) {
+        const double d = reinterpret_cast<const double*>(a.layer)[src];
+        v = (float)d;
+        exact = (d != d) || ((double)v == d);
+      } else {
+        const unsigned b = reinterpret_cast<const unsigned char*>(a.layer)[src];
+        v = b == 0u ? 0.0f : (b == 1u ? 1.0f : __int_as_float(0x7fc00000));
+      }
+    }
+    if (a.out_dtype == SMF_OBS_U8) {
+      unsigned char code = 255;
+      if (v == 0.0f) code = 0;
+      else if (v == 1.0f) code = 1;
+      else if (v == v) odd = true;  // a probabilistic / non-binary call: the byte code cannot carry it
+      reinterpret_cast<unsigned char*>(a.out)[idx] = code;
+    } else {
+      if (!exact) odd = true;  // float64 input that float32 cannot represent
+      reinterpret_cast<float*>(a.out)[idx] = v;
+    }
+  }
+  if (odd && a.nonbinary != nullptr) *a.nonbinary = 1;
+}
+
 static int stream_grid() {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -245,6 +300,38 @@ int smf_hmm_expand_layers(int64_t n_reads, int64_t n_grid, int64_t n_pos, const 
   const int cap = stream_grid();
   if (blocks > cap) blocks = cap;
   expand_layers_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
+}
+
+int smf_hmm_build_obs(const void* layer, int layer_dtype, int64_t n_reads, int64_t n_grid, const int32_t* cols,
+                      int64_t n_pos, int n_channels, const uint8_t* covered, int64_t n_cov_grid,
+                      const int32_t* covered_cols, void* out, int out_dtype, int* flag, void* stream) {
+  if (n_reads < 0 || n_grid < 0 || n_pos < 0 || n_channels < 1 || n_channels > SMF_MAX_CHANNELS) return SMF_ERR_BAD_ARG;
+  if (n_reads == 0 || n_pos == 0) return SMF_OK;
+  if (!layer || !cols || !out) return SMF_ERR_BAD_ARG;
+  if (layer_dtype < SMF_OBS_F32 || layer_dtype > SMF_OBS_U8) return SMF_ERR_BAD_ARG;
+  if (out_dtype != SMF_OBS_U8 && out_dtype != SMF_OBS_F32) return SMF_ERR_BAD_ARG;
+  if (covered != nullptr && covered_cols == nullptr) return SMF_ERR_BAD_ARG;
+  if (n_grid > 0x3fffffff || n_cov_grid > 0x3fffffff || n_pos * n_channels > 0x3fffffff) return SMF_ERR_TOO_LONG;
+  BuildArgs a;
+  a.layer = layer;
+  a.layer_dtype = layer_dtype;
+  a.N = n_reads;
+  a.V = (int)n_grid;
+  a.L = (int)n_pos;
+  a.C = n_channels;
+  a.cols = cols;
+  a.covered = covered;
+  a.VC = (int)n_cov_grid;
+  a.covered_cols = covered_cols;
+  a.out = out;
+  a.out_dtype = out_dtype;
+  a.nonbinary = flag;
+  const long long total = n_reads * n_pos * n_channels;
+  long long blocks = (total + 255) / 256;
+  const int cap = stream_grid();
+  if (blocks > cap) blocks = cap;
+  build_obs_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
 }
 

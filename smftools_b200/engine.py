@@ -423,3 +423,50 @@ def copy_to_device_async(dst: torch.Tensor, src: np.ndarray, stream: torch.cuda.
         rc = _lib.load().smf_hmm_copy_async(_ptr(dst), ctypes.c_void_p(src.ctypes.data), nbytes, _lib.COPY_H2D,
                                             int(stream.cuda_stream))
     _lib.check(rc, "smf_hmm_copy_async")
+
+
+def build_obs(layer: torch.Tensor, cols: torch.Tensor, n_channels: int, *, coded_layer: bool = False,
+              covered: Optional[torch.Tensor] = None, covered_cols: Optional[torch.Tensor] = None,
+              out_u8: bool = True, out: Optional[torch.Tensor] = None, flag: Optional[torch.Tensor] = None):
+    """Model-input builder (``smf_hmm_build_obs``): gathers the site columns ``cols`` (int32 [L, C], -1 = no
+    site) of ``layer`` [N, V] (float32 / float64 with NaN = missing, or -- ``coded_layer`` -- the uint8 code)
+    into ``[N, L(, C)]`` observations, missing where ``covered`` (uint8 [N, VC]) is 0 at ``covered_cols[l]``.
+    Returns ``(obs, flag)``; ``flag`` (device int32) becomes 1 when the output type cannot carry a value exactly."""
+    lib = _lib.load()
+    _require_cuda(layer, "layer")
+    if layer.dim() != 2 or not layer.is_contiguous():
+        raise ValueError("layer must be a contiguous [N, V] tensor")
+    if coded_layer:
+        if layer.dtype != torch.uint8:
+            raise ValueError("a coded layer must be uint8")
+        ldt = _lib.OBS_U8
+    elif layer.dtype in (torch.float32, torch.float64):
+        ldt = _lib.OBS_F32 if layer.dtype == torch.float32 else _lib.OBS_F64
+    else:
+        raise ValueError(f"unsupported layer dtype {layer.dtype}")
+    N, V = int(layer.shape[0]), int(layer.shape[1])
+    C = int(n_channels)
+    if cols.dtype != torch.int32 or not cols.is_contiguous() or cols.numel() % C:
+        raise ValueError("cols must be a contiguous int32 [L, C] tensor")
+    L = cols.numel() // C
+    dev = layer.device
+    vc = 0
+    if covered is not None:
+        if covered.dtype != torch.uint8 or covered.dim() != 2 or int(covered.shape[0]) != N or not covered.is_contiguous():
+            raise ValueError("covered must be a contiguous uint8 [N, VC] tensor")
+        if covered_cols is None or covered_cols.dtype != torch.int32 or covered_cols.numel() != L:
+            raise ValueError("covered_cols must be int32 of length L")
+        vc = int(covered.shape[1])
+    shape = (N, L) if C == 1 else (N, L, C)
+    odt = torch.uint8 if out_u8 else torch.float32
+    if out is None:
+        out = torch.empty(shape, dtype=odt, device=dev)
+    elif out.dtype != odt or out.numel() != N * L * C or not out.is_contiguous():
+        raise ValueError("out has the wrong dtype / size")
+    if flag is None:
+        flag = torch.zeros((1,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.smf_hmm_build_obs(_ptr(layer), ldt, N, V, _ptr(cols), L, C, _ptr(covered), vc, _ptr(covered_cols),
+                                   _ptr(out), _lib.OBS_U8 if out_u8 else _lib.OBS_F32, _ptr(flag), _stream_ptr(dev))
+    _lib.check(rc, "smf_hmm_build_obs")
+    return out, flag
