@@ -48,9 +48,9 @@ WORKLOADS = {
                      "one 262,144-read chunk"),
     "c4": dict(N=262_144, L=8_000, K=4, prob=False, op="estep",
                desc="BASELINE configs[3]: 4-state Baum-Welch iteration, 262,144 reads x 8 kb per GPU"),
-    "c5": dict(N=32_768, L=20_000, K=2, prob=False, op="groups",
-               desc="BASELINE configs[4] (scaled): 16 reference groups x 32,768 reads, ragged lengths 2-20 kb, "
-                    "per-group 2-state HMM: 5 Baum-Welch iterations + posterior decode"),
+    "c5": dict(N=500_000, L=20_000, K=2, prob=False, op="groups",
+               desc="BASELINE configs[4]: 16 reference groups x 500,000 reads, ragged lengths 2-20 kb, "
+                    "per-group 2-state HMM: 5 Baum-Welch iterations (grouped device-resident fit) + posterior decode"),
 }
 
 
@@ -636,52 +636,138 @@ def e2e_legs(args, ctx, model, obs, N, L, K):
     return e2e, compact
 
 
-def run_groups(args, wl):
-    """Config #5: many (model, N_g, L_g) groups, each its own call sequence (fit 5 iterations with the
-    host M-step in the loop, then posterior decode); groups are dealt round-robin to the ranks."""
+def groups_workload(ctx, reads_per_group=500_000, n_groups=16, iters=5, K=2):
+    """BASELINE configs[4]: per-reference HMMs on 16 references x 500k reads x 2-20 kb ragged lengths.
+    Groups are dealt WHOLE to the ranks, largest first (no data-path collective); a rank fits all its groups in
+    ONE grouped, device-resident Baum-Welch (smf_hmm_grouped_fit: `iters` iterations, M-step and stop rule on the
+    device, no host round trip), the fitted parameters are exchanged once (all-reduce of a [G, P] matrix), then
+    every group's reads are posterior-decoded with that group's model in 65,536-read chunks."""
     import torch
     import torch.distributed as dist
 
     import smftools_b200 as S
+    from smftools_b200 import engine, grouped
 
-    world, rank, local, device = _dist_ctx()
+    world, rank, local, device = ctx
+    rng = np.random.default_rng(17)
+    lengths = (np.exp(rng.uniform(np.log(2000), np.log(20000), size=n_groups)).astype(int) // 16 * 16).tolist()
+    N = int(reads_per_group)
+    costs = [float(N) * L for L in lengths]
+    owned = grouped.deal_groups(costs, world)
+    mine = owned[rank]
+
+    def fresh_models():
+        return [S.create_hmm({"hmm_n_states": K, "hmm_init_emission_probs": [0.8 - 0.01 * g, 0.2 + 0.005 * g][:K]},
+                             arch="single") for g in range(n_groups)]
+
+    data = {g: device_reads(N, lengths[g], K, False, 500 + g, device, coded_u8=True) for g in mine}
+    torch.cuda.synchronize()
+    # warm-up on read prefixes (module load, allocator) + in-run parity of the same calls against the oracle
+    parity = None
+    models = fresh_models()
+    if mine:
+        pre = [S.CodedU8(data[g][:96]) for g in mine[:3]]
+        pm = [models[g] for g in mine[:3]]
+        init = grouped.pack_parameters(pm)
+        hist = grouped.fit_groups(pm, pre, max_iter=iters, tol=0.0)
+        dec = grouped.decode_groups(pm, pre)
+        torch.cuda.synchronize()
+        if rank == 0:
+            from oracle import hmm_oracle as O
+
+            t0 = time.perf_counter()
+            worst_ll = worst_p = worst_g = 0.0
+            for i, g in enumerate(mine[:3]):
+                xh = data[g][:96].cpu().numpy().astype(np.float64)
+                xh[xh > 1] = np.nan
+                p0 = O.Params(init[i, :K], init[i, K:K + K * K].reshape(K, K), init[i, K + K * K:], eps=1e-8)
+                q, h_ref = O.fit(xh, p0, max_iter=iters, tol=0.0)
+                worst_ll = max(worst_ll, float(np.max(np.abs(np.array(hist[i]) - np.array(h_ref)) / np.maximum(np.abs(h_ref), 1.0))))
+                got = grouped.pack_parameters([pm[i]])[0]
+                want = np.concatenate([q.start, q.trans.reshape(-1), q.emission.reshape(-1)])
+                worst_p = max(worst_p, float(np.abs(got - want).max()))
+                # the decode ran with the device-fitted parameters: the oracle decodes with exactly those
+                pg = O.Params(got[:K], got[K:K + K * K].reshape(K, K), got[K + K * K:], eps=1e-8)
+                g_ref, _ = O.posterior(xh, pg)
+                worst_g = max(worst_g, float(np.abs(dec[i][0].cpu().numpy() - g_ref).max()))
+            parity = {"groups": len(mine[:3]), "reads_per_group": 96, "iterations": iters,
+                      "against": "oracle/hmm_oracle.py fit + posterior per group",
+                      "max_rel_dloglik": worst_ll, "max_abs_dparam": worst_p, "max_abs_dgamma": worst_g,
+                      "tol": {"loglik_rel": 1e-6, "param_abs": 1e-4, "gamma_abs": 1e-5},
+                      "ok": bool(worst_ll <= 1e-6 and worst_p <= 1e-4 and worst_g <= 1e-5),
+                      "seconds": round(time.perf_counter() - t0, 2)}
+        del pre, dec
+    models = fresh_models()
+    obs_list = [S.CodedU8(data[g]) for g in mine]
+    _barrier(world)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record()
+    if mine:
+        hists = grouped.fit_groups([models[g] for g in mine], obs_list, max_iter=iters, tol=0.0)
+    if world > 1:
+        grouped.exchange_group_parameters(models, owned)
+    ev[1].record()
+    chunk = 65_536
+    Lmax = max(lengths)
+    gam = torch.empty((chunk * Lmax * K,), dtype=torch.float32, device=device)
+    stt = torch.empty((chunk * Lmax,), dtype=torch.int8, device=device)
+    launches = 0
+    for g in mine:
+        tables = models[g]._host_tables()
+        L = lengths[g]
+        for lo in range(0, N, chunk):
+            n = min(chunk, N - lo)
+            engine.posterior(tables, data[g][lo:lo + n], None, out_gamma=gam[:n * L * K].view(n, L, K),
+                             out_states=stt[:n * L].view(n, L))
+            launches += 1
+    ev[2].record()
+    torch.cuda.synchronize()
+    fit_ms = _max_over_ranks(ev[0].elapsed_time(ev[1]), device, world)
+    dec_ms = _max_over_ranks(ev[1].elapsed_time(ev[2]), device, world)
+    total_ms = _max_over_ranks(ev[0].elapsed_time(ev[2]), device, world)
+    rec = None
+    if rank == 0:
+        pos = float(sum(costs))
+        my_pos = float(sum(costs[g] for g in mine))
+        rec = {"name": "c5", "workload": f"BASELINE configs[4]: {n_groups} reference groups x {N} reads, ragged lengths "
+                                         f"{min(lengths)}-{max(lengths)}, per-group {K}-state HMM: {iters} Baum-Welch "
+                                         "iterations (grouped device-resident fit) + posterior decode, u8 coded obs",
+               "op": "grouped fit + decode", "K": K, "groups": n_groups, "reads_per_group": N, "lengths": lengths,
+               "groups_of_rank": owned, "value": pos * (iters + 1) / (total_ms * 1e-3), "unit": "read-positions/s",
+               "ms_total": total_ms, "fit_ms": fit_ms, "decode_ms": dec_ms,
+               "fit_read_positions_per_s": pos * iters / (fit_ms * 1e-3), "decode_read_positions_per_s": pos / (dec_ms * 1e-3),
+               "gpu_launches_rank0": launches + 1 + 4 * iters, "host_round_trips_in_fit": 1,
+               "roofline": {"fit": roofline_of("estep", K, 1, my_pos * iters, ev[0].elapsed_time(ev[1])),
+                            "decode": roofline_of("posterior", K, 1, my_pos, ev[1].elapsed_time(ev[2]))},
+               "loglik_monotone": bool(all(all(b2 >= a2 - 1e-6 * abs(a2) for a2, b2 in zip(h, h[1:])) for h in hists)) if mine else None,
+               "parity": parity}
+    del data, gam, stt, obs_list
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_groups(args, wl):
+    """`--workload c5`: BASELINE configs[4] on its own (the default run carries it in `workloads`)."""
+    import torch.distributed as dist
+
+    ctx = _dist_ctx()
+    world, rank, local, device = ctx
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    rng = np.random.default_rng(17)
-    lengths = np.exp(rng.uniform(np.log(2000), np.log(20000), size=16)).astype(int) // 4 * 4
-    N, K = wl["N"], wl["K"]
-    mine = [g for g in range(16) if g % world == rank]
-    data = {g: device_reads(N, int(lengths[g]), K, False, 500 + g, device) for g in mine}
-    gam = {g: torch.empty((N, int(lengths[g]), K), dtype=torch.float32, device=device) for g in mine}
-    stt = {g: torch.empty((N, int(lengths[g])), dtype=torch.int8, device=device) for g in mine}
-    from smftools_b200 import engine
-
-    def one_pass():
-        for g in mine:
-            m = S.create_hmm({"hmm_n_states": K, "hmm_init_emission_probs": [0.8, 0.2]}, arch="single")
-            m.fit(data[g], max_iter=5, tol=0.0)
-            engine.posterior(m._host_tables(), data[g], None, out_gamma=gam[g], out_states=stt[g])
-
-    for _ in range(max(1, min(args.warmup, 2))):
-        one_pass()
-    _barrier(world)
-    steps = max(1, min(args.steps, 3))
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(steps):
-        one_pass()
-    b.record()
-    torch.cuda.synchronize()
-    ms = _max_over_ranks(a.elapsed_time(b), device, world) / steps
-    rp = float(sum(N * int(lengths[g]) * 6 for g in range(16)))  # 5 E-steps + 1 decode per position
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    rec = groups_workload(ctx, reads_per_group=args.group_reads)
+    clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
         emit({
-            "metric": "HMM read-positions/sec", "value": rp / (ms * 1e-3), "unit": "read-positions/s", "n_gpus": world,
-            "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": ms, "higher_is_better": True,
+            "metric": "HMM read-positions/sec", "value": rec["value"], "unit": "read-positions/s", "n_gpus": world,
+            "steps": 1, "warmup": 1, "ms_per_step": rec["ms_total"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "op": "5x Baum-Welch iteration + posterior decode per group",
-                       "groups": 16, "reads_per_group": N, "lengths": [int(x) for x in lengths], "K": K},
-            "gpu_launches": steps * len(mine) * 11,
+            "config": {"workload": rec["workload"], "op": rec["op"], "groups": rec["groups"],
+                       "reads_per_group": rec["reads_per_group"], "lengths": rec["lengths"], "K": rec["K"]},
+            "clocks": clocks, "gpu_launches": rec["gpu_launches_rank0"], "roofline": rec["roofline"]["decode"],
+            "parity": rec["parity"], "workloads": [rec],
         })
     if world > 1:
         dist.destroy_process_group()
@@ -804,6 +890,9 @@ def run_ours(args, wl):
             rec = stream_workload(name, ctx)
             if rec is not None:
                 extra.append(rec)
+        rec = groups_workload(ctx, reads_per_group=args.group_reads)
+        if rec is not None:
+            extra.append(rec)
 
     if rank == 0:
         k_ms = statistics.mean(kernel_ms)
@@ -875,6 +964,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the full-size runs of the other BASELINE shapes")
     ap.add_argument("--bw-reads", type=int, default=4_000_000, help="total reads of the configs[3] fit (sharded over the GPUs)")
     ap.add_argument("--bw-iters", type=int, default=20, help="Baum-Welch iterations of the configs[3] fit")
+    ap.add_argument("--group-reads", type=int, default=500_000, help="reads per reference group of the configs[4] workload")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

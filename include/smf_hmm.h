@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SMF_HMM_ABI_VERSION 3
+#define SMF_HMM_ABI_VERSION 4
 
 #define SMF_MAX_STATES 4
 #define SMF_MAX_CHANNELS 4
@@ -146,6 +146,65 @@ int64_t smf_hmm_stats_len(const smf_hmm_tables* tab);
 int smf_hmm_estep(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int64_t n_reads,
                   int64_t n_pos, const int8_t* bins, double* stats, void* workspace,
                   size_t workspace_bytes, void* stream);
+
+/*
+ * ---- grouped launches: many (parameters, N_g, L_g) groups per call ------------------------------------
+ *
+ * The reference fits and applies one HMM per (reference x methylation type [x sample / barcode]) group, one
+ * after the other (cli/hmm_adata.py:488-524 HMMTrainer.fit_or_load per task; hmm/fit_plan.py:12-14 group
+ * fields; hmm_max_fit_reads = 1000 reads per fit).  A group that small cannot fill the GPU, and an EM
+ * iteration per group costs a host round trip.  These entry points take a TABLE of groups -- each with its own
+ * observation matrix, read count, read length and parameters -- and run all of them in one launch sequence:
+ * one thread per read (checkpointed forward pass + one backward pass), work items of 128
+ * reads dealt over the SMs regardless of group boundaries.  smf_hmm_grouped_fit additionally keeps the whole
+ * Baum-Welch loop on the device (E-step statistics -> per-group reduction -> M-step + stop rule + table
+ * rebuild, HMM.py:1566-1630), so max_iter iterations of every group are enqueued without a host round trip.
+ * Single-channel, homogeneous-transition models (arch "single") only.
+ */
+typedef struct smf_hmm_group {
+  const void* obs;     /* device [n_reads, row_stride] of obs_dtype (SMF_OBS_U8 or SMF_OBS_F32), 16-byte aligned   */
+  int64_t n_reads;
+  int32_t n_pos;       /* L_g: positions per read of this group                                                   */
+  int32_t row_stride;  /* elements between rows, >= n_pos; a multiple of 16 (uint8) / 4 (float); the pad is not read
+                          as data but must be addressable                                                           */
+  float* gamma;        /* posterior: device [n_reads, out_stride, K] (gamma_state < 0) or [n_reads, out_stride]; NULL ok */
+  int8_t* states;      /* posterior: device [n_reads, out_stride]; NULL ok                                          */
+  double* loglik;      /* device [n_reads] per-read log-likelihood; NULL ok                                         */
+  int32_t gamma_state;
+  int32_t out_stride;  /* positions between output rows, >= n_pos, a multiple of 4 (columns >= n_pos are scratch)   */
+} smf_hmm_group;
+
+#define SMF_FIT_RAN_ALL 0     /* the group ran max_iter iterations                                                 */
+#define SMF_FIT_CONVERGED 1   /* |dLL| < tol * max(1, |LL|) (HMM.py:1616-1628) after n_iter iterations             */
+#define SMF_FIT_HANDED_BACK 2 /* after n_iter iterations the parameters left the dynamic range these kernels cover
+                                 with their fixed rescale cadence: params / hist are valid up to there and the caller
+                                 continues the group with smf_hmm_estep (which routes such models itself)          */
+
+/* fit != 0: workspace of smf_hmm_grouped_fit, else of smf_hmm_grouped_posterior.  0 on invalid arguments. */
+size_t smf_hmm_grouped_workspace_bytes(int n_states, const smf_hmm_group* groups_host, int n_groups, int fit);
+
+/*
+ * Posterior decode of every group with its own model (HMM.py:572-629, 718 per group).  tabs_host[g] are the
+ * log tables of group g (host pointers, as everywhere).  Outputs per group as in smf_hmm_posterior.
+ * SMF_ERR_BAD_ARG when a model is not single-channel / homogeneous or needs a finer rescale cadence than
+ * these kernels use (decode such a group with smf_hmm_posterior).
+ */
+int smf_hmm_grouped_posterior(int obs_dtype, const smf_hmm_group* groups_host, int n_groups,
+                              const smf_hmm_tables* tabs_host, void* workspace, size_t workspace_bytes,
+                              void* stream);
+
+/*
+ * Baum-Welch fit of every group, entirely on the device (replaces n_groups x the fit_em loop, HMM.py:1518-1630).
+ *   params     device double [n_groups, K + K*K + K] = start | trans | emission per group: initial values in,
+ *              fitted values out (normalised and clamped like HMM.py:492-511 after every update)
+ *   update_mask bit 0 start, bit 1 transitions, bit 2 emissions (the reference's update_* flags)
+ *   hist       device double [n_groups, max_iter]: total log-likelihood before each M-step
+ *   n_iter     device int32 [n_groups]: iterations done;  status: device int32 [n_groups] SMF_FIT_*
+ * Everything is enqueued on `stream`; read params / hist / n_iter / status back after synchronising it.
+ */
+int smf_hmm_grouped_fit(int n_states, int obs_dtype, const smf_hmm_group* groups_host, int n_groups,
+                        double* params, int max_iter, double tol, double eps, int update_mask, double* hist,
+                        int32_t* n_iter, int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Footprint / feature calling on decoded reads.  Replaces the per-read Python loops of
@@ -311,7 +370,8 @@ int smf_hmm_layer_colsums(const uint8_t* cls_or_code, int packed, const uint8_t*
                           uint64_t* colvalid /*[V]*/, void* stream);
 
 /* means[v] = colsum[v] / colvalid[v] (0 where no read covers v: nan_to_num) and metric = the 'same'-mode rolling
- * mean np.convolve(means, ones(w) / w, "same") (hmm/call_hmm_peaks.py:151-158). */
+ * mean np.convolve(means, ones(w) / w, "same") (hmm/call_hmm_peaks.py:151-158).  Like np.convolve, `metric` has
+ * max(n_grid, w) elements when w > 1 (a grid narrower than the window yields w values), else n_grid. */
 int smf_hmm_column_metric(const uint64_t* colsum, const uint64_t* colvalid, int64_t n_grid, int rolling_window,
                           double* means, double* metric, void* stream);
 

@@ -35,6 +35,9 @@ EXPORTS = (
     "smf_hmm_viterbi",
     "smf_hmm_stats_len",
     "smf_hmm_estep",
+    "smf_hmm_grouped_workspace_bytes",
+    "smf_hmm_grouped_posterior",
+    "smf_hmm_grouped_fit",
     "smf_hmm_call_features",
     "smf_hmm_merge_runs",
     "smf_hmm_merge_chain",
@@ -82,6 +85,22 @@ class Tables(ctypes.Structure):
     ]
 
 
+class Group(ctypes.Structure):
+    """Mirror of ``smf_hmm_group``."""
+
+    _fields_ = [
+        ("obs", c_void_p),
+        ("n_reads", c_int64),
+        ("n_pos", c_int32),
+        ("row_stride", c_int32),
+        ("gamma", c_void_p),
+        ("states", c_void_p),
+        ("loglik", c_void_p),
+        ("gamma_state", c_int32),
+        ("out_stride", c_int32),
+    ]
+
+
 class HostTables:
     """Owns the fp64 host arrays a ``Tables`` struct points at."""
 
@@ -118,7 +137,7 @@ def library_built() -> bool:
     return os.path.isfile(LIB_PATH)
 
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 def load():
@@ -154,6 +173,14 @@ def load():
     lib.smf_hmm_estep.restype = c_int
     lib.smf_hmm_estep.argtypes = [T, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                   c_size_t, c_void_p]
+    GP = POINTER(Group)
+    lib.smf_hmm_grouped_workspace_bytes.restype = c_size_t
+    lib.smf_hmm_grouped_workspace_bytes.argtypes = [c_int, GP, c_int, c_int]
+    lib.smf_hmm_grouped_posterior.restype = c_int
+    lib.smf_hmm_grouped_posterior.argtypes = [c_int, GP, c_int, T, c_void_p, c_size_t, c_void_p]
+    lib.smf_hmm_grouped_fit.restype = c_int
+    lib.smf_hmm_grouped_fit.argtypes = [c_int, c_int, GP, c_int, c_void_p, c_int, c_double, c_double, c_int, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.smf_hmm_call_features.restype = c_int
     lib.smf_hmm_call_features.argtypes = [c_void_p, c_void_p, c_int, c_double, c_int64, c_int64, c_void_p,
                                           c_void_p, c_void_p, c_int64, POINTER(c_double), POINTER(c_double),

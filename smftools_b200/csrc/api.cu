@@ -19,6 +19,8 @@
 #include "smf_hmm.h"
 #include "post_sweep_kernel.cuh"
 #include "seq_kernel.cuh"
+#include <algorithm>
+#include <vector>
 #include "short_kernel.cuh"
 #include "sweep_kernel.cuh"
 #include "walk_kernel.cuh"
@@ -495,6 +497,15 @@ static bool seq_launch_eligible(const smf_hmm_tables* t, int64_t N, int64_t L, i
   if (obs_dtype == SMF_OBS_F32) return (L & 3) == 0;
   return false;
 }
+// posterior decode on the sequential kernels: K >= 3 by default (K = 2 has the faster chunk-parallel kernel;
+// "seq" = 1 forces it for every eligible batch)
+static bool seq_post_shape_eligible(const smf_hmm_tables* t, int64_t N, int64_t L) {
+  if (!seq_shape_eligible(t, N, L)) return false;
+  if (g_seq_mode == 1) return true;
+  // measured (profiles/r02_seq_post.txt): K = 4 wins at every length (0.31-0.37 of HBM peak vs 0.26-0.30 for the
+  // chunk-parallel kernels at 5 kb); K = 3 only for short reads, where fb2_kernel's scan is amortised badly
+  return t->n_states == 4 || (t->n_states == 3 && L <= 640);
+}
 static size_t seq_ws_bytes(int K, int64_t N, int64_t L) {
   const size_t tact = (size_t)((L + kSeqCH - 1) / kSeqCH);
   return tact * (size_t)N * SeqVec<4>::KP * sizeof(float) + (size_t)N * sizeof(double) + 64;
@@ -755,9 +766,15 @@ size_t smf_hmm_workspace_bytes(int op, const smf_hmm_tables* tab, int64_t n_read
       }
       return b + extra;
     }
-    case SMF_OP_POSTERIOR:
+    case SMF_OP_POSTERIOR: {
       if (check_tables(tab) != SMF_OK) return 0;
-      return walk_eligible(tab, n_reads, n_pos, false) ? walk_ws_bytes(tab->n_states, n_reads, n_pos) : 0;
+      size_t b = walk_eligible(tab, n_reads, n_pos, false) ? walk_ws_bytes(tab->n_states, n_reads, n_pos) : 0;
+      if (seq_post_shape_eligible(tab, n_reads, n_pos)) {
+        const size_t sq = seq_ws_bytes(tab->n_states, n_reads, n_pos);
+        if (sq > b) b = sq;
+      }
+      return b;
+    }
     default: return 0;
   }
 }
@@ -813,6 +830,34 @@ int smf_hmm_posterior(const smf_hmm_tables* tab, const void* obs, int obs_dtype,
         sa.loglik = loglik;
         return launch_short(tab, obs_dtype, sa, di, (cudaStream_t)stream);
       }
+    }
+    // large batches of K >= 3: one thread per read (checkpointed forward pass, one backward pass, posteriors
+    // staged in shared memory and written as whole sectors) when the caller provided the checkpoint workspace
+    if (workspace != nullptr && seq_post_shape_eligible(tab, n_reads, n_pos) &&
+        seq_launch_eligible(tab, n_reads, n_pos, obs_dtype, obs) && (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0 &&
+        (reinterpret_cast<uintptr_t>(states) & 3u) == 0 && (reinterpret_cast<uintptr_t>(gamma) & 15u) == 0) {
+      if (workspace_bytes < seq_ws_bytes(tab->n_states, n_reads, n_pos)) return SMF_ERR_WORKSPACE;
+      char* wws = reinterpret_cast<char*>(workspace);
+      SeqArgs q;
+      memset(&q, 0, sizeof(q));
+      q.g.obs = obs;
+      q.g.N = n_reads;
+      q.g.L = (int)n_pos;
+      q.g.row_stride = (int)n_pos;
+      q.g.Tact = (int)((n_pos + kSeqCH - 1) / kSeqCH);
+      q.g.ll = loglik != nullptr ? loglik : reinterpret_cast<double*>(wws);
+      q.g.ckpt = reinterpret_cast<float*>(wws + (((size_t)n_reads * sizeof(double) + 63) & ~(size_t)63));
+      q.g.gamma = gamma;
+      q.g.states = states;
+      q.g.gamma_state = gamma_state;
+      q.g.out_stride = (int)n_pos;
+      q.n_items = (n_reads + kSeqThreads - 1) / kSeqThreads;
+      q.flush_chunks = 8;
+      const int mode = (gamma != nullptr || states != nullptr) ? MODE_POST : -1;
+      cudaStream_t st = (cudaStream_t)stream;
+      return (tab->n_states == 2)   ? launch_seq_k2(obs_dtype, mode, tab, q, di, nullptr, st)
+             : (tab->n_states == 3) ? launch_seq_k3(obs_dtype, mode, tab, q, di, nullptr, st)
+                                    : launch_seq_k4(obs_dtype, mode, tab, q, di, nullptr, st);
     }
     Fb2Args b;
     memset(&b, 0, sizeof(b));
@@ -969,19 +1014,22 @@ int smf_hmm_estep(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int
       char* wws = reinterpret_cast<char*>(workspace) + (size_t)kMaxEstepBlocks * (size_t)S * sizeof(double);
       SeqArgs q;
       memset(&q, 0, sizeof(q));
-      q.obs = obs;
-      q.N = n_reads;
-      q.L = (int)n_pos;
-      q.Tact = (int)((n_pos + kSeqCH - 1) / kSeqCH);
-      q.ll = reinterpret_cast<double*>(wws);
-      q.ckpt = reinterpret_cast<float*>(wws + (((size_t)n_reads * sizeof(double) + 63) & ~(size_t)63));
+      q.g.obs = obs;
+      q.g.N = n_reads;
+      q.g.L = (int)n_pos;
+      q.g.row_stride = (int)n_pos;
+      q.g.Tact = (int)((n_pos + kSeqCH - 1) / kSeqCH);
+      q.g.ll = reinterpret_cast<double*>(wws);
+      q.g.ckpt = reinterpret_cast<float*>(wws + (((size_t)n_reads * sizeof(double) + 63) & ~(size_t)63));
+      q.g.gamma_state = -1;
+      q.n_items = (n_reads + kSeqThreads - 1) / kSeqThreads;
       q.partials = reinterpret_cast<double*>(workspace);
       q.S = S;
       q.flush_chunks = 8;
       int nb2 = kMaxEstepBlocks;
-      rc = (tab->n_states == 2)   ? launch_seq_estep_k2(obs_dtype, tab, q, di, &nb2, st)
-           : (tab->n_states == 3) ? launch_seq_estep_k3(obs_dtype, tab, q, di, &nb2, st)
-                                  : launch_seq_estep_k4(obs_dtype, tab, q, di, &nb2, st);
+      rc = (tab->n_states == 2)   ? launch_seq_k2(obs_dtype, MODE_STATS, tab, q, di, &nb2, st)
+           : (tab->n_states == 3) ? launch_seq_k3(obs_dtype, MODE_STATS, tab, q, di, &nb2, st)
+                                  : launch_seq_k4(obs_dtype, MODE_STATS, tab, q, di, &nb2, st);
       if (rc != SMF_OK) return rc;
       reduce_partials_kernel<<<(S + 127) / 128, 128, 0, st>>>(q.partials, nb2, S, stats);
       return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
@@ -1288,6 +1336,252 @@ int smf_hmm_span_mask(const uint8_t* covered, const int64_t* coords, const doubl
             (unsigned)(n_reads > 32768 ? 32768 : n_reads));
   span_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// grouped launches (seq_kernel.cuh, GROUPED = true)
+// ---------------------------------------------------------------------------------------
+namespace {
+
+struct GroupedPlan {
+  size_t off_groups, off_item_group, off_tabs, off_active, off_stats, off_partials, off_scratch, total;
+  long long n_items;
+  int S;
+};
+
+inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
+inline size_t seq_tables_bytes(int K) {
+  return K == 2 ? sizeof(FbTables<2>) : (K == 3 ? sizeof(FbTables<3>) : sizeof(FbTables<4>));
+}
+
+// Validates the group table and lays the workspace out:
+//   SeqGroup[G] | item_group[n_items] | FbTables<K>[G] | active[G] | stats[G][S] | partials[n_items][S] (fit)
+//   | per group: log-likelihood [N] (when the caller gave none) and alpha checkpoints [Tact][N][KP]
+// With `out` != nullptr the device group table and the item table are also written (host copies).
+int grouped_plan(int K, int obs_dtype, const smf_hmm_group* gh, int G, bool fit, GroupedPlan* pl, char* ws_base,
+                 SeqGroup* out_groups, int* out_item_group) {
+  if (K < 2 || K > SMF_MAX_STATES || gh == nullptr || G < 1) return SMF_ERR_BAD_ARG;
+  if (obs_dtype != SMF_OBS_U8 && obs_dtype != SMF_OBS_F32) return SMF_ERR_BAD_ARG;
+  const int KP = (K == 2) ? 2 : 4;
+  const int S = K + K * K + 2 * K + 1;
+  long long n_items = 0;
+  for (int g = 0; g < G; ++g) {
+    const smf_hmm_group& q = gh[g];
+    if (q.n_reads < 1 || q.n_pos < 1 || q.n_pos > (1 << 24) || q.obs == nullptr) return SMF_ERR_BAD_ARG;
+    if (q.row_stride < q.n_pos || (q.row_stride % (obs_dtype == SMF_OBS_U8 ? 16 : 4)) != 0) return SMF_ERR_ALIGN;
+    if (reinterpret_cast<uintptr_t>(q.obs) & 15u) return SMF_ERR_ALIGN;
+    if (!fit && (q.gamma != nullptr || q.states != nullptr)) {
+      if (q.out_stride < q.n_pos || (q.out_stride & 3)) return SMF_ERR_ALIGN;
+      if ((reinterpret_cast<uintptr_t>(q.gamma) & 15u) || (reinterpret_cast<uintptr_t>(q.states) & 3u)) return SMF_ERR_ALIGN;
+      if (q.gamma_state >= K) return SMF_ERR_BAD_ARG;
+    }
+    n_items += (q.n_reads + kSeqThreads - 1) / kSeqThreads;
+    if (n_items > 0x7fffffff) return SMF_ERR_BAD_ARG;
+  }
+  size_t off = 0;
+  pl->S = S;
+  pl->n_items = n_items;
+  pl->off_groups = off;
+  off = up256(off + (size_t)G * sizeof(SeqGroup));
+  pl->off_item_group = off;
+  off = up256(off + (size_t)n_items * sizeof(int));
+  pl->off_tabs = off;
+  off = up256(off + (size_t)G * seq_tables_bytes(K));
+  pl->off_active = off;
+  off = up256(off + (size_t)G * sizeof(int));
+  pl->off_stats = off;
+  off = up256(off + (fit ? (size_t)G * S * sizeof(double) : 0));
+  pl->off_partials = off;
+  off = up256(off + (fit ? (size_t)n_items * S * sizeof(double) : 0));
+  pl->off_scratch = off;
+  // Work items are dealt to the CTAs in table order: the groups with the longest reads come first in the item
+  // table so that the tail of the launch is made of short items (outputs keep the caller's group order).
+  std::vector<int> order(G);
+  for (int g = 0; g < G; ++g) order[g] = g;
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return gh[x].n_pos > gh[y].n_pos; });
+  long long item0 = 0;
+  for (int oi = 0; oi < G; ++oi) {
+    const int g = order[oi];
+    const smf_hmm_group& q = gh[g];
+    const int tact = (q.n_pos + kSeqCH - 1) / kSeqCH;
+    size_t off_ll = 0;
+    const bool own_ll = fit || q.loglik == nullptr;
+    if (own_ll) {
+      off_ll = off;
+      off = up256(off + (size_t)q.n_reads * sizeof(double));
+    }
+    const size_t off_ck = off;
+    off = up256(off + (size_t)tact * (size_t)q.n_reads * KP * sizeof(float));
+    const long long items = (q.n_reads + kSeqThreads - 1) / kSeqThreads;
+    if (out_groups != nullptr) {
+      SeqGroup& d = out_groups[g];
+      memset(&d, 0, sizeof(d));
+      d.obs = q.obs;
+      d.N = q.n_reads;
+      d.L = q.n_pos;
+      d.row_stride = q.row_stride;
+      d.Tact = tact;
+      d.item0 = (int)item0;
+      d.ckpt = reinterpret_cast<float*>(ws_base + off_ck);
+      d.ll = own_ll ? reinterpret_cast<double*>(ws_base + off_ll) : q.loglik;
+      d.gamma = fit ? nullptr : q.gamma;
+      d.states = fit ? nullptr : q.states;
+      d.gamma_state = q.gamma_state;
+      d.out_stride = q.out_stride;
+      for (long long i = 0; i < items; ++i) out_item_group[item0 + i] = g;
+    }
+    item0 += items;
+  }
+  pl->total = off;
+  return SMF_OK;
+}
+
+int grouped_upload(const GroupedPlan& pl, int G, const std::vector<SeqGroup>& groups, const std::vector<int>& item_group,
+                   char* ws, cudaStream_t st) {
+  if (cudaMemcpyAsync(ws + pl.off_groups, groups.data(), (size_t)G * sizeof(SeqGroup), cudaMemcpyHostToDevice, st) !=
+      cudaSuccess)
+    return SMF_ERR_CUDA;
+  if (cudaMemcpyAsync(ws + pl.off_item_group, item_group.data(), (size_t)pl.n_items * sizeof(int),
+                      cudaMemcpyHostToDevice, st) != cudaSuccess)
+    return SMF_ERR_CUDA;
+  return SMF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t smf_hmm_grouped_workspace_bytes(int n_states, const smf_hmm_group* groups_host, int n_groups, int fit) {
+  GroupedPlan pl;
+  // the dtype only decides the row-stride rule; sizes do not depend on it
+  int rc = grouped_plan(n_states, SMF_OBS_F32, groups_host, n_groups, fit != 0, &pl, nullptr, nullptr, nullptr);
+  if (rc == SMF_ERR_ALIGN) rc = grouped_plan(n_states, SMF_OBS_U8, groups_host, n_groups, fit != 0, &pl, nullptr, nullptr, nullptr);
+  return rc == SMF_OK ? pl.total : 0;
+}
+
+int smf_hmm_grouped_posterior(int obs_dtype, const smf_hmm_group* groups_host, int n_groups,
+                              const smf_hmm_tables* tabs_host, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  if (tabs_host == nullptr || workspace == nullptr || n_groups < 1) return SMF_ERR_BAD_ARG;
+  const int K = tabs_host[0].n_states;
+  for (int g = 0; g < n_groups; ++g) {
+    int rc = check_tables(&tabs_host[g]);
+    if (rc != SMF_OK) return rc;
+    if (tabs_host[g].n_states != K || tabs_host[g].n_channels != 1 || tabs_host[g].n_bins != 1) return SMF_ERR_BAD_ARG;
+    if (rescale_cadence(&tabs_host[g]) != 4) return SMF_ERR_BAD_ARG;
+  }
+  GroupedPlan pl;
+  std::vector<SeqGroup> groups(n_groups);
+  int rc = grouped_plan(K, obs_dtype, groups_host, n_groups, false, &pl, nullptr, nullptr, nullptr);
+  if (rc != SMF_OK) return rc;
+  if (workspace_bytes < pl.total) return SMF_ERR_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(workspace) & 255u) return SMF_ERR_ALIGN;
+  std::vector<int> item_group((size_t)pl.n_items);
+  char* ws = reinterpret_cast<char*>(workspace);
+  rc = grouped_plan(K, obs_dtype, groups_host, n_groups, false, &pl, ws, groups.data(), item_group.data());
+  if (rc != SMF_OK) return rc;
+  DeviceInfo di;
+  rc = get_device_info(&di);
+  if (rc != SMF_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = grouped_upload(pl, n_groups, groups, item_group, ws, st);
+  if (rc != SMF_OK) return rc;
+  // per-group kernel tables, built on the host like for every other launch
+  const size_t tb = seq_tables_bytes(K);
+  std::vector<unsigned char> tabs((size_t)n_groups * tb);
+  for (int g = 0; g < n_groups; ++g) {
+    void* dst = tabs.data() + (size_t)g * tb;
+    if (K == 2) build_fb_tables<2>(&tabs_host[g], reinterpret_cast<FbTables<2>*>(dst));
+    else if (K == 3) build_fb_tables<3>(&tabs_host[g], reinterpret_cast<FbTables<3>*>(dst));
+    else build_fb_tables<4>(&tabs_host[g], reinterpret_cast<FbTables<4>*>(dst));
+  }
+  if (cudaMemcpyAsync(ws + pl.off_tabs, tabs.data(), tabs.size(), cudaMemcpyHostToDevice, st) != cudaSuccess)
+    return SMF_ERR_CUDA;
+  bool any_out = false;
+  for (int g = 0; g < n_groups; ++g) any_out = any_out || groups_host[g].gamma != nullptr || groups_host[g].states != nullptr;
+  SeqArgs a;
+  memset(&a, 0, sizeof(a));
+  a.groups = reinterpret_cast<const SeqGroup*>(ws + pl.off_groups);
+  a.tabs = ws + pl.off_tabs;
+  a.item_group = reinterpret_cast<const int*>(ws + pl.off_item_group);
+  a.active = nullptr;
+  a.n_items = pl.n_items;
+  a.S = 0;
+  a.flush_chunks = 8;
+  const int mode = any_out ? MODE_POST : -1;
+  return K == 2 ? launch_seq_grouped_k2(obs_dtype, mode, a, di, st)
+                : (K == 3 ? launch_seq_grouped_k3(obs_dtype, mode, a, di, st) : launch_seq_grouped_k4(obs_dtype, mode, a, di, st));
+}
+
+int smf_hmm_grouped_fit(int n_states, int obs_dtype, const smf_hmm_group* groups_host, int n_groups,
+                        double* params, int max_iter, double tol, double eps, int update_mask, double* hist,
+                        int32_t* n_iter, int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+  const int K = n_states;
+  if (params == nullptr || hist == nullptr || n_iter == nullptr || status == nullptr || workspace == nullptr)
+    return SMF_ERR_BAD_ARG;
+  if (max_iter < 0 || !(eps > 0.0)) return SMF_ERR_BAD_ARG;
+  GroupedPlan pl;
+  int rc = grouped_plan(K, obs_dtype, groups_host, n_groups, true, &pl, nullptr, nullptr, nullptr);
+  if (rc != SMF_OK) return rc;
+  if (workspace_bytes < pl.total) return SMF_ERR_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(workspace) & 255u) return SMF_ERR_ALIGN;
+  std::vector<SeqGroup> groups(n_groups);
+  std::vector<int> item_group((size_t)pl.n_items);
+  char* ws = reinterpret_cast<char*>(workspace);
+  rc = grouped_plan(K, obs_dtype, groups_host, n_groups, true, &pl, ws, groups.data(), item_group.data());
+  if (rc != SMF_OK) return rc;
+  DeviceInfo di;
+  rc = get_device_info(&di);
+  if (rc != SMF_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = grouped_upload(pl, n_groups, groups, item_group, ws, st);
+  if (rc != SMF_OK) return rc;
+  SeqFitState f;
+  memset(&f, 0, sizeof(f));
+  f.params = params;
+  f.stats = reinterpret_cast<double*>(ws + pl.off_stats);
+  f.hist = hist;
+  f.active = reinterpret_cast<int*>(ws + pl.off_active);
+  f.n_iter = n_iter;
+  f.status = status;
+  f.tabs = ws + pl.off_tabs;
+  f.n_groups = n_groups;
+  f.S = pl.S;
+  f.max_iter = max_iter > 0 ? max_iter : 1;
+  f.eps = eps;
+  f.tol = tol;
+  f.update_start = (update_mask & 1) != 0;
+  f.update_trans = (update_mask & 2) != 0;
+  f.update_emission = (update_mask & 4) != 0;
+  auto mstep = [&](int iter) {
+    f.iter = iter;
+    return K == 2 ? launch_seq_mstep_k2(f, st) : (K == 3 ? launch_seq_mstep_k3(f, st) : launch_seq_mstep_k4(f, st));
+  };
+  rc = mstep(-1);  // tables of the initial parameters; every group active
+  if (rc != SMF_OK) return rc;
+  SeqArgs a;
+  memset(&a, 0, sizeof(a));
+  a.groups = reinterpret_cast<const SeqGroup*>(ws + pl.off_groups);
+  a.tabs = ws + pl.off_tabs;
+  a.item_group = reinterpret_cast<const int*>(ws + pl.off_item_group);
+  a.active = f.active;
+  a.n_items = pl.n_items;
+  a.partials = reinterpret_cast<double*>(ws + pl.off_partials);
+  a.S = pl.S;
+  a.flush_chunks = 8;
+  for (int it = 0; it < max_iter; ++it) {
+    rc = K == 2 ? launch_seq_grouped_k2(obs_dtype, MODE_STATS, a, di, st)
+                : (K == 3 ? launch_seq_grouped_k3(obs_dtype, MODE_STATS, a, di, st)
+                          : launch_seq_grouped_k4(obs_dtype, MODE_STATS, a, di, st));
+    if (rc != SMF_OK) return rc;
+    seq_reduce_groups_kernel<<<n_groups * pl.S, 256, 0, st>>>(a.partials, a.groups, pl.S, f.stats);
+    if (cudaGetLastError() != cudaSuccess) return SMF_ERR_CUDA;
+    rc = mstep(it);
+    if (rc != SMF_OK) return rc;
+  }
+  return SMF_OK;
 }
 
 }  // extern "C"

@@ -136,12 +136,16 @@ struct SeqArgs;
 struct SweepArgs;
 struct ShortArgs;
 struct PostSweepArgs;
-int launch_seq_estep_k2(int obs_dtype, const smf_hmm_tables* t, const SeqArgs& a, const DeviceInfo& di, int* nblocks,
-                        cudaStream_t s);
-int launch_seq_estep_k3(int obs_dtype, const smf_hmm_tables* t, const SeqArgs& a, const DeviceInfo& di, int* nblocks,
-                        cudaStream_t s);
-int launch_seq_estep_k4(int obs_dtype, const smf_hmm_tables* t, const SeqArgs& a, const DeviceInfo& di, int* nblocks,
-                        cudaStream_t s);
+struct SeqFitState;
+#define SMF_DECLARE_SEQ(KV)                                                                                          \
+  int launch_seq_k##KV(int obs_dtype, int mode, const smf_hmm_tables* t, const SeqArgs& a, const DeviceInfo& di,     \
+                       int* nblocks, cudaStream_t s);                                                                \
+  int launch_seq_grouped_k##KV(int obs_dtype, int mode, const SeqArgs& a, const DeviceInfo& di, cudaStream_t s);     \
+  int launch_seq_mstep_k##KV(const SeqFitState& f, cudaStream_t s);
+SMF_DECLARE_SEQ(2)
+SMF_DECLARE_SEQ(3)
+SMF_DECLARE_SEQ(4)
+#undef SMF_DECLARE_SEQ
 int launch_walk_k2(int obs_dtype, const smf_hmm_tables* t, const WalkArgs& a, cudaStream_t s);
 int launch_post_sweep_k2(int obs_dtype, const smf_hmm_tables* t, PostSweepArgs& a, const DeviceInfo& di, cudaStream_t s);
 int launch_post_sweep_k3(int obs_dtype, const smf_hmm_tables* t, PostSweepArgs& a, const DeviceInfo& di, cudaStream_t s);

@@ -75,20 +75,22 @@ struct MetricArgs {
 // nan-mean per column (0 where no read covers the column) and the 'same'-mode rolling mean of np.convolve.
 __global__ void column_metric_kernel(const __grid_constant__ MetricArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.V) return;
+  const int w = a.window;
+  // np.convolve(..., "same") returns max(V, w) values: the centre of the full convolution, offset (min(V, w) - 1) / 2
+  const int out_len = (w > 1 && w > a.V) ? w : a.V;
+  if (i >= out_len) return;
   auto mean_at = [&](int j) -> double {
     const unsigned long long d = a.colvalid[j];
     return d ? (double)a.colsum[j] / (double)d : 0.0;
   };
-  a.means[i] = mean_at(i);
-  const int w = a.window;
+  if (i < a.V) a.means[i] = mean_at(i);
   if (w <= 1) {
     a.metric[i] = mean_at(i);
     return;
   }
-  // full[k] = sum_j means[j] * kern[k - j], same = full[(w - 1) / 2 + i]; kern = 1 / w
+  // full[k] = sum_j means[j] * kern[k - j], same = full[off + i]; kern = 1 / w
   const double kv = 1.0 / (double)w;
-  const int k = (w - 1) / 2 + i;
+  const int k = ((w < a.V ? w : a.V) - 1) / 2 + i;
   double s = 0.0;
   // numpy accumulates over the kernel index m = k - j from 0 upwards; keep that order
   for (int m = 0; m < w; ++m) {
@@ -221,7 +223,8 @@ int smf_hmm_column_metric(const uint64_t* colsum, const uint64_t* colvalid, int6
   a.window = rolling_window;
   a.means = means;
   a.metric = metric;
-  column_metric_kernel<<<(int)((n_grid + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+  const int64_t out_len = (rolling_window > 1 && rolling_window > n_grid) ? rolling_window : n_grid;
+  column_metric_kernel<<<(int)((out_len + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
 }
 

@@ -71,7 +71,8 @@ def column_mean_metric(colsum: torch.Tensor, colvalid: torch.Tensor, rolling_win
     dev = colsum.device
     colsum = colsum.contiguous()
     means = torch.empty((V,), dtype=torch.float64, device=dev)
-    metric = torch.empty((V,), dtype=torch.float64, device=dev)
+    w = max(1, int(rolling_window))
+    metric = torch.empty((max(V, w) if w > 1 else V,), dtype=torch.float64, device=dev)  # np.convolve "same" length
     with torch.cuda.device(dev):
         rc = _lib.load().smf_hmm_column_metric(engine._ptr(colsum), engine._ptr(colvalid), V, max(1, int(rolling_window)),
                                                engine._ptr(means), engine._ptr(metric), engine._stream_ptr(dev))

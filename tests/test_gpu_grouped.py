@@ -1,0 +1,201 @@
+"""GPU parity of the grouped launches (smf_hmm_grouped_fit / smf_hmm_grouped_posterior): many ragged
+(model, N_g, L_g) groups in one launch sequence, the Baum-Welch loop entirely on the device.
+
+Every group is checked against the oracle run on that group alone with that group's parameters, and against
+the per-group path of the host mirror (model.fit / model.decode)."""
+import numpy as np
+import pytest
+import torch
+
+import smftools_b200 as S
+from helpers import assert_states_match_up_to_ties, model_from_params, params_of_model
+from oracle import hmm_oracle as O
+from smftools_b200 import grouped
+
+pytestmark = pytest.mark.gpu
+
+
+def _code(X32):
+    return np.where(np.isnan(X32), 255, X32).astype(np.uint8)
+
+
+def _perturbed(K, g):
+    """Per-group parameters: the synthetic ones with a group-dependent tilt (every group its own model)."""
+    p = O.synth_params(K)
+    em = np.clip(p.emission + 0.04 * ((g % 5) - 2) * np.linspace(1.0, -1.0, K), 0.02, 0.98)
+    tr = p.trans.copy()
+    tr *= 1.0 + 0.1 * (g % 3)
+    np.fill_diagonal(tr, 0.0)
+    np.fill_diagonal(tr, 1.0 - tr.sum(axis=1))
+    return O.Params(p.start, tr, em, eps=p.eps).normalize()
+
+
+SHAPES = [(70, 16), (300, 170), (129, 1008), (1, 37), (257, 500), (40, 2003), (128, 64), (513, 333)]
+
+
+def _groups(K, prob, seed0):
+    out = []
+    for g, (N, L) in enumerate(SHAPES):
+        X = O.synth_reads(N, L, K, seed0 + g, prob=prob, nan_rate=0.3)
+        out.append((X, _perturbed(K, g)))
+    return out
+
+
+@pytest.mark.parametrize("K,prob", [(2, False), (3, False), (4, False), (3, True), (2, True)])
+def test_grouped_posterior_matches_oracle_per_group(K, prob):
+    gs = _groups(K, prob, 1000 + 10 * K)
+    models = [model_from_params(p) for _, p in gs]
+    obs = [S.CodedU8(_code(X)) if not prob else X.astype(np.float32) for X, _ in gs]
+    res = grouped.decode_groups(models, obs, want_loglik=True)
+    torch.cuda.synchronize()
+    for (X, p), (gam, st, ll) in zip(gs, res):
+        g_ref, ll_ref = O.posterior(X.astype(np.float64), p)
+        assert tuple(gam.shape) == g_ref.shape
+        gam_h = gam.cpu().numpy()
+        assert np.abs(gam_h - g_ref).max() <= 1e-5
+        assert_states_match_up_to_ties(st.cpu().numpy().astype(np.int64), g_ref.argmax(axis=2), g_ref)
+        np.testing.assert_allclose(ll.cpu().numpy(), ll_ref, rtol=1e-6, atol=1e-4)
+
+
+def test_grouped_posterior_single_state_column_and_states_only():
+    K = 3
+    gs = _groups(K, False, 77)
+    models = [model_from_params(p) for _, p in gs]
+    obs = [S.CodedU8(_code(X)) for X, _ in gs]
+    res1 = grouped.decode_groups(models, obs, gamma_state=1, want_states=False)
+    res2 = grouped.decode_groups(models, obs, want_gamma=False)
+    torch.cuda.synchronize()
+    for (X, p), (gam, st, _), (gam2, st2, _) in zip(gs, res1, res2):
+        g_ref, _ = O.posterior(X.astype(np.float64), p)
+        assert st is None and gam2 is None
+        assert np.abs(gam.cpu().numpy() - g_ref[:, :, 1]).max() <= 1e-5
+        assert_states_match_up_to_ties(st2.cpu().numpy().astype(np.int64), g_ref.argmax(axis=2), g_ref)
+
+
+@pytest.mark.parametrize("K,prob", [(2, False), (3, False), (4, False), (3, True)])
+def test_grouped_fit_matches_oracle_per_group(K, prob):
+    gs = _groups(K, prob, 2000 + 10 * K)
+    models = [model_from_params(p) for _, p in gs]
+    obs = [S.CodedU8(_code(X)) if not prob else X.astype(np.float32) for X, _ in gs]
+    hists, status = grouped.fit_groups(models, obs, max_iter=6, tol=0.0, return_status=True)
+    assert status == [grouped.FIT_RAN_ALL] * len(gs)
+    for (X, p), m, h in zip(gs, models, hists):
+        q, h_ref = O.fit(X.astype(np.float64), p, max_iter=6, tol=0.0)
+        np.testing.assert_allclose(h, h_ref, rtol=1e-6)
+        got = params_of_model(m)
+        assert np.abs(got.start - q.start).max() <= 1e-4
+        assert np.abs(got.trans - q.trans).max() <= 1e-4
+        assert np.abs(got.emission.reshape(-1) - q.emission.reshape(-1)).max() <= 1e-4
+
+
+def test_grouped_fit_equals_per_group_fit_and_is_deterministic():
+    K = 2
+    gs = _groups(K, False, 31)
+    obs = [S.CodedU8(_code(X)) for X, _ in gs]
+    a = [model_from_params(p) for _, p in gs]
+    b = [model_from_params(p) for _, p in gs]
+    c = [model_from_params(p) for _, p in gs]
+    ha = grouped.fit_groups(a, obs, max_iter=5, tol=0.0)
+    hb = grouped.fit_groups(b, obs, max_iter=5, tol=0.0)
+    assert ha == hb, "grouped fit is not run-to-run deterministic"
+    for ma, mb in zip(a, b):
+        for k in ("start", "trans", "emission"):
+            assert torch.equal(ma.state_dict()[k], mb.state_dict()[k])
+    for (X, _), ma, mc, h in zip(gs, a, c, ha):
+        hc = mc.fit(S.CodedU8(_code(X)), max_iter=5, tol=0.0)
+        np.testing.assert_allclose(h, hc, rtol=1e-6)  # different kernels (chunk-parallel vs sequential), fp32 recursions
+        for k in ("start", "trans", "emission"):
+            assert (ma.state_dict()[k] - mc.state_dict()[k]).abs().max().item() <= 1e-5
+
+
+def test_grouped_fit_stop_rule_is_per_group():
+    """With a loose tolerance groups stop at different iterations; each must stop exactly where the oracle stops,
+    with the parameters of that iteration (HMM.py:1616-1628), while the others keep iterating."""
+    K = 2
+    gs = _groups(K, False, 555)
+    models = [model_from_params(p) for _, p in gs]
+    obs = [S.CodedU8(_code(X)) for X, _ in gs]
+    tol = 2e-4
+    hists, status = grouped.fit_groups(models, obs, max_iter=12, tol=tol, return_status=True)
+    n_iters = set()
+    for (X, p), m, h, st in zip(gs, models, hists, status):
+        q, h_ref = O.fit(X.astype(np.float64), p, max_iter=12, tol=tol)
+        assert len(h) == len(h_ref), (len(h), len(h_ref))
+        assert st == (grouped.FIT_CONVERGED if len(h_ref) < 12 else st)
+        np.testing.assert_allclose(h, h_ref, rtol=1e-6, atol=1e-5)  # a one-read group's log-likelihood goes to ~0
+        assert np.abs(params_of_model(m).emission.reshape(-1) - q.emission.reshape(-1)).max() <= 1e-4
+        n_iters.add(len(h))
+    assert len(n_iters) > 1, "test needs groups that stop at different iterations"
+
+
+def test_grouped_fit_update_flags():
+    K = 3
+    gs = _groups(K, False, 808)[:4]
+    models = [model_from_params(p) for _, p in gs]
+    obs = [S.CodedU8(_code(X)) for X, _ in gs]
+    grouped.fit_groups(models, obs, max_iter=3, tol=0.0, update_start=False, update_trans=False)
+    for (X, p), m in zip(gs, models):
+        q, _ = O.fit(X.astype(np.float64), p, max_iter=3, tol=0.0, update_start=False, update_trans=False)
+        got = params_of_model(m)
+        assert np.abs(got.start - q.start).max() <= 1e-12
+        assert np.abs(got.trans - q.trans).max() <= 1e-12
+        assert np.abs(got.emission.reshape(-1) - q.emission.reshape(-1)).max() <= 1e-4
+
+
+def test_grouped_fit_hands_extreme_groups_back():
+    """A group whose emissions sit at the eps clamp needs a finer rescale cadence than the grouped kernels use:
+    it is reported as handed back and finished through the model's own fit -- same result as fitting it alone."""
+    K = 2
+    gs = _groups(K, False, 99)[:3]
+    p_ext = O.Params(np.array([0.5, 0.5]), np.array([[0.999999, 1e-6], [1e-6, 0.999999]]), np.array([1e-8, 1.0 - 1e-8]),
+                     eps=1e-8).normalize()
+    Xe = O.synth_reads(50, 200, K, 5, prob=False, nan_rate=0.3)
+    gs.insert(1, (Xe, p_ext))
+    models = [model_from_params(p) for _, p in gs]
+    alone = model_from_params(p_ext)
+    obs = [S.CodedU8(_code(X)) for X, _ in gs]
+    hists, status = grouped.fit_groups(models, obs, max_iter=3, tol=0.0, return_status=True)
+    assert status[1] == grouped.FIT_HANDED_BACK and status[0] == status[2] == grouped.FIT_RAN_ALL
+    h_alone = alone.fit(S.CodedU8(_code(Xe)), max_iter=3, tol=0.0)
+    np.testing.assert_allclose(hists[1], h_alone, rtol=1e-12)
+    for (X, p), m, h in zip(gs, models, hists):
+        _, h_ref = O.fit(X.astype(np.float64), p, max_iter=3, tol=0.0)
+        np.testing.assert_allclose(h, h_ref, rtol=1e-6)
+
+
+def test_grouped_accepts_padded_views_and_rejects_mixed_input():
+    K = 2
+    X = O.synth_reads(64, 100, K, 3, prob=False, nan_rate=0.3)
+    p = O.synth_params(K)
+    dev = torch.device("cuda")
+    buf = torch.full((64, 112), 255, dtype=torch.uint8, device=dev)
+    buf[:, :100] = torch.from_numpy(_code(X)).to(dev)
+    view = S.CodedU8(buf[:, :100])
+    (gam, st, _), = grouped.decode_groups([model_from_params(p)], [view])
+    g_ref, _ = O.posterior(X.astype(np.float64), p)
+    assert np.abs(gam.cpu().numpy() - g_ref).max() <= 1e-5
+    with pytest.raises(ValueError):
+        grouped.decode_groups([model_from_params(p)] * 2, [view, X.astype(np.float32)])
+    with pytest.raises(ValueError):
+        grouped.decode_groups([model_from_params(p), model_from_params(O.synth_params(3))], [view, view])
+    with pytest.raises(ValueError):
+        grouped.fit_groups([S.create_hmm({"hmm_n_states": 2}, arch="multi")], [view])
+
+
+def test_many_small_groups_one_launch():
+    """The reference's regime: hundreds of <= 1000-read fits.  256 groups, all fitted in one enqueue."""
+    K = 2
+    rng = np.random.default_rng(4)
+    gs = []
+    for g in range(256):
+        N = int(rng.integers(20, 400))
+        L = int(rng.integers(30, 400))
+        gs.append((O.synth_reads(N, L, K, 9000 + g, prob=False, nan_rate=0.3), _perturbed(K, g)))
+    models = [model_from_params(p) for _, p in gs]
+    obs = [S.CodedU8(_code(X)) for X, _ in gs]
+    hists = grouped.fit_groups(models, obs, max_iter=4, tol=0.0)
+    for g in range(0, 256, 37):
+        X, p = gs[g]
+        q, h_ref = O.fit(X.astype(np.float64), p, max_iter=4, tol=0.0)
+        np.testing.assert_allclose(hists[g], h_ref, rtol=1e-6)
+        assert np.abs(params_of_model(models[g]).emission.reshape(-1) - q.emission.reshape(-1)).max() <= 1e-4

@@ -89,7 +89,7 @@ def test_built_input_feeds_fit_and_decode_like_the_float_matrix():
     m2 = S.create_hmm({"hmm_n_states": 2, "hmm_init_emission_probs": [0.8, 0.2]}, arch="single")
     h1 = m1.fit(v, coords, max_iter=4, tol=0.0)
     h2 = m2.fit(Xf, coords, max_iter=4, tol=0.0)
-    np.testing.assert_allclose(h1, h2, rtol=1e-9)
+    np.testing.assert_allclose(h1, h2, rtol=1e-6)  # uint8 and float64 inputs run different instantiations
     s1, g1 = m1.decode(v, coords)
     s2, g2 = m2.decode(Xf, coords)
     assert np.abs(g1 - g2).max() <= 2e-6

@@ -76,3 +76,35 @@ def test_seq_path_is_the_policy_for_the_configs3_shape():
     finally:
         engine.set_option("seq", -1)
     assert np.all(np.abs(st0 - st) / scale <= 4e-6)
+
+
+@pytest.mark.parametrize("K,L,N,prob", [(3, 1008, 129, False), (4, 2000, 257, False), (2, 512, 300, False), (3, 500, 200, True),
+                                        (4, 1204, 131, True), (4, 16, 1000, False), (3, 8000, 40, True)])
+def test_seq_posterior_matches_oracle(K, L, N, prob, force_seq):
+    """Posterior decode on the sequential kernels (seq_backward_kernel<MODE_POST>: posteriors staged in shared
+    memory, written as whole sectors) for every output combination of smf_hmm_posterior."""
+    from helpers import assert_states_match_up_to_ties
+    from smftools_b200 import engine
+
+    dev = torch.device("cuda")
+    p = O.synth_params(K)
+    tables = model_from_params(p)._host_tables()
+    X32 = O.synth_reads(N, L, K, 700 + K + L % 97, prob=prob, nan_rate=0.3)
+    g_ref, ll_ref = O.posterior(X32.astype(np.float64), p)
+    variants = [torch.from_numpy(X32.astype(np.float32)).to(dev)]
+    if not prob and L % 16 == 0:
+        variants.append(torch.from_numpy(_code(X32)).to(dev))
+    for obs in variants:
+        gam, st, ll = engine.posterior(tables, obs, want_loglik=True)
+        assert np.abs(gam.cpu().numpy() - g_ref).max() <= 1e-5
+        assert_states_match_up_to_ties(st.cpu().numpy().astype(np.int64), g_ref.argmax(axis=2), g_ref)
+        np.testing.assert_allclose(ll.cpu().numpy(), ll_ref, rtol=1e-6, atol=1e-4)
+        g1, s1, _ = engine.posterior(tables, obs, gamma_state=K - 1, want_states=False)
+        assert s1 is None and np.abs(g1.cpu().numpy() - g_ref[:, :, K - 1]).max() <= 1e-5
+        g2, s2, _ = engine.posterior(tables, obs, want_gamma=False)
+        assert g2 is None and torch.equal(s2, st)
+        # the same batch on the chunk-parallel kernels
+        engine.set_option("seq", 0)
+        gam0, st0, _ = engine.posterior(tables, obs)
+        engine.set_option("seq", 1)
+        assert (gam0 - gam).abs().max().item() <= 4e-6

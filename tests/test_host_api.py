@@ -211,13 +211,21 @@ def test_tuning_options_and_workspace_policy():
         assert lib.smf_hmm_workspace_bytes(_lib.OP_ESTEP, t4.ref, 100_000, 500) == partials + need
         assert lib.smf_hmm_workspace_bytes(_lib.OP_ESTEP, t4.ref, 100, 500) == partials
         assert lib.smf_hmm_set_option(b"walk", 0) == _lib.SMF_OK
+        # without the two-kernel path a large K = 4 batch still asks for the checkpoints of the sequential kernels:
+        # ceil(500 / 16) chunks x N x 4 floats + N doubles (+ 64 bytes of alignment slack)
+        seq_need = 32 * 100_000 * 16 + 100_000 * 8 + 64
+        assert lib.smf_hmm_workspace_bytes(_lib.OP_POSTERIOR, t4.ref, 100_000, 500) == seq_need
+        assert lib.smf_hmm_workspace_bytes(_lib.OP_ESTEP, t4.ref, 100_000, 500) == partials + seq_need
+        assert lib.smf_hmm_set_option(b"seq", 0) == _lib.SMF_OK
         assert lib.smf_hmm_workspace_bytes(_lib.OP_POSTERIOR, t4.ref, 100_000, 500) == 0
         assert lib.smf_hmm_workspace_bytes(_lib.OP_ESTEP, t4.ref, 100_000, 500) == partials
+        assert lib.smf_hmm_set_option(b"seq", -1) == _lib.SMF_OK
         assert lib.smf_hmm_set_option(b"walk", 1) == _lib.SMF_OK
         assert lib.smf_hmm_workspace_bytes(_lib.OP_POSTERIOR, t4.ref, 100, 500) > 0
     finally:
         assert lib.smf_hmm_set_option(b"walk", -1) == _lib.SMF_OK
         assert lib.smf_hmm_set_option(b"short", -1) == _lib.SMF_OK
+        assert lib.smf_hmm_set_option(b"seq", -1) == _lib.SMF_OK
 
 
 def test_log_tables_are_the_reference_expressions():

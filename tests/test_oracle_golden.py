@@ -5,7 +5,7 @@ import pytest
 from conftest import golden_names, load_golden, params_from_golden
 from oracle import hmm_oracle as O
 
-CORE = [n for n in golden_names() if not n.startswith("annotate")]
+CORE = [n for n in golden_names() if not n.startswith(("annotate", "inputs_", "reduce_"))]
 ANNOT = golden_names("annotate")
 
 
