@@ -95,6 +95,10 @@ const char* smf_hmm_strerror(int code);
  *            rows of a multiple of 16 positions, or float rows of a multiple of 4) runs on the
  *            one-thread-per-read kernels (checkpointed forward pass + one backward pass); 0 never /
  *            1 whenever the batch is eligible.  smf_hmm_workspace_bytes() follows the setting.
+ *   "vit"    -1 (default) Viterbi decode of single-channel, homogeneous-transition models with float / uint8-coded
+ *            rows of a multiple of 4 (uint8: 16) positions runs on the direct kernel (no shared-memory staging) where
+ *            it measured faster: uint8 code, K = 2, K = 4, and K = 3 up to 2,048 positions; 0 never / 1 wherever it
+ *            applies.  Both kernels make bit-identical decisions.
  * Returns SMF_ERR_BAD_ARG for an unknown key or value.
  */
 int smf_hmm_set_option(const char* key, int value);

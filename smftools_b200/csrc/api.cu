@@ -472,6 +472,8 @@ static int launch_walk_path(bool stats, const smf_hmm_tables* t, int obs_dtype, 
 // sequential E-step (seq_kernel.cuh): one thread per read, three recursions per position
 // ---------------------------------------------------------------------------------------
 // -1 = measured policy, 0 = never, 1 = whenever the batch is eligible.  SMF_SEQ / smf_hmm_set_option("seq", v).
+// Viterbi: -1 = measured policy, 1 = direct kernel wherever it applies, 0 = staged kernel only.  SMF_VIT / smf_hmm_set_option("vit", v).
+static std::atomic<int> g_vit_mode{[] { const char* e = getenv("SMF_VIT"); return e ? atoi(e) : -1; }()};
 static std::atomic<int> g_seq_mode{[] { const char* e = getenv("SMF_SEQ"); return e ? atoi(e) : -1; }()};
 // Reads per launch from which the reads alone fill the machine (148 SMs x 4-5 CTAs x 128 threads); measured
 // break-even against the chunk-parallel kernels in profiles/r02_seq_estep.txt.
@@ -736,6 +738,11 @@ int smf_hmm_set_option(const char* key, int value) {
   if (strcmp(key, "short") == 0) {
     if (value < -1 || value > 1) return SMF_ERR_BAD_ARG;
     g_short_mode = value;
+    return SMF_OK;
+  }
+  if (strcmp(key, "vit") == 0) {
+    if (value < -1 || value > 1) return SMF_ERR_BAD_ARG;
+    g_vit_mode = value;
     return SMF_OK;
   }
   if (strcmp(key, "seq") == 0) {
@@ -1146,6 +1153,25 @@ int smf_hmm_viterbi(const smf_hmm_tables* tab, const void* obs, int obs_dtype, i
   a.states = states;
   a.bp = reinterpret_cast<uint8_t*>(workspace);
   cudaStream_t st = (cudaStream_t)stream;
+  // single channel, homogeneous transitions, float / coded rows of whole 4-position words: the direct kernel
+  // (no shared-memory staging); "vit" = 0 keeps the staged kernel, which handles every other case
+  const bool rows_ok = (n_pos & 3) == 0 && (reinterpret_cast<uintptr_t>(obs) & 15u) == 0 &&
+                       (reinterpret_cast<uintptr_t>(states) & 3u) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 3u) == 0 &&
+                       (obs_dtype == SMF_OBS_F32 || (obs_dtype == SMF_OBS_U8 && (n_pos & 15) == 0 &&
+                                                     (reinterpret_cast<uintptr_t>(states) & 15u) == 0 &&
+                                                     (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0));
+  // measured (profiles/r02_viterbi.txt): 2-2.8x faster for the uint8 code, 1.4x for K = 4, on par for K = 2 and for
+  // short K = 3 reads; long float K = 3 reads stay on the staged kernel (9.1 vs 9.8 ms on 262,144 x 10 kb: both are
+  // bound by the fp64 pipe there, and the staged kernel's 128-byte row segments are kinder to DRAM)
+  const bool direct_wins = obs_dtype == SMF_OBS_U8 || tab->n_states != 3 || n_pos <= 2048;
+  if (g_vit_mode != 0 && (g_vit_mode == 1 || direct_wins) && tab->n_channels == 1 && tab->n_bins == 1 && rows_ok &&
+      !g_force_generic) {
+    switch (tab->n_states) {
+      case 2: return launch_vit_direct_k2(tab, a, di, st);
+      case 3: return launch_vit_direct_k3(tab, a, di, st);
+      case 4: return launch_vit_direct_k4(tab, a, di, st);
+    }
+  }
   switch (tab->n_states) {
     case 2: return launch_vit_k2(tab, a, di, st);
     case 3: return launch_vit_k3(tab, a, di, st);

@@ -119,7 +119,8 @@ static void build_vit_tables(const smf_hmm_tables* t, VitTables<K>* out) {
                        Fb2Args& a, const Fb2Plan& plan, const DeviceInfo& di, int* nblocks, cudaStream_t s);  \
   int launch_fb_k##KV(bool stats, const smf_hmm_tables* t, FbArgs& a, const FbPlan& plan, const DeviceInfo& di, \
                       int* nblocks, cudaStream_t s);                                                           \
-  int launch_vit_k##KV(const smf_hmm_tables* t, const VitArgs& a, const DeviceInfo& di, cudaStream_t s);
+  int launch_vit_k##KV(const smf_hmm_tables* t, const VitArgs& a, const DeviceInfo& di, cudaStream_t s);       \
+  int launch_vit_direct_k##KV(const smf_hmm_tables* t, const VitArgs& a, const DeviceInfo& di, cudaStream_t s);
 SMF_DECLARE_K(2)
 SMF_DECLARE_K(3)
 SMF_DECLARE_K(4)

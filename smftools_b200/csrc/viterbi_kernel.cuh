@@ -266,4 +266,199 @@ __global__ void __launch_bounds__(kVitReads, 4) viterbi_kernel(const __grid_cons
   }
 }
 
+// -----------------------------------------------------------------------------------------------------
+// viterbi_direct_kernel: single channel, homogeneous transitions, rows of a multiple of 4 positions.
+//
+// Same arithmetic as viterbi_kernel (fp64, the reference's operation order, first-index ties: bit-identical
+// decisions), different data movement: NOTHING is staged.  A thread reads its own read 16 positions at a time
+// straight from global memory (4 x LDG.128 of floats / one LDG.128 of the uint8 code, the next 16 positions in
+// flight while the current ones are decoded: every sector fetched is used whole), keeps the 16 packed
+// back-pointer bytes of the chunk in four registers and writes them with one 16-byte store (four 4-byte stores
+// when the rows are not 16-byte aligned); the back-trace streams them back the same way, one chunk ahead, and
+// writes 16 states per store.  No shared memory, no barrier, no transposition: ~25 of viterbi_kernel's 93
+// thread-instructions per position were tile traffic (profiles/r01_c3v_viterbi_ncu.txt).
+// -----------------------------------------------------------------------------------------------------
+constexpr int kVitCH = 16;
+
+template <int OBSK>
+struct VitChunk;
+template <>
+struct VitChunk<SMF_OBS_F32> {
+  float4 q[4];
+  __device__ __forceinline__ void load(const void* row, int t0, int len) {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(row) + t0);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) q[g] = (4 * g < len) ? __ldg(p + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __device__ __forceinline__ double value(int j) const {
+    const float4 v = q[j >> 2];
+    return (double)((j & 3) == 0 ? v.x : ((j & 3) == 1 ? v.y : ((j & 3) == 2 ? v.z : v.w)));
+  }
+};
+template <>
+struct VitChunk<SMF_OBS_U8> {
+  uint4 w;
+  __device__ __forceinline__ void load(const void* row, int t0, int len) {
+    const unsigned char* p = reinterpret_cast<const unsigned char*>(row) + t0;
+    if (len == kVitCH) {
+      w = __ldg(reinterpret_cast<const uint4*>(p));  // rows are 16-byte aligned in this variant (L % 16 == 0)
+    } else {
+      unsigned v[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        if (4 * g < len) v[g] = __ldg(reinterpret_cast<const unsigned*>(p) + g);
+      w = make_uint4(v[0], v[1], v[2], v[3]);
+    }
+  }
+  __device__ __forceinline__ unsigned code(int j) const {
+    const unsigned word = (j >> 2) == 0 ? w.x : ((j >> 2) == 1 ? w.y : ((j >> 2) == 2 ? w.z : w.w));
+    return (word >> (8 * (j & 3))) & 0xffu;
+  }
+};
+
+template <bool A16>
+__device__ __forceinline__ void vit_store16(uint8_t* p, const unsigned (&v)[4], int len) {
+  if (A16 && len == kVitCH) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(v[0], v[1], v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (4 * g < len) *reinterpret_cast<unsigned*>(p + 4 * g) = v[g];
+  }
+}
+template <bool A16>
+__device__ __forceinline__ void vit_load16(const uint8_t* p, unsigned (&v)[4], int len) {
+  if (A16 && len == kVitCH) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    v[0] = t.x;
+    v[1] = t.y;
+    v[2] = t.z;
+    v[3] = t.w;
+  } else {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) v[g] = (4 * g < len) ? *reinterpret_cast<const unsigned*>(p + 4 * g) : 0u;
+  }
+}
+
+// A16: every row of obs (uint8) / bp / states starts on a 16-byte boundary (L % 16 == 0)
+template <int K, int OBSK, bool A16>
+__global__ void __launch_bounds__(128) viterbi_direct_kernel(const __grid_constant__ VitTables<K> tab,
+                                                             const __grid_constant__ VitArgs a) {
+  const int L = a.L;
+  const int nch = (L + kVitCH - 1) / kVitCH;
+  // transition / emission tables in registers (constant-bank reads inside the unrolled steps otherwise)
+  double lA[K][K], l1[K], l0[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    l1[i] = tab.l1[i][0];
+    l0[i] = tab.l0[i][0];
+#pragma unroll
+    for (int j = 0; j < K; ++j) lA[i][j] = tab.logA[0][i][j];
+  }
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < a.N; n += (long long)gridDim.x * blockDim.x) {
+    const void* row = (OBSK == SMF_OBS_U8) ? (const void*)(reinterpret_cast<const unsigned char*>(a.obs) + n * (long long)L)
+                                           : (const void*)(reinterpret_cast<const float*>(a.obs) + n * (long long)L);
+    uint8_t* bprow = a.bp + n * (long long)L;
+    uint8_t* strow = reinterpret_cast<uint8_t*>(a.states) + n * (long long)L;
+    double delta[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) delta[k] = 0.0;
+    VitChunk<OBSK> cur, nxt;
+    cur.load(row, 0, min(kVitCH, L));
+    // ---------------- forward max-plus sweep ----------------
+    for (int c = 0; c < nch; ++c) {
+      const int t0 = c * kVitCH;
+      const int len = min(kVitCH, L - t0);
+      if (c + 1 < nch) nxt.load(row, t0 + kVitCH, min(kVitCH, L - t0 - kVitCH));
+      unsigned bpw[4] = {0u, 0u, 0u, 0u};
+      auto step = [&](int j, bool maybe_first) {
+        double logB[K];
+        if constexpr (OBSK == SMF_OBS_U8) {
+          const unsigned code = cur.code(j);
+#pragma unroll
+          for (int k = 0; k < K; ++k) logB[k] = code < 2u ? (code != 0u ? l1[k] : l0[k]) : 0.0;
+        } else {
+          // branch-free; exact for o in {0, 1}; a missing site adds a (signed) zero: see viterbi_kernel
+          const double o = cur.value(j);
+          const bool m = (o == o);
+          const double os = m ? o : 0.0;
+          const double om = m ? __dsub_rn(1.0, os) : 0.0;
+#pragma unroll
+          for (int k = 0; k < K; ++k) logB[k] = __dadd_rn(__dmul_rn(os, l1[k]), __dmul_rn(om, l0[k]));
+        }
+        unsigned packed = 0;
+        if (maybe_first && t0 + j == 0) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) delta[k] = __dadd_rn(tab.log_pi[k], logB[k]);
+        } else {
+          double nd[K];
+#pragma unroll
+          for (int jn = 0; jn < K; ++jn) {
+            double best = __dadd_rn(delta[0], lA[0][jn]);
+            unsigned arg = 0;
+#pragma unroll
+            for (int i = 1; i < K; ++i) {
+              const double cnd = __dadd_rn(delta[i], lA[i][jn]);
+              if (cnd > best) {
+                best = cnd;
+                arg = i;
+              }
+            }
+            nd[jn] = __dadd_rn(best, logB[jn]);
+            packed |= arg << (2 * jn);
+          }
+#pragma unroll
+          for (int k = 0; k < K; ++k) delta[k] = nd[k];
+        }
+        bpw[j >> 2] |= packed << (8 * (j & 3));
+      };
+      if (c > 0 && len == kVitCH) {
+#pragma unroll
+        for (int j = 0; j < kVitCH; ++j) step(j, false);
+      } else {
+#pragma unroll
+        for (int j = 0; j < kVitCH; ++j)
+          if (j < len) step(j, true);
+      }
+      vit_store16<A16>(bprow + t0, bpw, len);
+      cur = nxt;
+    }
+    // last state: first maximum of delta[L-1] (torch.argmax, HMM.py:664)
+    unsigned s = 0;
+    {
+      double best = delta[0];
+#pragma unroll
+      for (int k = 1; k < K; ++k)
+        if (delta[k] > best) {
+          best = delta[k];
+          s = k;
+        }
+    }
+    // ---------------- back-trace, chunks in reverse (this thread re-reads its own stores) ----------------
+    unsigned bw[4], bn[4];
+    {
+      const int t0 = (nch - 1) * kVitCH;
+      vit_load16<A16>(bprow + t0, bw, L - t0);
+    }
+    for (int c = nch - 1; c >= 0; --c) {
+      const int t0 = c * kVitCH;
+      const int len = min(kVitCH, L - t0);
+      if (c > 0) vit_load16<A16>(bprow + t0 - kVitCH, bn, kVitCH);
+      unsigned sw[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int j = kVitCH - 1; j >= 0; --j) {
+        if (j < len) {
+          const unsigned packed = (bw[j >> 2] >> (8 * (j & 3))) & 0xffu;
+          sw[j >> 2] |= s << (8 * (j & 3));       // state at position t0 + j
+          if (t0 + j > 0) s = (packed >> (2 * s)) & 3u;  // s[t-1] = psi[t, s[t]]
+        }
+      }
+      vit_store16<A16>(strow + t0, sw, len);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) bw[g] = bn[g];
+    }
+  }
+}
+
+
 }  // namespace smf
