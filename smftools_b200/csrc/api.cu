@@ -1573,6 +1573,8 @@ int smf_hmm_grouped_fit(int n_states, int obs_dtype, const smf_hmm_group* groups
   f.n_iter = n_iter;
   f.status = status;
   f.tabs = ws + pl.off_tabs;
+  f.groups = reinterpret_cast<const SeqGroup*>(ws + pl.off_groups);
+  f.partials = reinterpret_cast<const double*>(ws + pl.off_partials);
   f.n_groups = n_groups;
   f.S = pl.S;
   f.max_iter = max_iter > 0 ? max_iter : 1;
@@ -1602,8 +1604,6 @@ int smf_hmm_grouped_fit(int n_states, int obs_dtype, const smf_hmm_group* groups
                 : (K == 3 ? launch_seq_grouped_k3(obs_dtype, MODE_STATS, a, di, st)
                           : launch_seq_grouped_k4(obs_dtype, MODE_STATS, a, di, st));
     if (rc != SMF_OK) return rc;
-    seq_reduce_groups_kernel<<<n_groups * pl.S, 256, 0, st>>>(a.partials, a.groups, pl.S, f.stats);
-    if (cudaGetLastError() != cudaSuccess) return SMF_ERR_CUDA;
     rc = mstep(it);
     if (rc != SMF_OK) return rc;
   }

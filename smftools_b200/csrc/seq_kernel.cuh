@@ -827,6 +827,8 @@ struct SeqFitState {
   int* n_iter;      // [G] iterations done
   int* status;      // [G] SMF_FIT_* (0 ran all iterations, 1 converged, 2 handed back to the caller)
   void* tabs;       // [G] FbTables<K>
+  const SeqGroup* groups;   // [G] device group table
+  const double* partials;   // [n_items][S] per-item statistics of the E-step
   int n_groups, S, max_iter, iter;  // iter < 0: build the tables of the initial parameters only
   double eps, tol;
   int update_start, update_trans, update_emission;
@@ -834,11 +836,31 @@ struct SeqFitState {
 
 // M-step + convergence test + table rebuild of every active group (one thread per group): the closed forms
 // and the unconditional re-normalisation of HMM.py:1598-1614, the stop rule of :1616-1628.
+// Launched with one CTA of 256 threads per group: the CTA first reduces the group's per-item partial statistics
+// in a fixed order (threads sum strided subsets, then a fixed-shape tree: deterministic), then thread 0 updates.
 template <int K>
-__global__ void seq_mstep_kernel(const __grid_constant__ SeqFitState f) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= f.n_groups) return;
+__global__ void __launch_bounds__(256) seq_mstep_kernel(const __grid_constant__ SeqFitState f) {
+  const int g = blockIdx.x;
   constexpr int KK = K * K;
+  if (f.iter >= 0) {
+    if (f.active[g] == 0) return;  // uniform across the CTA
+    __shared__ double red[256];
+    const SeqGroup grp = f.groups[g];
+    const long long n_items = (grp.N + kSeqThreads - 1) / kSeqThreads;
+    for (int sidx = 0; sidx < f.S; ++sidx) {
+      double tot = 0.0;
+      for (long long i = threadIdx.x; i < n_items; i += 256) tot += f.partials[(size_t)(grp.item0 + i) * f.S + sidx];
+      red[threadIdx.x] = tot;
+      __syncthreads();
+      for (int d = 128; d > 0; d >>= 1) {
+        if (threadIdx.x < d) red[threadIdx.x] += red[threadIdx.x + d];
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) f.stats[(size_t)g * f.S + sidx] = red[0];
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x != 0) return;
   double* p = f.params + (size_t)g * (K + KK + K);
   double* start = p;
   double* trans = p + K;
@@ -926,26 +948,6 @@ __global__ void seq_mstep_kernel(const __grid_constant__ SeqFitState f) {
   memset(&tab, 0, sizeof(tab));
   seq_tables_from_logs<K>(ls, lt, l1, l0, &tab);
   reinterpret_cast<FbTables<K>*>(f.tabs)[g] = tab;
-}
-
-// Fixed-order reduction of the per-item partial statistics of every group (grouped launches):
-// one CTA per (group, statistic); threads sum strided subsets, then a fixed-shape tree.
-static __global__ void __launch_bounds__(256) seq_reduce_groups_kernel(const double* __restrict__ partials,
-                                                                const SeqGroup* __restrict__ groups, int S,
-                                                                double* __restrict__ stats /*[G][S]*/) {
-  __shared__ double red[256];
-  const int gidx = blockIdx.x / S, s = blockIdx.x % S;
-  const SeqGroup g = groups[gidx];
-  const long long n_items = (g.N + kSeqThreads - 1) / kSeqThreads;
-  double tot = 0.0;
-  for (long long i = threadIdx.x; i < n_items; i += 256) tot += partials[(size_t)(g.item0 + i) * S + s];
-  red[threadIdx.x] = tot;
-  __syncthreads();
-  for (int d = 128; d > 0; d >>= 1) {
-    if (threadIdx.x < d) red[threadIdx.x] += red[threadIdx.x + d];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) stats[(size_t)gidx * S + s] = red[0];
 }
 
 }  // namespace smf

@@ -215,8 +215,12 @@ def fit_groups(models, obs_list, *, max_iter: int = 50, tol: float = 1e-5, updat
             from .hmm import CodedU8
 
             X = CodedU8(t) if t.dtype == torch.uint8 else t
-            out.append(m.fit(X, max_iter=max_iter, tol=tol, device=device, update_start=update_start,
-                             update_trans=update_trans, update_emission=update_emission))
+            m._host_loop_only = True  # the general path: host M-step, kernels with a finer rescale cadence
+            try:
+                out.append(m.fit(X, max_iter=max_iter, tol=tol, device=device, update_start=update_start,
+                                 update_trans=update_trans, update_emission=update_emission))
+            finally:
+                m._host_loop_only = False
         else:
             out.append([float(v) for v in hist_h[g, :int(n_h[g])]])
     if return_status:

@@ -668,6 +668,13 @@ class BaseHMM(nn.Module):
         self._check_fit_input(src)
         device = self._ensure_device_dtype(device)
         N, L = int(src.shape[0]), int(src.shape[1])
+        if self._device_loop_eligible(N, L, int(max_iter), verbose):
+            # small fit (the reference's regime: hmm_max_fit_reads = 1000): the whole Baum-Welch loop -- E-step,
+            # M-step, stop rule -- runs on the device without a host round trip per iteration (grouped.py, one group)
+            from .grouped import fit_groups
+
+            return fit_groups([self], [X], max_iter=int(max_iter), tol=float(tol), update_start=update_start,
+                              update_trans=update_trans, update_emission=update_emission, device=device)[0]
         self._prepare_fit(src, device)
         bins = self._bins_for(np.asarray(coords, dtype=int), L, device)
         resident = self._resident_chunks(src, device, numeric_u8)
@@ -707,6 +714,17 @@ class BaseHMM(nn.Module):
                 prof.append({"estep_ms": ev[0].elapsed_time(ev[1]), "allreduce_ms": ev[1].elapsed_time(ev[2]),
                              "host_mstep_ms": 1e3 * host_s})
         return hist
+
+    # read-positions up to which ``fit`` keeps the EM loop on the device (beyond, one E-step takes long enough that
+    # the ~0.25 ms host M-step per iteration does not matter and the chunk-parallel kernels are the faster E-step)
+    device_loop_max_positions = 4_000_000
+    # ... and the longest read: the device loop walks a read sequentially (one thread per read, ~80 ns per position
+    # and iteration), which only beats the ~0.2 ms host round trip for amplicon-sized reads
+    device_loop_max_length = 1024
+
+    def _device_loop_eligible(self, N: int, L: int, max_iter: int, verbose: bool) -> bool:
+        """Only the plain single-channel model has the device-side M-step (``SingleBernoulliHMM`` overrides)."""
+        return False
 
     def _estep_local(self, tables, resident, bins, workspace, device) -> torch.Tensor:
         """This rank's sufficient statistics [start | trans | emit_num | emit_den | ll] (fp64, on
@@ -1375,6 +1393,11 @@ class SingleBernoulliHMM(BaseHMM):
 
     def _expected_ndim(self):
         return 2
+
+    def _device_loop_eligible(self, N: int, L: int, max_iter: int, verbose: bool) -> bool:
+        return (type(self) is SingleBernoulliHMM and not verbose and max_iter >= 1 and N >= 1 and L >= 1
+                and N * L <= self.device_loop_max_positions and L <= self.device_loop_max_length and not self.distributed and self.process_group is None
+                and getattr(self, "fit_profile", None) is None and not getattr(self, "_host_loop_only", False))
 
     def _assign_emission(self, em: torch.Tensor):
         self.emission.data = em.reshape(-1).to(self.emission.device)
