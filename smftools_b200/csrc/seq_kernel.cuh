@@ -398,11 +398,19 @@ struct SeqCopyPlan {
   }
 };
 
+// resident CTAs per SM the backward kernel is compiled for (register cap = 65536 / (128 * blocks))
+constexpr int seq_bwd_min_blocks(int K, size_t obs_size, int mode) {
+  // posterior decode of float rows, K <= 3: one CTA fewer (128 registers), so that the chunk-ahead observation
+  // loads stay in registers (K = 3, 100,000 x 5 kb: 4.27 -> 3.37 ms); K = 4 measured mixed with 3 CTAs and keeps 4
+  if (mode == 1 && obs_size > 1 && K < 4) return 4;
+  return K == 4 ? 4 : 5;
+}
+
 // -----------------------------------------------------------------------------------------------------
 // backward: alpha recomputed per chunk, one beta recursion; statistics (MODE_STATS) or posteriors (MODE_POST)
 // -----------------------------------------------------------------------------------------------------
 template <int K, typename ObsT, bool GROUPED, int MODE>
-__global__ void __launch_bounds__(kSeqThreads, (K == 4 ? 4 : 5)) seq_backward_kernel(const __grid_constant__ FbTables<K> tab0,
+__global__ void __launch_bounds__(kSeqThreads, seq_bwd_min_blocks(K, sizeof(ObsT), MODE)) seq_backward_kernel(const __grid_constant__ FbTables<K> tab0,
                                                                                       const __grid_constant__ SeqArgs a) {
   constexpr int KP = SeqVec<K>::KP;
   constexpr int KK = K * K;
@@ -539,6 +547,11 @@ __global__ void __launch_bounds__(kSeqThreads, (K == 4 ? 4 : 5)) seq_backward_ke
       const int len = min(kSeqCH, L - t0);
       const bool first = (c == 0);
       float v[K];
+      if (sizeof(ObsT) > 1 && c >= 2) {
+        // float rows: the register prefetch below holds 16 registers per chunk, which ptxas trades away under the
+        // register cap (the loads then sit right before their use); an L2 prefetch two chunks ahead costs none
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(row + t0 - 2 * kSeqCH));
+      }
       if (!first) {
         prv.load(row + t0 - kSeqCH, kSeqCH);
 #pragma unroll
