@@ -515,6 +515,14 @@ static size_t seq_ws_bytes(int K, int64_t N, int64_t L) {
 
 static inline int obs_elem_size(int dt) { return dt == SMF_OBS_F32 ? 4 : (dt == SMF_OBS_F64 ? 8 : 1); }
 
+// multi-channel models on the fast-path kernel (fb2_kernel<..., C>): K <= 3, C = 2 or 3, float / uint8-coded rows.
+// SMF_FB2_MULTI=0 keeps them on the generic kernel.
+static bool fb2_multi_eligible(const smf_hmm_tables* t, int obs_dtype) {
+  static const int env = [] { const char* e = getenv("SMF_FB2_MULTI"); return e ? atoi(e) : 1; }();
+  return env != 0 && t->n_bins == 1 && t->n_states <= 3 && (t->n_channels == 2 || t->n_channels == 3) &&
+         (obs_dtype == SMF_OBS_F32 || obs_dtype == SMF_OBS_U8);
+}
+
 // ---------------------------------------------------------------------------------------
 // short reads (short_kernel): several reads per warp
 // ---------------------------------------------------------------------------------------
@@ -948,6 +956,28 @@ int smf_hmm_posterior(const smf_hmm_tables* tab, const void* obs, int obs_dtype,
       return launch_fb2(false, tab, obs_dtype, b, p2, di, nullptr, (cudaStream_t)stream);
     }
   }
+  if (fb2_multi_eligible(tab, obs_dtype) && !g_force_generic && cadence == 4 &&
+      fb2_aligned(obs, obs_dtype, gamma, tab->n_states, gamma_state)) {
+    Fb2Args b;
+    memset(&b, 0, sizeof(b));
+    Fb2Plan p2;
+    if (plan_fb2_chunk(tab->n_states, 17, n_pos, false, stats_len(tab), obs_elem_size(obs_dtype) * tab->n_channels,
+                       gamma != nullptr && gamma_state >= 0, states != nullptr, di.max_smem_optin, &b, &p2) == SMF_OK) {
+      b.obs = obs;
+      b.N = n_reads;
+      b.L = (int)n_pos;
+      b.gamma = gamma;
+      b.gamma_state = gamma_state;
+      b.states = states;
+      b.loglik = loglik;
+      b.partials = nullptr;
+      b.S = stats_len(tab);
+      b.flush_every = 1;
+      return tab->n_states == 2
+                 ? launch_fb2m_k2(tab->n_channels, false, obs_dtype, tab, b, p2, di, nullptr, (cudaStream_t)stream)
+                 : launch_fb2m_k3(tab->n_channels, false, obs_dtype, tab, b, p2, di, nullptr, (cudaStream_t)stream);
+    }
+  }
   FbArgs a;
   memset(&a, 0, sizeof(a));
   FbPlan plan;
@@ -1097,6 +1127,29 @@ int smf_hmm_estep(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int
       b.flush_every = 8;
       int nb2 = kMaxEstepBlocks;
       rc = launch_fb2(true, tab, obs_dtype, b, p2, di, &nb2, st);
+      if (rc != SMF_OK) return rc;
+      reduce_partials_kernel<<<(S + 127) / 128, 128, 0, st>>>(b.partials, nb2, S, stats);
+      return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
+    }
+  }
+  if (fb2_multi_eligible(tab, obs_dtype) && !g_force_generic && cadence == 4 &&
+      fb2_aligned(obs, obs_dtype, nullptr, tab->n_states, -1)) {
+    Fb2Args b;
+    memset(&b, 0, sizeof(b));
+    Fb2Plan p2;
+    if (plan_fb2_chunk(tab->n_states, 17, n_pos, true, S, obs_elem_size(obs_dtype) * tab->n_channels, false, false,
+                       di.max_smem_optin, &b, &p2) == SMF_OK) {
+      b.obs = obs;
+      b.N = n_reads;
+      b.L = (int)n_pos;
+      b.gamma_state = -1;
+      b.partials = reinterpret_cast<double*>(workspace);
+      b.S = S;
+      b.flush_every = 8;
+      b.late_load = 1;  // the backward sweep re-reads the observations for the per-channel emission statistics
+      int nb2 = kMaxEstepBlocks;
+      rc = tab->n_states == 2 ? launch_fb2m_k2(tab->n_channels, true, obs_dtype, tab, b, p2, di, &nb2, st)
+                              : launch_fb2m_k3(tab->n_channels, true, obs_dtype, tab, b, p2, di, &nb2, st);
       if (rc != SMF_OK) return rc;
       reduce_partials_kernel<<<(S + 127) / 128, 128, 0, st>>>(b.partials, nb2, S, stats);
       return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;

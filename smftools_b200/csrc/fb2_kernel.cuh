@@ -47,6 +47,8 @@ struct Fb2Args {
   const double* ll_in;
   int Tact;  // chunks per read
   int gc;    // 1: staging tile sized for the compact (OUT == 3) layout
+  int late_load;  // 1: the next read is requested at the end of the iteration (multi-channel E-step: the backward
+                  //    sweep re-reads the observations from shared memory for the per-channel emission statistics)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -136,7 +138,12 @@ __device__ __forceinline__ void store_row_bulk(void* dst, const void* src, uint3
 //
 // WALK = true: the chunk boundary vectors come from walk_kernel (walk_kernel.cuh) instead of the
 // chunk-product + scan phases; the kernel is then just the load / local sweeps / store pipeline.
-template <int K, int CH, bool STATS, typename ObsT, int MAXT, int MINB, int OUT, bool WALK = false>
+//
+// C > 1: multi-channel observations [N, L, C] (MultiBernoulliHMM, HMM.py:1766-1782): the emission ratio of a
+// position is the product over its observed channels, computed once in phase 1 like the single-channel ratio --
+// everything after that (chunk products, scans, sweeps, stores) is unchanged.  The E-step keeps K x C emission
+// accumulators and re-reads the observations from shared memory in the backward sweep (late_load).
+template <int K, int CH, bool STATS, typename ObsT, int MAXT, int MINB, int OUT, bool WALK = false, int C = 1>
 __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__ FbTables<K> tab,
                                                    const __grid_constant__ Fb2Args a) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -146,6 +153,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
   // K = 4 would need 3*CH registers for the cached ratios: keep the observation instead and
   // recompute the ratios (3 ex2 per position and phase; the kernel is FMA-bound there anyway)
   constexpr bool RECOMP = (K >= 4);
+  static_assert(C == 1 || (!WALK && OUT == 2 && K <= 3), "multi-channel variant: K <= 3, run-time output set, single kernel");
 
   const int tid = threadIdx.x;
   const int T = a.T;
@@ -180,15 +188,17 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
 
   constexpr int NXI = STATS ? KK : 1;
   constexpr int NEM = STATS ? K : 1;
-  float acc_xi[NXI], acc_num[NEM], acc_den[NEM], acc_start[NEM];
+  constexpr int NEC = STATS ? K * C : 1;  // emission accumulators: [state][channel]
+  float acc_xi[NXI], acc_num[NEC], acc_den[NEC], acc_start[NEM];
   double acc_ll = 0.0;
 #pragma unroll
   for (int i = 0; i < NXI; ++i) acc_xi[i] = 0.0f;
 #pragma unroll
-  for (int i = 0; i < NEM; ++i) {
+  for (int i = 0; i < NEM; ++i) acc_start[i] = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NEC; ++i) {
     acc_num[i] = 0.0f;
     acc_den[i] = 0.0f;
-    acc_start[i] = 0.0f;
   }
 
   auto flush_stats = [&]() {
@@ -197,16 +207,19 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
 #pragma unroll
     for (int k = 0; k < NEM; ++k) {
       const float r0 = warp_sum_f32(acc_start[k]);
-      const float r1 = warp_sum_f32(acc_num[k]);
-      const float r2 = warp_sum_f32(acc_den[k]);
-      if (lane == 0) {
-        my[k] += (double)r0;
-        my[K + KK + k] += (double)r1;
-        my[K + KK + K + k] += (double)r2;
-      }
+      if (lane == 0) my[k] += (double)r0;
       acc_start[k] = 0.0f;
-      acc_num[k] = 0.0f;
-      acc_den[k] = 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < NEC; ++i) {
+      const float r1 = warp_sum_f32(acc_num[i]);
+      const float r2 = warp_sum_f32(acc_den[i]);
+      if (lane == 0) {
+        my[K + KK + i] += (double)r1;
+        my[K + KK + K * C + i] += (double)r2;
+      }
+      acc_num[i] = 0.0f;
+      acc_den[i] = 0.0f;
     }
 #pragma unroll
     for (int i = 0; i < NXI; ++i) {
@@ -231,7 +244,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
   const bool w_gamma_all = !STATS && (OUT == 0 || GC || (OUT == 2 && a.gamma != nullptr && gs < 0));
   const bool w_gamma_one = !STATS && (OUT == 1 || (OUT == 2 && a.gamma != nullptr && gs >= 0));
   const bool w_states = !STATS && (OUT != 2 || a.states != nullptr);
-  const uint32_t row_bytes = (uint32_t)L * (uint32_t)sizeof(ObsT);
+  const uint32_t row_bytes = (uint32_t)L * (uint32_t)(C * sizeof(ObsT));
   const char* obs_base = static_cast<const char*>(a.obs);
   // this warp's slice of the read: positions [w0, w1)
   const int w0 = gw * 32 * CH;
@@ -310,7 +323,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
 
     // ---------------- phase 1: chunk -> registers, transfer-matrix product ----------------
     float rt[RECOMP ? 1 : CH][KR];          // c_k(t) = s_k b_k / (s_0 b_0), k = 1..K-1
-    float ov[(STATS || RECOMP) ? CH : 1];  // observation values (NaN = missing)
+    float ov[((STATS && C == 1) || RECOMP) ? CH : 1];  // observation values (NaN = missing)
     auto ratios = [&](int j, float (&c)[K]) {
       c[0] = 1.0f;
       if (RECOMP) {
@@ -327,40 +340,73 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
     mask_t obsmask = 0;        // bit j: position t0+j observed (E-step only)
     float P[K][K];
     mat_set_identity<K>(P);
-    float ll_sumo = 0.0f;
-    int ll_cnt = 0;
+    float ll_sumo[C];
+    int ll_cnt[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      ll_sumo[c] = 0.0f;
+      ll_cnt[c] = 0;
+    }
     bool prev_obs0 = false;  // observation just before this chunk present? (E-step xi validity)
     unsigned in_dep = 0;
     if (active) {
       if (STATS && !first) {
-        const float op = obs_to_float<ObsT>(s_in[t0 - 1]);
-        prev_obs0 = (op == op);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float op = obs_to_float<ObsT>(s_in[(t0 - 1) * C + c]);
+          prev_obs0 = prev_obs0 || (op == op);  // multi-channel: a position counts when any channel is observed
+        }
       }
       if (t0 + CH > L) {
         // pad the ragged end with missing observations (this thread is the only reader)
-        for (int t = L; t < t0 + CH; ++t) s_in[t] = obs_missing<ObsT>();
+        for (int t = L * C; t < (t0 + CH) * C; ++t) s_in[t] = obs_missing<ObsT>();
       }
       if (want_ll) {
-        // state-0 emission mass of the chunk as (count, sum o): combined in fp64 below
+        // state-0 emission mass of the chunk as (count, sum o) per channel: combined in fp64 below
         for (int j = 0; j < CH; ++j) {
-          const float o = obs_to_float<ObsT>(s_in[t0 + j]);
-          if (o == o) {
-            ll_sumo += o;
-            ++ll_cnt;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const float o = obs_to_float<ObsT>(s_in[(t0 + j) * C + c]);
+            if (o == o) {
+              ll_sumo[c] += o;
+              ++ll_cnt[c];
+            }
           }
         }
       }
 #pragma unroll
       for (int j = 0; j < CH; ++j) {
-        const float o = obs_to_float<ObsT>(s_in[t0 + j]);
-        const bool m = (o == o);
-        if (STATS) obsmask |= m ? ((mask_t)1 << j) : (mask_t)0;
-        if (STATS || RECOMP) ov[j] = o;
         float c[K];
         c[0] = 1.0f;
+        bool m;
+        float o;
+        if (C == 1) {
+          o = obs_to_float<ObsT>(s_in[t0 + j]);
+          m = (o == o);
+#pragma unroll
+          for (int k = 1; k < K; ++k) c[k] = ex2_approx(m ? fmaf(o, tab.rdl[k][0], tab.rl0p[k]) : tab.rmiss[k]);
+        } else {
+          // log2 of the ratio: the transition-scale term + one term per observed channel
+          float x[K];
+#pragma unroll
+          for (int k = 1; k < K; ++k) x[k] = tab.rmiss[k];
+          m = false;
+          o = 0.0f;
+#pragma unroll
+          for (int ch = 0; ch < C; ++ch) {
+            const float oc = obs_to_float<ObsT>(s_in[(t0 + j) * C + ch]);
+            const bool mc = (oc == oc);
+            m = m || mc;
+#pragma unroll
+            for (int k = 1; k < K; ++k) x[k] += mc ? fmaf(oc, tab.rdl[k][ch], tab.rl0[k][ch]) : 0.0f;
+          }
+#pragma unroll
+          for (int k = 1; k < K; ++k) c[k] = ex2_approx(x[k]);
+        }
+        if (STATS) obsmask |= m ? ((mask_t)1 << j) : (mask_t)0;
+        if ((STATS && C == 1) || RECOMP) ov[j] = o;
 #pragma unroll
         for (int k = 1; k < K; ++k) {
-          c[k] = ex2_approx(m ? fmaf(o, tab.rdl[k][0], tab.rl0p[k]) : tab.rmiss[k]);
           if (!RECOMP) rt[RECOMP ? 0 : j][k - 1] = c[k];
         }
         if (WALK) {
@@ -397,7 +443,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
     if constexpr (WALK) {
       if (RECOMP && in_dep == 0x7fa5a5a5u) __nanosleep(1);  // (never-taken in practice) consumer of the loads
       if (G > 1) group_sync(bar_id, T); else __syncwarp();  // B1: chunk registers loaded by everyone
-      if (gt == 0 && !a.alias_in) {
+      if (gt == 0 && !a.alias_in && !a.late_load) {
         const long long nn = n + read_stride;
         if (nn < a.N) issue_load(nn);
       }
@@ -462,7 +508,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
     } else {
       __syncwarp();
     }
-    if (gt == 0 && !a.alias_in) {
+    if (gt == 0 && !a.alias_in && !a.late_load) {
       // the observation buffer is free: prefetch the next read of this group
       const long long nn = n + read_stride;
       if (nn < a.N) issue_load(nn);
@@ -654,8 +700,9 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
 #pragma unroll
         for (int k = 1; k < K; ++k) s += al[k];
         // log P(chunk | past) with the dropped scalars (s_0 per transition, b_0 per observed site) restored
-        ll_thread = (double)logf(s) + (double)e * 0.6931471805599453094 + (double)ll_cnt * tab.l00[0] +
-                    (double)ll_sumo * tab.dl0[0] + (double)(first ? CH - 1 : CH) * tab.log_s0;
+        ll_thread = (double)logf(s) + (double)e * 0.6931471805599453094 + (double)(first ? CH - 1 : CH) * tab.log_s0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) ll_thread += (double)ll_cnt[c] * tab.l00[c] + (double)ll_sumo[c] * tab.dl0[c];
         if (first) ll_thread += tab.log_pi2_sum;
       }
 
@@ -740,11 +787,27 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
 #pragma unroll
             for (int k = 0; k < K; ++k) acc_start[k] += gk[k];
           }
-          if ((obsmask >> j) & (mask_t)1) {
+          if (C == 1) {
+            if ((obsmask >> j) & (mask_t)1) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-              acc_num[k] = fmaf(gk[k], ov[j], acc_num[k]);
-              acc_den[k] += gk[k];
+              for (int k = 0; k < K; ++k) {
+                acc_num[k] = fmaf(gk[k], ov[(STATS && C == 1) ? j : 0], acc_num[k]);
+                acc_den[k] += gk[k];
+              }
+            }
+          } else {
+            // per-channel emission statistics (HMM.py:1874-1880): the observations are still in shared memory
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) {
+              const float oc = obs_to_float<ObsT>(s_in[(t0 + j) * C + ch]);
+              const float mc = (oc == oc) ? 1.0f : 0.0f;
+              const float ov1 = (oc == oc) ? oc : 0.0f;
+#pragma unroll
+              for (int k = 0; k < K; ++k) {
+                const float gm = gk[k] * mc;
+                acc_num[(STATS ? k * C + ch : 0)] = fmaf(gm, ov1, acc_num[(STATS ? k * C + ch : 0)]);
+                acc_den[(STATS ? k * C + ch : 0)] += gm;
+              }
             }
           }
         }
@@ -821,10 +884,10 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
       }
     }
     if (STATS && ((iter + 1) % a.flush_every) == 0) flush_stats();
-    if (a.alias_in) {
-      // the staging buffer doubles as the observation buffer: the next read may only be loaded once
-      // every warp's bulk stores have finished reading it
-      if (!STATS && lane == 0) bulk_wait_read_all();
+    if (a.alias_in || a.late_load) {
+      // the staging buffer doubles as the observation buffer (alias_in), or the backward sweep was still reading
+      // the observations (late_load): the next read may only be loaded once every warp is done with the buffer
+      if (!STATS && a.alias_in && lane == 0) bulk_wait_read_all();
       group_sync(bar_id, T);
       if (gt == 0) {
         const long long nn = n + read_stride;

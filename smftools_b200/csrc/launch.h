@@ -132,6 +132,11 @@ int launch_fb2y_k2(int chunk, int obs_dtype, int out_mode, const smf_hmm_tables*
                    const DeviceInfo& di, int* nblocks, cudaStream_t s);
 int launch_fb2x_k3(int chunk, int obs_dtype, int out_mode, const smf_hmm_tables* t, Fb2Args& a, const Fb2Plan& plan,
                    const DeviceInfo& di, int* nblocks, cudaStream_t s);
+// multi-channel variant of the fast-path kernel (fb2m_k2.cu, fb2m_k3.cu): C = 2, 3
+int launch_fb2m_k2(int n_channels, bool stats, int obs_dtype, const smf_hmm_tables* t, Fb2Args& a, const Fb2Plan& plan,
+                   const DeviceInfo& di, int* nblocks, cudaStream_t s);
+int launch_fb2m_k3(int n_channels, bool stats, int obs_dtype, const smf_hmm_tables* t, Fb2Args& a, const Fb2Plan& plan,
+                   const DeviceInfo& di, int* nblocks, cudaStream_t s);
 struct WalkArgs;
 struct SeqArgs;
 struct SweepArgs;
