@@ -230,7 +230,8 @@ static int fb2_resident(int total_smem, int block, int groups, int regs) {
 
 static int plan_fb2_chunk(int K, int CH, int64_t L64, bool stats, int S, int es, bool want_gamma_one,
                           bool want_states, int max_smem, Fb2Args* a, Fb2Plan* plan, bool walk = false,
-                          bool gc_ok = false /* caller produces the one output set the compact staging serves */) {
+                          bool gc_ok = false /* caller produces the one output set the compact staging serves */,
+                          int cta_extra = 0 /* CTA-wide bytes placed after the statistics accumulators */) {
   if (L64 < 1) return SMF_ERR_TOO_LONG;
   if (L64 > (int64_t)CH * 1024) return SMF_ERR_TOO_LONG;
   const int L = (int)L64;
@@ -281,13 +282,14 @@ static int plan_fb2_chunk(int K, int CH, int64_t L64, bool stats, int S, int es,
     for (int gr = groups; gr >= 1; --gr) {
       const int warps = gr * T / 32;
       const int wacc_b = stats ? align_up(warps * S * 8, 16) : 0;
-      const int total = wacc_b + gr * group_bytes;
+      const int total = wacc_b + cta_extra + gr * group_bytes;
       if (total > max_smem) continue;
       const int res = fb2_resident(total, T * gr, gr, regs);
       if (res > best_res) {
         best_res = res;
         a->off_wacc = 0;
-        a->off_group0 = wacc_b;
+        a->off_bins = wacc_b;  // distance-binned variant: the caller lays [bins | table | log s0] out inside cta_extra
+        a->off_group0 = wacc_b + cta_extra;
         a->group_bytes = group_bytes;
         a->goff_bar = 0;
         a->goff_in = bar_b;
@@ -515,6 +517,13 @@ static size_t seq_ws_bytes(int K, int64_t N, int64_t L) {
 
 static inline int obs_elem_size(int dt) { return dt == SMF_OBS_F32 ? 4 : (dt == SMF_OBS_F64 ? 8 : 1); }
 
+// distance-binned models on the fast-path kernel (fb2_kernel<..., BINNED>, posterior decode): K <= 3, float /
+// uint8-coded rows.  SMF_FB2_BINNED=0 keeps them on the generic kernel.
+static bool fb2_binned_eligible(const smf_hmm_tables* t, int obs_dtype) {
+  static const int env = [] { const char* e = getenv("SMF_FB2_BINNED"); return e ? atoi(e) : 1; }();
+  return env != 0 && t->n_bins > 1 && t->n_channels == 1 && t->n_states <= 3 &&
+         (obs_dtype == SMF_OBS_F32 || obs_dtype == SMF_OBS_U8);
+}
 // multi-channel models on the fast-path kernel (fb2_kernel<..., C>): K <= 3, C = 2 or 3, float / uint8-coded rows.
 // SMF_FB2_MULTI=0 keeps them on the generic kernel.
 static bool fb2_multi_eligible(const smf_hmm_tables* t, int obs_dtype) {
@@ -954,6 +963,36 @@ int smf_hmm_posterior(const smf_hmm_tables* tab, const void* obs, int obs_dtype,
       b.S = stats_len(tab);
       b.flush_every = 1;
       return launch_fb2(false, tab, obs_dtype, b, p2, di, nullptr, (cudaStream_t)stream);
+    }
+  }
+  if (fb2_binned_eligible(tab, obs_dtype) && !g_force_generic && cadence == 4 && n_pos > 1 &&
+      fb2_aligned(obs, obs_dtype, gamma, tab->n_states, gamma_state)) {
+    Fb2Args b;
+    memset(&b, 0, sizeof(b));
+    Fb2Plan p2;
+    const int lpad = (int)((n_pos + 16) / 17 * 17);
+    const int bins_b = align_up(lpad, 16);
+    const int btab_b = tab->n_bins * (tab->n_states == 2 ? 4 : 8) * 4;
+    const int ls0_b = tab->n_bins * 8;
+    if (plan_fb2_chunk(tab->n_states, 17, n_pos, false, stats_len(tab), obs_elem_size(obs_dtype),
+                       gamma != nullptr && gamma_state >= 0, states != nullptr, di.max_smem_optin, &b, &p2, false, false,
+                       bins_b + align_up(btab_b, 16) + align_up(ls0_b, 16)) == SMF_OK) {
+      b.off_btab = b.off_bins + bins_b;
+      b.off_ls0 = b.off_btab + align_up(btab_b, 16);
+      b.bins = bins;
+      b.n_bins = tab->n_bins;
+      b.obs = obs;
+      b.N = n_reads;
+      b.L = (int)n_pos;
+      b.gamma = gamma;
+      b.gamma_state = gamma_state;
+      b.states = states;
+      b.loglik = loglik;
+      b.partials = nullptr;
+      b.S = stats_len(tab);
+      b.flush_every = 1;
+      return tab->n_states == 2 ? launch_fb2b_k2(obs_dtype, tab, b, p2, di, (cudaStream_t)stream)
+                                : launch_fb2b_k3(obs_dtype, tab, b, p2, di, (cudaStream_t)stream);
     }
   }
   if (fb2_multi_eligible(tab, obs_dtype) && !g_force_generic && cadence == 4 &&

@@ -47,6 +47,11 @@ struct Fb2Args {
   const double* ll_in;
   int Tact;  // chunks per read
   int gc;    // 1: staging tile sized for the compact (OUT == 3) layout
+  const int8_t* bins;  // BINNED: device [L-1] distance-bin index of every transition
+  int n_bins;
+  int off_bins;     // BINNED, CTA-wide: int8 [Lpad] bin of the transition INTO position t at index t (0 for t = 0 / pads)
+  int off_btab;     // BINNED, CTA-wide: float [n_bins][kBinRow] column-normalised transitions + log2 scale ratios
+  int off_ls0;      // BINNED, CTA-wide: double [n_bins] log A_b[0][0]
   int late_load;  // 1: the next read is requested at the end of the iteration (multi-channel E-step: the backward
                   //    sweep re-reads the observations from shared memory for the per-channel emission statistics)
 };
@@ -143,7 +148,14 @@ __device__ __forceinline__ void store_row_bulk(void* dst, const void* src, uint3
 // position is the product over its observed channels, computed once in phase 1 like the single-channel ratio --
 // everything after that (chunk products, scans, sweeps, stores) is unchanged.  The E-step keeps K x C emission
 // accumulators and re-reads the observations from shared memory in the backward sweep (late_load).
-template <int K, int CH, bool STATS, typename ObsT, int MAXT, int MINB, int OUT, bool WALK = false, int C = 1>
+//
+// BINNED: distance-binned transitions (DistanceBinnedSingleBernoulliHMM, HMM.py:2127-2188): the transition into
+// position t is A_b with b = bins[t-1].  Every bin's matrix is column-normalised on its own (A_b = A'_b diag(s_b));
+// a shared-memory table holds, per bin, the off-diagonal entries of A'_b and log2(s_b[k] / s_b[0]), one 16- or
+// 32-byte row that a position fetches with its bin index in each of the three phases; the scale ratio is folded
+// into the cached emission ratio, the dropped scalar s_b[0] returns in the log-likelihood.  Posterior decode only.
+template <int K, int CH, bool STATS, typename ObsT, int MAXT, int MINB, int OUT, bool WALK = false, int C = 1,
+          bool BINNED = false>
 __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__ FbTables<K> tab,
                                                    const __grid_constant__ Fb2Args a) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -154,6 +166,8 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
   // recompute the ratios (3 ex2 per position and phase; the kernel is FMA-bound there anyway)
   constexpr bool RECOMP = (K >= 4);
   static_assert(C == 1 || (!WALK && OUT == 2 && K <= 3), "multi-channel variant: K <= 3, run-time output set, single kernel");
+  static_assert(!BINNED || (C == 1 && !WALK && !STATS && OUT == 2 && K <= 3), "distance-binned variant: posterior decode, K <= 3");
+  constexpr int kBinRow = (K == 2) ? 4 : 8;  // floats per bin: K (K - 1) off-diagonal entries + K - 1 scale ratios (+ pad)
 
   const int tid = threadIdx.x;
   const int T = a.T;
@@ -179,6 +193,24 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
   double* s_ll = reinterpret_cast<double*>(s_z + 32 * K);  // [32]
 
   if (gt == 0) mbar_init(mbar, 1);
+  const int8_t* s_bins = reinterpret_cast<const int8_t*>(smem + a.off_bins);
+  const float* s_btab = reinterpret_cast<const float*>(smem + a.off_btab);
+  const double* s_ls0 = reinterpret_cast<const double*>(smem + a.off_ls0);
+  if (BINNED) {
+    int8_t* wb = reinterpret_cast<int8_t*>(smem + a.off_bins);
+    const int lpad = ((L + CH - 1) / CH) * CH;
+    for (int i = tid; i < lpad; i += blockDim.x) wb[i] = (i >= 1 && i < L) ? a.bins[i - 1] : (int8_t)0;
+    float* wt = reinterpret_cast<float*>(smem + a.off_btab);
+    double* wl = reinterpret_cast<double*>(smem + a.off_ls0);
+    for (int b = tid; b < a.n_bins; b += blockDim.x) {
+      int o = 0;
+      for (int i = 0; i < K; ++i)
+        for (int j = 0; j < K; ++j)
+          if (i != j) wt[b * kBinRow + o++] = tab.A[b][i][j] / tab.A[b][j][j];
+      for (int k = 1; k < K; ++k) wt[b * kBinRow + o++] = log2f(tab.A[b][k][k] / tab.A[b][0][0]);
+      wl[b] = tab.log_s0b[b];
+    }
+  }
   if (STATS) {
     const int nw = blockDim.x >> 5;
     for (int i = tid; i < nw * a.S; i += blockDim.x) wacc[i] = 0.0;
@@ -271,25 +303,56 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
     for (int j = 0; j < K; ++j) A[i][j] = tab.Ap[i][j];
 
   // row-vector x Ap  and  Ap x column-vector with the unit diagonal folded into the addend
-  auto vecA = [&](const float (&x)[K], float (&y)[K]) {
+  auto vecA = [&](const float (&Am)[K][K], const float (&x)[K], float (&y)[K]) {
 #pragma unroll
     for (int j = 0; j < K; ++j) {
       float s = x[j];
 #pragma unroll
       for (int i = 0; i < K; ++i)
-        if (i != j) s = fmaf(x[i], A[i][j], s);
+        if (i != j) s = fmaf(x[i], Am[i][j], s);
       y[j] = s;
     }
   };
-  auto Avec = [&](const float (&x)[K], float (&y)[K]) {
+  auto Avec = [&](const float (&Am)[K][K], const float (&x)[K], float (&y)[K]) {
 #pragma unroll
     for (int i = 0; i < K; ++i) {
       float s = x[i];
 #pragma unroll
       for (int j = 0; j < K; ++j)
-        if (j != i) s = fmaf(A[i][j], x[j], s);
+        if (j != i) s = fmaf(Am[i][j], x[j], s);
       y[i] = s;
     }
+  };
+  // BINNED: the table row of the transition into position t (off-diagonal entries of A'_b, then log2 scale ratios)
+  auto bin_row = [&](int t, float (&Ab)[K][K], float (&rs)[K]) {
+    const float* row = s_btab + (int)s_bins[t] * kBinRow;
+    float r[kBinRow];
+    if (K == 2) {
+      const float4 q = *reinterpret_cast<const float4*>(row);
+      r[0] = q.x;
+      r[1] = q.y;
+      r[2] = q.z;
+      r[3] = q.w;
+    } else {
+      const float4 q0 = *reinterpret_cast<const float4*>(row);
+      const float4 q1 = *reinterpret_cast<const float4*>(row + 4);
+      r[0] = q0.x;
+      r[1] = q0.y;
+      r[2] = q0.z;
+      r[3] = q0.w;
+      r[4 % kBinRow] = q1.x;
+      r[5 % kBinRow] = q1.y;
+      r[6 % kBinRow] = q1.z;
+      r[7 % kBinRow] = q1.w;
+    }
+    int o = 0;
+#pragma unroll
+    for (int i = 0; i < K; ++i)
+#pragma unroll
+      for (int j = 0; j < K; ++j) Ab[i][j] = (i == j) ? 1.0f : r[o++];
+    rs[0] = 0.0f;
+#pragma unroll
+    for (int k = 1; k < K; ++k) rs[k] = r[o++];
   };
 
   int iter = 0;
@@ -380,7 +443,17 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
         c[0] = 1.0f;
         bool m;
         float o;
-        if (C == 1) {
+        float Ab[K][K], rsb[K];
+        if (BINNED) bin_row(t0 + j, Ab, rsb);
+        const float(&Am)[K][K] = BINNED ? Ab : A;
+        if (BINNED) {
+          o = obs_to_float<ObsT>(s_in[t0 + j]);
+          m = (o == o);
+          const bool start = first && j == 0;  // no transition into the first position: no scale ratio either
+#pragma unroll
+          for (int k = 1; k < K; ++k)
+            c[k] = ex2_approx((m ? fmaf(o, tab.rdl[k][0], tab.rl0[k][0]) : 0.0f) + (start ? 0.0f : rsb[k]));
+        } else if (C == 1) {
           o = obs_to_float<ObsT>(s_in[t0 + j]);
           m = (o == o);
 #pragma unroll
@@ -423,14 +496,14 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
           for (int i = 0; i < K; ++i)
 #pragma unroll
             for (int jj = 0; jj < K; ++jj) {
-              const float aij = (i == jj) ? 1.0f : (first ? 0.0f : A[i][jj]);
+              const float aij = (i == jj) ? 1.0f : (first ? 0.0f : Am[i][jj]);
               P[i][jj] = (jj == 0) ? aij : aij * c[jj];
             }
         } else {
 #pragma unroll
           for (int i = 0; i < K; ++i) {
             float q[K];
-            vecA(P[i], q);
+            vecA(Am, P[i], q);
 #pragma unroll
             for (int jj = 0; jj < K; ++jj) P[i][jj] = (jj == 0) ? q[jj] : q[jj] * c[jj];
           }
@@ -661,9 +734,12 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
         float nx[K];
         float cf[K];
         ratios(j, cf);
+        float Ab[K][K], rsb[K];
+        if (BINNED) bin_row(t0 + j, Ab, rsb);
+        const float(&Am)[K][K] = BINNED ? Ab : A;
         if (j == 0) {
           float y[K];
-          vecA(al, y);
+          vecA(Am, al, y);
 #pragma unroll
           for (int jj = 0; jj < K; ++jj) {
             const float s = first ? al[jj] : y[jj];  // alpha_0 = pi * b_0: no transition
@@ -671,7 +747,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
           }
         } else {
           float y[K];
-          vecA(al, y);
+          vecA(Am, al, y);
 #pragma unroll
           for (int jj = 0; jj < K; ++jj) nx[jj] = (jj == 0) ? y[jj] : y[jj] * cf[jj];
         }
@@ -700,7 +776,13 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
 #pragma unroll
         for (int k = 1; k < K; ++k) s += al[k];
         // log P(chunk | past) with the dropped scalars (s_0 per transition, b_0 per observed site) restored
-        ll_thread = (double)logf(s) + (double)e * 0.6931471805599453094 + (double)(first ? CH - 1 : CH) * tab.log_s0;
+        ll_thread = (double)logf(s) + (double)e * 0.6931471805599453094;
+        if (BINNED) {
+          // the dropped scalar of every transition into this chunk's positions: s_b[0] of that transition's bin
+          for (int j = first ? 1 : 0; j < CH; ++j) ll_thread += s_ls0[(int)s_bins[t0 + j]];
+        } else {
+          ll_thread += (double)(first ? CH - 1 : CH) * tab.log_s0;
+        }
 #pragma unroll
         for (int c = 0; c < C; ++c) ll_thread += (double)ll_cnt[c] * tab.l00[c] + (double)ll_sumo[c] * tab.dl0[c];
         if (first) ll_thread += tab.log_pi2_sum;
@@ -819,7 +901,10 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
           cb[0] = bv[0];
 #pragma unroll
           for (int k = 1; k < K; ++k) cb[k] = cr[k] * bv[k];
-          Avec(cb, nb);
+          float Ab[K][K], rsb[K];
+          if (BINNED) bin_row(t0 + j, Ab, rsb);
+          const float(&Am)[K][K] = BINNED ? Ab : A;
+          Avec(Am, cb, nb);
           if (STATS) {
             // xi_{t-1}(i,jj) ~ alpha_{t-1}(i) Ap[i][jj] cb[jj], t = t0+j > 0, counted when both
             // endpoints are observed (HMM.py:1583-1591)

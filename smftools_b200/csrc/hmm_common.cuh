@@ -39,6 +39,7 @@ struct FbTables {
   float rmiss[K];
   double log_s0;
   double log_pi2_sum;
+  double log_s0b[kMaxB];  // distance-binned fast path: log A_b[0][0] of every bin
   int nb;
   int C;
 };

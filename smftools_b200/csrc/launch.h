@@ -90,6 +90,7 @@ static void build_fb_tables(const smf_hmm_tables* t, FbTables<K>* out) {
     }
     out->log_s0 = t->log_trans[0];
     out->log_pi2_sum = log(p2sum);
+    for (int b = 0; b < t->n_bins; ++b) out->log_s0b[b] = t->log_trans[(size_t)b * K * K];
   }
   out->nb = t->n_bins;
   out->C = C;
@@ -137,6 +138,11 @@ int launch_fb2m_k2(int n_channels, bool stats, int obs_dtype, const smf_hmm_tabl
                    const DeviceInfo& di, int* nblocks, cudaStream_t s);
 int launch_fb2m_k3(int n_channels, bool stats, int obs_dtype, const smf_hmm_tables* t, Fb2Args& a, const Fb2Plan& plan,
                    const DeviceInfo& di, int* nblocks, cudaStream_t s);
+// distance-binned variant of the fast-path kernel, posterior decode (fb2b_k2.cu, fb2b_k3.cu)
+int launch_fb2b_k2(int obs_dtype, const smf_hmm_tables* t, Fb2Args& a, const Fb2Plan& plan, const DeviceInfo& di,
+                   cudaStream_t s);
+int launch_fb2b_k3(int obs_dtype, const smf_hmm_tables* t, Fb2Args& a, const Fb2Plan& plan, const DeviceInfo& di,
+                   cudaStream_t s);
 struct WalkArgs;
 struct SeqArgs;
 struct SweepArgs;
