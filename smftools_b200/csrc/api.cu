@@ -489,26 +489,37 @@ static bool seq_shape_eligible(const smf_hmm_tables* t, int64_t N, int64_t L) {
   const int mode = g_seq_mode;
   if (mode == 0 || g_force_generic) return false;
   if (t->n_channels != 1 || t->n_bins != 1) return false;
-  if (L < 2 || L > (1 << 24) || (L & 3)) return false;
+  if (L < 2 || L > (1 << 24)) return false;
   if (rescale_cadence(t) != 4) return false;
   if (mode == 1) return true;
   return N >= seq_min_reads(t->n_states);
 }
-static bool seq_launch_eligible(const smf_hmm_tables* t, int64_t N, int64_t L, int obs_dtype, const void* obs) {
-  if (!seq_shape_eligible(t, N, L)) return false;
+// rows on 16-byte boundaries whose 16-element loads stay inside the buffer: vector loads
+static bool seq_rows_aligned(int64_t L, int obs_dtype, const void* obs) {
   if (reinterpret_cast<uintptr_t>(obs) & 15u) return false;
-  if (obs_dtype == SMF_OBS_U8) return (L & 15) == 0;  // rows are whole 16-byte groups
-  if (obs_dtype == SMF_OBS_F32) return (L & 3) == 0;
-  return false;
+  return obs_dtype == SMF_OBS_U8 ? (L & 15) == 0 : (L & 3) == 0;
+}
+// E-step: any float / uint8-coded rows (unaligned rows are read element-wise); posterior decode additionally needs
+// output rows on 16-byte boundaries (need_aligned)
+static bool seq_launch_eligible(const smf_hmm_tables* t, int64_t N, int64_t L, int obs_dtype, const void* obs,
+                                bool need_aligned) {
+  if (!seq_shape_eligible(t, N, L)) return false;
+  if (obs_dtype != SMF_OBS_U8 && obs_dtype != SMF_OBS_F32) return false;
+  if (need_aligned) return seq_rows_aligned(L, obs_dtype, obs) && (L & 3) == 0;
+  return true;
 }
 // posterior decode on the sequential kernels: K >= 3 by default (K = 2 has the faster chunk-parallel kernel;
 // "seq" = 1 forces it for every eligible batch)
 static bool seq_post_shape_eligible(const smf_hmm_tables* t, int64_t N, int64_t L) {
-  if (!seq_shape_eligible(t, N, L)) return false;
+  if (!seq_shape_eligible(t, N, L) || (L & 3)) return false;
   if (g_seq_mode == 1) return true;
-  // measured (profiles/r02_seq_post.txt): K = 4 wins at every length (0.31-0.37 of HBM peak vs 0.26-0.30 for the
-  // chunk-parallel kernels at 5 kb); K = 3 only for short reads, where fb2_kernel's scan is amortised badly
-  return t->n_states == 4 || (t->n_states == 3 && L <= 640);
+  // measured (profiles/r02_seq_post.txt, r02_final_sweep.txt; ~2.4 ms per 4e8 positions for K = 3 at any length):
+  // K = 4 wins at every length (0.31-0.44 of HBM peak vs 0.26-0.40); K = 3 where the chunk-parallel kernels are
+  // weak -- short reads (<= 400: 0.31-0.41) and reads beyond the single kernel's reach (> 13.4 kb: 0.27); K = 2 only
+  // beyond the fast path's reach (> 21 kb: 0.21-0.25)
+  if (t->n_states == 4) return true;
+  if (t->n_states == 3) return L <= 400 || L > 13440;
+  return L > 21120;
 }
 static size_t seq_ws_bytes(int K, int64_t N, int64_t L) {
   const size_t tact = (size_t)((L + kSeqCH - 1) / kSeqCH);
@@ -858,7 +869,7 @@ int smf_hmm_posterior(const smf_hmm_tables* tab, const void* obs, int obs_dtype,
     // large batches of K >= 3: one thread per read (checkpointed forward pass, one backward pass, posteriors
     // staged in shared memory and written as whole sectors) when the caller provided the checkpoint workspace
     if (workspace != nullptr && seq_post_shape_eligible(tab, n_reads, n_pos) &&
-        seq_launch_eligible(tab, n_reads, n_pos, obs_dtype, obs) && (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0 &&
+        seq_launch_eligible(tab, n_reads, n_pos, obs_dtype, obs, true) && (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0 &&
         (reinterpret_cast<uintptr_t>(states) & 3u) == 0 && (reinterpret_cast<uintptr_t>(gamma) & 15u) == 0) {
       if (workspace_bytes < seq_ws_bytes(tab->n_states, n_reads, n_pos)) return SMF_ERR_WORKSPACE;
       char* wws = reinterpret_cast<char*>(workspace);
@@ -1062,8 +1073,12 @@ int smf_hmm_estep(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int
   const int cadence = rescale_cadence(tab);
   if (tab->n_channels == 1 && tab->n_bins == 1 && !g_force_generic && cadence == 4 &&
       fb2_aligned(obs, obs_dtype, nullptr, tab->n_states, -1)) {
+    // large batches of K >= 3: the sequential kernels also beat the bundled short-read kernel (K = 4, 10^6 x 304:
+    // 1.8e11 vs 7e10 read-positions/s; K = 3: 2.0e11 vs 1.4e11); K = 2 short reads stay bundled (3.0e11 either way)
+    const bool seq_first = tab->n_states >= 3 && g_short_mode != 1 &&
+                           seq_launch_eligible(tab, n_reads, n_pos, obs_dtype, obs, false);
     // short reads: several reads per warp (E-step variant of short_kernel)
-    if (g_short_mode != 0 && obs_dtype != SMF_OBS_F64 &&
+    if (!seq_first && g_short_mode != 0 && obs_dtype != SMF_OBS_F64 &&
         (g_short_mode == 1 || n_pos <= short_max_len(tab->n_states, true))) {
       ShortArgs sa;
       memset(&sa, 0, sizeof(sa));
@@ -1085,7 +1100,7 @@ int smf_hmm_estep(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int
         return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
       }
     }
-    if (seq_launch_eligible(tab, n_reads, n_pos, obs_dtype, obs)) {
+    if (seq_launch_eligible(tab, n_reads, n_pos, obs_dtype, obs, false)) {
       // large batch: one thread per read, checkpointed forward pass + one backward pass with statistics
       char* wws = reinterpret_cast<char*>(workspace) + (size_t)kMaxEstepBlocks * (size_t)S * sizeof(double);
       SeqArgs q;
@@ -1094,6 +1109,7 @@ int smf_hmm_estep(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int
       q.g.N = n_reads;
       q.g.L = (int)n_pos;
       q.g.row_stride = (int)n_pos;
+      q.g.unaligned = seq_rows_aligned(n_pos, obs_dtype, obs) ? 0 : 1;
       q.g.Tact = (int)((n_pos + kSeqCH - 1) / kSeqCH);
       q.g.ll = reinterpret_cast<double*>(wws);
       q.g.ckpt = reinterpret_cast<float*>(wws + (((size_t)n_reads * sizeof(double) + 63) & ~(size_t)63));

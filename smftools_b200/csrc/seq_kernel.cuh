@@ -48,7 +48,9 @@ struct SeqGroup {
   const void* obs;   // [N, row_stride] observations
   long long N;       // reads
   int L;             // positions per read
-  int row_stride;    // elements between rows (uint8: multiple of 16, float: multiple of 4)
+  int row_stride;    // elements between rows
+  int unaligned;     // 0: every row starts on a 16-byte boundary and a 16-element load never leaves the buffer (row_stride a
+                     // multiple of 16 for uint8 / 4 for float): vector loads; 1: element-wise loads (E-step of arbitrary rows)
   int Tact;          // chunks per read = ceil(L / 16)
   int item0;         // first work item of the group (grouped launches)
   float* ckpt;       // [Tact][N][KP] alpha entering chunk c (slot 0 unused)
@@ -86,9 +88,16 @@ struct SeqChunk;
 template <>
 struct SeqChunk<unsigned char> {
   uint4 w;
-  __device__ __forceinline__ void load(const unsigned char* p, int len) {
-    (void)len;  // rows of the uint8 code are padded to whole 16-byte groups (row_stride % 16 == 0)
-    w = __ldg(reinterpret_cast<const uint4*>(p));
+  __device__ __forceinline__ void load(const unsigned char* p, int len, int unaligned = 0) {
+    if (!unaligned) {
+      w = __ldg(reinterpret_cast<const uint4*>(p));  // rows padded to whole 16-byte groups
+      return;
+    }
+    unsigned v[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};  // beyond the row: missing
+#pragma unroll
+    for (int j = 0; j < kSeqCH; ++j)
+      if (j < len) v[j >> 2] = (v[j >> 2] & ~(0xffu << (8 * (j & 3)))) | ((unsigned)__ldg(p + j) << (8 * (j & 3)));
+    w = make_uint4(v[0], v[1], v[2], v[3]);
   }
   __device__ __forceinline__ unsigned code(int j) const {
     const unsigned x = (j < 4) ? w.x : (j < 8 ? w.y : (j < 12 ? w.z : w.w));
@@ -100,14 +109,22 @@ struct SeqChunk<unsigned char> {
 template <>
 struct SeqChunk<float> {
   float4 q[4];
-  __device__ __forceinline__ void load(const float* p, int len) {
+  __device__ __forceinline__ void load(const float* p, int len, int unaligned = 0) {
+    if (!unaligned) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      if (4 * g < len)
-        q[g] = __ldg(reinterpret_cast<const float4*>(p) + g);
-      else
-        q[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int g = 0; g < 4; ++g) {
+        if (4 * g < len)
+          q[g] = __ldg(reinterpret_cast<const float4*>(p) + g);
+        else
+          q[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      return;
     }
+    float v[kSeqCH];
+#pragma unroll
+    for (int j = 0; j < kSeqCH; ++j) v[j] = (j < len) ? __ldg(p + j) : 0.0f;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) q[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
   }
   __device__ __forceinline__ float value(int j) const {
     const float4 v = q[j >> 2];
@@ -305,11 +322,11 @@ __global__ void __launch_bounds__(kSeqThreads) seq_forward_kernel(const __grid_c
     double sumo = 0.0;
     float* dst = g.ckpt + cstride + (size_t)n * KP;
     SeqChunk<ObsT> cur, nxt;
-    cur.load(row, min(kSeqCH, L));
+    cur.load(row, min(kSeqCH, L), g.unaligned);
     for (int c = 0; c < g.Tact; ++c) {
       const int t0 = c * kSeqCH;
       const int len = min(kSeqCH, L - t0);
-      if (c + 1 < g.Tact) nxt.load(row + t0 + kSeqCH, min(kSeqCH, L - t0 - kSeqCH));
+      if (c + 1 < g.Tact) nxt.load(row + t0 + kSeqCH, min(kSeqCH, L - t0 - kSeqCH), g.unaligned);
       if (c > 0) {
         seq_store_vec<K>(dst, al);
         dst += cstride;
@@ -535,7 +552,7 @@ __global__ void __launch_bounds__(kSeqThreads, seq_bwd_min_blocks(K, sizeof(ObsT
     SeqChunk<ObsT> cur, prv;
     {
       const int t0 = (g.Tact - 1) * kSeqCH;
-      cur.load(row + t0, L - t0);
+      cur.load(row + t0, L - t0, g.unaligned);
     }
     int since_flush = 0;
     float vnext[K];
@@ -553,7 +570,7 @@ __global__ void __launch_bounds__(kSeqThreads, seq_bwd_min_blocks(K, sizeof(ObsT
         asm volatile("prefetch.global.L2 [%0];" ::"l"(row + t0 - 2 * kSeqCH));
       }
       if (!first) {
-        prv.load(row + t0 - kSeqCH, kSeqCH);
+        prv.load(row + t0 - kSeqCH, kSeqCH, g.unaligned);
 #pragma unroll
         for (int k = 0; k < K; ++k) v[k] = vnext[k];
         // checkpoint of the chunk before this one: in flight while this chunk is processed

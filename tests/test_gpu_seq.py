@@ -27,7 +27,8 @@ def _code(X32):
 
 @pytest.mark.parametrize("K,L,N,prob", [(2, 16, 70, False), (2, 512, 300, False), (3, 1008, 129, False), (4, 2000, 257, False),
                                         (4, 48, 1000, False), (3, 500, 200, True), (4, 1204, 131, True), (2, 4, 33, True),
-                                        (4, 8000, 40, False)])
+                                        (4, 8000, 40, False), (2, 170, 129, False), (4, 37, 300, False), (3, 1001, 64, True),
+                                        (4, 170, 500, False)])
 def test_seq_estep_matches_oracle_and_chunk_parallel_path(K, L, N, prob, force_seq):
     from smftools_b200 import engine
 
@@ -38,8 +39,8 @@ def test_seq_estep_matches_oracle_and_chunk_parallel_path(K, L, N, prob, force_s
     ref = O.stats_vector(O.estep(X32.astype(np.float64), p, None))
     scale = np.maximum(np.abs(ref), 1.0)
     variants = [("f32", torch.from_numpy(X32.astype(np.float32)).to(dev))]
-    if not prob and L % 16 == 0:
-        variants.append(("u8", torch.from_numpy(_code(X32)).to(dev)))
+    if not prob:
+        variants.append(("u8", torch.from_numpy(_code(X32)).to(dev)))  # rows off 16-byte boundaries are read element-wise
     for name, obs in variants:
         engine.set_option("seq", 1)
         st = engine.estep(tables, obs, None).cpu().numpy()
@@ -108,3 +109,33 @@ def test_seq_posterior_matches_oracle(K, L, N, prob, force_seq):
         gam0, st0, _ = engine.posterior(tables, obs)
         engine.set_option("seq", 1)
         assert (gam0 - gam).abs().max().item() <= 4e-6
+
+
+def test_seq_posterior_is_the_policy_for_large_k4_batches():
+    """49,152 replicated reads x 512 positions, K = 4: the default policy decodes on the sequential kernels (the
+    library asks for the checkpoint workspace); every replica must get the oracle's posterior of its base read."""
+    from helpers import assert_states_match_up_to_ties
+    from smftools_b200 import _lib, engine
+
+    K, L, base_n, reps = 4, 512, 48, 1024
+    dev = torch.device("cuda")
+    p = O.synth_params(K)
+    tables = model_from_params(p)._host_tables()
+    base = O.synth_reads(base_n, L, K, 4242, prob=True, nan_rate=0.3)
+    g_ref, ll_ref = O.posterior(base.astype(np.float64), p)
+    obs = torch.from_numpy(np.tile(base.astype(np.float32), (reps, 1))).to(dev)
+    N = base_n * reps
+    need = int(_lib.load().smf_hmm_workspace_bytes(_lib.OP_POSTERIOR, tables.ref, N, L))
+    assert need >= (L // 16) * N * 16  # alpha checkpoints of the sequential kernels
+    g, s, ll = engine.posterior(tables, obs, want_loglik=True)
+    g = g.view(reps, base_n, L, K)
+    assert torch.equal(g[0], g[reps - 1]) and torch.equal(g[0], g[reps // 2])  # same read, same result, any thread
+    assert np.abs(g[3].cpu().numpy() - g_ref).max() <= 1e-5
+    assert_states_match_up_to_ties(s.view(reps, base_n, L)[5].cpu().numpy().astype(np.int64), g_ref.argmax(axis=2), g_ref)
+    np.testing.assert_allclose(ll.view(reps, base_n)[7].cpu().numpy(), ll_ref, rtol=1e-6, atol=1e-4)
+    engine.set_option("seq", 0)
+    try:
+        g0, _, _ = engine.posterior(tables, obs)
+    finally:
+        engine.set_option("seq", -1)
+    assert (g0.view(reps, base_n, L, K)[0] - g[0]).abs().max().item() <= 4e-6
