@@ -361,7 +361,8 @@ static int plan_fb2(int K, int64_t L64, bool stats, int S, int es, bool want_gam
         double sc = lane_eff(cand[i]) * (0.8 + 0.2 * (cand[i] - 17) / 16.0);
         // one resident read per SM around 9-10 kb: the extra warp of chunk 29 beats the longer chunk
         // (measured 0.59 / 0.66 vs 0.55 / 0.64 of HBM peak at 9 / 10 kb; the other way round at 11 kb)
-        if (cand[i] == 29 && L64 >= 8500 && L64 <= 10500) sc *= 1.06;
+        // (float rows only: with the uint8 code two reads stay resident and chunk 33 wins, 1.65 vs 2.73 ms at 10 kb)
+        if (cand[i] == 29 && L64 >= 8500 && L64 <= 10500 && es == 4) sc *= 1.06;
         if (sc > bs) {
           bs = sc;
           bi = i;
@@ -615,8 +616,8 @@ static int launch_short(const smf_hmm_tables* t, int obs_dtype, const ShortArgs&
 
 static int launch_fb2(bool stats, const smf_hmm_tables* t, int obs_dtype, Fb2Args& a, const Fb2Plan& plan,
                       const DeviceInfo& di, int* nblocks, cudaStream_t stream) {
-  // output-set specialisations exist for float observations; everything else decides at run time
-  int out = (stats || obs_dtype != SMF_OBS_F32 || a.gamma == nullptr || a.states == nullptr ||
+  // output-set specialisations exist for float and uint8-coded observations; everything else decides at run time
+  int out = (stats || (obs_dtype != SMF_OBS_F32 && obs_dtype != SMF_OBS_U8) || a.gamma == nullptr || a.states == nullptr ||
              a.loglik != nullptr)
                 ? 2
                 : (a.gamma_state < 0 ? 0 : 1);

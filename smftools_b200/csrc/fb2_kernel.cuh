@@ -303,6 +303,16 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
     for (int j = 0; j < K; ++j) A[i][j] = tab.Ap[i][j];
 
   // row-vector x Ap  and  Ap x column-vector with the unit diagonal folded into the addend
+  // uint8-coded observations have three possible emission ratios per state: evaluated once per thread (the same
+  // ex2 of the same argument as the per-position expression, so results are bit-identical), selected per position
+  constexpr bool CODE_TAB = (sizeof(ObsT) == 1) && C == 1 && !BINNED && !RECOMP;
+  float rc0[K], rc1[K], rcm[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    rc0[k] = CODE_TAB ? ex2_approx(fmaf(0.0f, tab.rdl[k][0], tab.rl0p[k])) : 0.0f;
+    rc1[k] = CODE_TAB ? ex2_approx(fmaf(1.0f, tab.rdl[k][0], tab.rl0p[k])) : 0.0f;
+    rcm[k] = CODE_TAB ? ex2_approx(tab.rmiss[k]) : 0.0f;
+  }
   auto vecA = [&](const float (&Am)[K][K], const float (&x)[K], float (&y)[K]) {
 #pragma unroll
     for (int j = 0; j < K; ++j) {
@@ -453,6 +463,12 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
 #pragma unroll
           for (int k = 1; k < K; ++k)
             c[k] = ex2_approx((m ? fmaf(o, tab.rdl[k][0], tab.rl0[k][0]) : 0.0f) + (start ? 0.0f : rsb[k]));
+        } else if (CODE_TAB) {
+          const unsigned code = (unsigned)s_in[t0 + j];
+          m = code < 2u;
+          o = m ? (code == 1u ? 1.0f : 0.0f) : __int_as_float(0x7fc00000);
+#pragma unroll
+          for (int k = 1; k < K; ++k) c[k] = (code == 0u) ? rc0[k] : ((code == 1u) ? rc1[k] : rcm[k]);
         } else if (C == 1) {
           o = obs_to_float<ObsT>(s_in[t0 + j]);
           m = (o == o);
