@@ -478,6 +478,9 @@ def stream_workload(name, ctx, steps_cap=None):
 FULL_WORKLOADS = {
     "c3p": dict(K=2, L=10_000, op="posterior", prob=False, chunk=65_536, chunks=16,
                 desc="headline target: posterior decode of 1M (16 x 65,536) reads x 10 kb, K=2 binary, f32 obs"),
+    "c3p_u8": dict(K=2, L=10_000, op="posterior", prob=False, chunk=65_536, chunks=16, es=1,
+                   desc="posterior decode of 1M (16 x 65,536) reads x 10 kb, K=2 binary, uint8-coded obs (what the device "
+                        "input builders emit: 0 / 1 / 255 = missing)"),
     "c3p_k3": dict(K=3, L=10_000, op="posterior", prob=True, chunk=65_536, chunks=16,
                    desc="posterior decode of 1M (16 x 65,536) reads x 10 kb, K=3 m6A probabilistic, f32 obs"),
     "c3v": dict(K=3, L=10_000, op="viterbi", prob=True, chunk=262_144, chunks=4, parity_reads=96,
@@ -886,7 +889,7 @@ def run_ours(args, wl):
     # ---- the other BASELINE shapes at full size ----
     extra = []
     if args.workload == "c2" and not args.no_extra:
-        for name in ("c3p", "c3p_k3", "c3v", "c4", "c4_u8"):
+        for name in ("c3p", "c3p_u8", "c3p_k3", "c3v", "c4", "c4_u8"):
             rec = stream_workload(name, ctx)
             if rec is not None:
                 extra.append(rec)

@@ -98,4 +98,58 @@ for N, L in ((33, 700), (20, 1024), (7, 16)):
     en = torch.from_numpy(full[-1] - rng.integers(0, 50, size=N).astype(np.float64)).to(dev)
     run(f"merge_chain V{V}", lambda: engine.merge_chain(layer, fc, True, 10, ranges, span_coords=fc, start=st, end=en))
     run(f"span_mask V{V}", lambda: engine.span_mask(N, V, dev, coords=fc, start=st, end=en))
+# round 2: sequential kernels (forced on small batches), grouped launches, direct Viterbi, multi-channel / binned fast path
+from smftools_b200 import grouped
+
+engine.set_option("seq", 1)
+for K in (2, 3, 4):
+    m, t = tables(K)
+    for L, N in ((16, 130), (170, 129), (1001, 70), (2048, 33)):
+        X = torch.from_numpy(O.synth_reads(N, L, K, 11 + L, prob=True, nan_rate=0.3)).to(dev)
+        X8 = torch.where(torch.isnan(X), torch.tensor(255.0, device=dev), (X > 0.5).float()).to(torch.uint8)
+        run(f"seq estep K{K} L{L}", lambda: engine.estep(t, X, None))
+        run(f"seq estep-u8 K{K} L{L}", lambda: engine.estep(t, X8, None))
+        if L % 4 == 0:
+            run(f"seq posterior K{K} L{L}", lambda: engine.posterior(t, X, None, want_loglik=True))
+            run(f"seq posterior-one K{K} L{L}", lambda: engine.posterior(t, X, None, gamma_state=1, want_states=False))
+        if L % 16 == 0:
+            run(f"seq posterior-u8 K{K} L{L}", lambda: engine.posterior(t, X8, None))
+engine.set_option("seq", -1)
+for K in (2, 3, 4):
+    shapes = [(70, 16), (300, 170), (129, 1008), (1, 37), (40, 2003), (513, 333)]
+    models = [tables(K)[0] for _ in shapes]
+    obs = [S.CodedU8(torch.from_numpy(np.where(np.isnan(x), 255, x).astype(np.uint8)).to(dev))
+           for x in (O.synth_reads(n, l, K, 50 + i, prob=False, nan_rate=0.3) for i, (n, l) in enumerate(shapes))]
+    run(f"grouped fit K{K}", lambda: grouped.fit_groups(models, obs, max_iter=3, tol=0.0))
+    run(f"grouped decode K{K}", lambda: grouped.decode_groups(models, obs, want_loglik=True))
+    obsf = [torch.from_numpy(O.synth_reads(n, l, K, 80 + i, prob=True, nan_rate=0.3)).to(dev) for i, (n, l) in enumerate(shapes)]
+    run(f"grouped fit f32 K{K}", lambda: grouped.fit_groups(models, obsf, max_iter=2, tol=0.0))
+    run(f"grouped decode-one f32 K{K}", lambda: grouped.decode_groups(models, obsf, gamma_state=0, want_states=False))
+engine.set_option("vit", 1)
+for K in (2, 3, 4):
+    m, t = tables(K)
+    for L, N in ((4, 33), (64, 130), (1204, 70), (5000, 9)):
+        X = torch.from_numpy(O.synth_reads(N, L, K, 13 + L, prob=True, nan_rate=0.3)).to(dev)
+        run(f"direct viterbi K{K} L{L}", lambda: engine.viterbi(t, X, None))
+        if L % 16 == 0:
+            X8 = torch.where(torch.isnan(X), torch.tensor(255.0, device=dev), (X > 0.5).float()).to(torch.uint8)
+            run(f"direct viterbi-u8 K{K} L{L}", lambda: engine.viterbi(t, X8, None))
+engine.set_option("vit", -1)
+for K, C in ((2, 2), (3, 2), (2, 3), (3, 3)):
+    m, t = tables(K, arch="multi", hmm_n_channels=C)
+    for L, N in ((17, 40), (333, 50), (5000, 5), (9000, 3)):
+        X = torch.from_numpy(O.synth_reads(N, L, K, 3 + L, prob=True, nan_rate=0.3, n_channels=C)).to(dev)
+        run(f"multi fast posterior K{K} C{C} L{L}", lambda: engine.posterior(t, X, None, want_loglik=True))
+        run(f"multi fast estep K{K} C{C} L{L}", lambda: engine.estep(t, X, None))
+        X8 = torch.where(torch.isnan(X), torch.tensor(255.0, device=dev), (X > 0.5).float()).to(torch.uint8)
+        run(f"multi fast posterior-u8 K{K} C{C} L{L}", lambda: engine.posterior(t, X8, None))
+        run(f"multi fast estep-u8 K{K} C{C} L{L}", lambda: engine.estep(t, X8, None))
+for K in (2, 3):
+    m, t = tables(K, arch="single_distance_binned", hmm_distance_bins=[1, 5, 10, 25, 50, 100])
+    for L, N in ((2, 9), (35, 100), (1000, 33), (9000, 3)):
+        coords = O.synth_coords(L, 4)
+        bins = m._bins_for(coords, L, dev)
+        X = torch.from_numpy(O.synth_reads(N, L, K, 4 + L, prob=True, nan_rate=0.3)).to(dev)
+        run(f"binned fast posterior K{K} L{L}", lambda: engine.posterior(t, X, bins, want_loglik=True))
+        run(f"binned fast posterior-one K{K} L{L}", lambda: engine.posterior(t, X, bins, gamma_state=0))
 print("all kernels ran")
