@@ -641,10 +641,13 @@ def e2e_legs(args, ctx, model, obs, N, L, K):
 
 def groups_workload(ctx, reads_per_group=500_000, n_groups=16, iters=5, K=2):
     """BASELINE configs[4]: per-reference HMMs on 16 references x 500k reads x 2-20 kb ragged lengths.
-    Groups are dealt WHOLE to the ranks, largest first (no data-path collective); a rank fits all its groups in
-    ONE grouped, device-resident Baum-Welch (smf_hmm_grouped_fit: `iters` iterations, M-step and stop rule on the
-    device, no host round trip), the fitted parameters are exchanged once (all-reduce of a [G, P] matrix), then
-    every group's reads are posterior-decoded with that group's model in 65,536-read chunks."""
+    With one GPU all groups are fitted in ONE grouped, device-resident Baum-Welch (smf_hmm_grouped_fit: `iters`
+    iterations, M-step and stop rule on the device, no host round trip).  With N GPUs a group (up to 1e10 read-positions)
+    is larger than a rank's share, so whole-group dealing cannot balance: the groups are laid end to end and the reads
+    cut into N equal-cost pieces (grouped.partition_reads) -- a group that crosses a cut is read-sharded -- every rank
+    runs the same grouped fit on its shards, and per iteration the [16, S] statistics matrix is NCCL-all-reduced between
+    the device E-step and the device M-step (stream-ordered, still no host round trip), which leaves identical
+    parameters on every rank.  Then every rank posterior-decodes its own reads with each group's model."""
     import torch
     import torch.distributed as dist
 
@@ -656,14 +659,16 @@ def groups_workload(ctx, reads_per_group=500_000, n_groups=16, iters=5, K=2):
     lengths = (np.exp(rng.uniform(np.log(2000), np.log(20000), size=n_groups)).astype(int) // 16 * 16).tolist()
     N = int(reads_per_group)
     costs = [float(N) * L for L in lengths]
-    owned = grouped.deal_groups(costs, world)
-    mine = owned[rank]
+    parts = grouped.partition_reads([N] * n_groups, lengths, world)
+    local = {g: (lo, hi) for g, lo, hi in parts[rank]}
+    mine = sorted(local)
 
     def fresh_models():
         return [S.create_hmm({"hmm_n_states": K, "hmm_init_emission_probs": [0.8 - 0.01 * g, 0.2 + 0.005 * g][:K]},
                              arch="single") for g in range(n_groups)]
 
-    data = {g: device_reads(N, lengths[g], K, False, 500 + g, device, coded_u8=True) for g in mine}
+    data = {g: device_reads(local[g][1] - local[g][0], lengths[g], K, False, 500 + g + 1000 * rank, device, coded_u8=True)
+            for g in mine}
     torch.cuda.synchronize()
     # warm-up on read prefixes (module load, allocator) + in-run parity of the same calls against the oracle
     parity = None
@@ -701,14 +706,18 @@ def groups_workload(ctx, reads_per_group=500_000, n_groups=16, iters=5, K=2):
                       "seconds": round(time.perf_counter() - t0, 2)}
         del pre, dec
     models = fresh_models()
-    obs_list = [S.CodedU8(data[g]) for g in mine]
+    if world > 1:
+        # every rank passes every group, with its own shard of that group's reads (possibly none)
+        fit_models = models
+        obs_list = [S.CodedU8(data[g] if g in local else torch.empty((0, lengths[g]), dtype=torch.uint8, device=device))
+                    for g in range(n_groups)]
+    else:
+        fit_models = [models[g] for g in mine]
+        obs_list = [S.CodedU8(data[g]) for g in mine]
     _barrier(world)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     ev[0].record()
-    if mine:
-        hists = grouped.fit_groups([models[g] for g in mine], obs_list, max_iter=iters, tol=0.0)
-    if world > 1:
-        grouped.exchange_group_parameters(models, owned)
+    hists = grouped.fit_groups(fit_models, obs_list, max_iter=iters, tol=0.0, sharded=world > 1)
     ev[1].record()
     chunk = 65_536
     Lmax = max(lengths)
@@ -718,8 +727,9 @@ def groups_workload(ctx, reads_per_group=500_000, n_groups=16, iters=5, K=2):
     for g in mine:
         tables = models[g]._host_tables()
         L = lengths[g]
-        for lo in range(0, N, chunk):
-            n = min(chunk, N - lo)
+        n_loc = int(data[g].shape[0])
+        for lo in range(0, n_loc, chunk):
+            n = min(chunk, n_loc - lo)
             engine.posterior(tables, data[g][lo:lo + n], None, out_gamma=gam[:n * L * K].view(n, L, K),
                              out_states=stt[:n * L].view(n, L))
             launches += 1
@@ -731,18 +741,22 @@ def groups_workload(ctx, reads_per_group=500_000, n_groups=16, iters=5, K=2):
     rec = None
     if rank == 0:
         pos = float(sum(costs))
-        my_pos = float(sum(costs[g] for g in mine))
+        my_pos = float(sum((local[g][1] - local[g][0]) * lengths[g] for g in mine))
         rec = {"name": "c5", "workload": f"BASELINE configs[4]: {n_groups} reference groups x {N} reads, ragged lengths "
                                          f"{min(lengths)}-{max(lengths)}, per-group {K}-state HMM: {iters} Baum-Welch "
                                          "iterations (grouped device-resident fit) + posterior decode, u8 coded obs",
                "op": "grouped fit + decode", "K": K, "groups": n_groups, "reads_per_group": N, "lengths": lengths,
-               "groups_of_rank": owned, "value": pos * (iters + 1) / (total_ms * 1e-3), "unit": "read-positions/s",
+               "partition": ("all groups on the one GPU" if world == 1 else
+                             "reads cut into equal-cost contiguous pieces (grouped.partition_reads): (group, first read, "
+                             "last read + 1) per rank; per-iteration NCCL all-reduce of the [%d, %d] statistics matrix"
+                             % (n_groups, K + K * K + 2 * K + 1)),
+               "reads_of_rank": parts, "value": pos * (iters + 1) / (total_ms * 1e-3), "unit": "read-positions/s",
                "ms_total": total_ms, "fit_ms": fit_ms, "decode_ms": dec_ms,
                "fit_read_positions_per_s": pos * iters / (fit_ms * 1e-3), "decode_read_positions_per_s": pos / (dec_ms * 1e-3),
-               "gpu_launches_rank0": launches + 1 + 4 * iters, "host_round_trips_in_fit": 1,
+               "gpu_launches_rank0": launches + 1 + 3 * iters, "host_round_trips_in_fit": 1,
                "roofline": {"fit": roofline_of("estep", K, 1, my_pos * iters, ev[0].elapsed_time(ev[1])),
                             "decode": roofline_of("posterior", K, 1, my_pos, ev[1].elapsed_time(ev[2]))},
-               "loglik_monotone": bool(all(all(b2 >= a2 - 1e-6 * abs(a2) for a2, b2 in zip(h, h[1:])) for h in hists)) if mine else None,
+               "loglik_monotone": bool(all(all(b2 >= a2 - 1e-6 * abs(a2) for a2, b2 in zip(h, h[1:])) for h in hists)),
                "parity": parity}
     del data, gam, stt, obs_list
     torch.cuda.empty_cache()

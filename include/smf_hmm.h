@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SMF_HMM_ABI_VERSION 4
+#define SMF_HMM_ABI_VERSION 5
 
 #define SMF_MAX_STATES 4
 #define SMF_MAX_CHANNELS 4
@@ -209,6 +209,28 @@ int smf_hmm_grouped_posterior(int obs_dtype, const smf_hmm_group* groups_host, i
 int smf_hmm_grouped_fit(int n_states, int obs_dtype, const smf_hmm_group* groups_host, int n_groups,
                         double* params, int max_iter, double tol, double eps, int update_mask, double* hist,
                         int32_t* n_iter, int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * The same fit in steps, for groups whose reads are SHARDED over several processes (one per GPU): every process
+ * passes the same group table (same order, same n_pos) with its own shard of each group's reads (n_reads may be 0),
+ * and between the E-step and the M-step of an iteration the caller sum-all-reduces `stats` over the processes
+ * (NCCL on the same stream: nothing waits on the host).  The M-step is deterministic, so every process ends each
+ * iteration with bit-identical parameters, stop decisions and kernel tables.
+ *   SMF_FIT_PHASE_BEGIN   once: uploads the group table, builds the tables of the initial parameters
+ *   SMF_FIT_PHASE_ESTEP   iteration `iter`: statistics of this process's reads -> stats (device double [n_groups, S],
+ *                         S = K + K*K + 2*K + 1; zeros for groups that have stopped)
+ *   SMF_FIT_PHASE_MSTEP   iteration `iter`: M-step, stop rule and table rebuild of every active group from `stats`
+ * Same workspace (smf_hmm_grouped_workspace_bytes(..., fit = 1)) and same params / hist / n_iter / status buffers in
+ * every call of one fit.
+ */
+#define SMF_FIT_PHASE_ALL 0
+#define SMF_FIT_PHASE_BEGIN 1
+#define SMF_FIT_PHASE_ESTEP 2
+#define SMF_FIT_PHASE_MSTEP 3
+int smf_hmm_grouped_fit_step(int phase, int n_states, int obs_dtype, const smf_hmm_group* groups_host, int n_groups,
+                             double* params, int iter, int max_iter, double tol, double eps, int update_mask,
+                             double* hist, int32_t* n_iter, int32_t* status, double* stats, void* workspace,
+                             size_t workspace_bytes, void* stream);
 
 /*
  * Footprint / feature calling on decoded reads.  Replaces the per-read Python loops of

@@ -23,6 +23,7 @@ SMF_ERR_ALIGN = -5
 
 OBS_F32, OBS_F64, OBS_U8 = 0, 1, 2
 OP_POSTERIOR, OP_VITERBI, OP_ESTEP, OP_FEATURES = 0, 1, 2, 3
+FIT_PHASE_ALL, FIT_PHASE_BEGIN, FIT_PHASE_ESTEP, FIT_PHASE_MSTEP = 0, 1, 2, 3
 MAX_STATES, MAX_CHANNELS, MAX_BINS = 4, 4, 16
 
 EXPORTS = (
@@ -38,6 +39,7 @@ EXPORTS = (
     "smf_hmm_grouped_workspace_bytes",
     "smf_hmm_grouped_posterior",
     "smf_hmm_grouped_fit",
+    "smf_hmm_grouped_fit_step",
     "smf_hmm_call_features",
     "smf_hmm_merge_runs",
     "smf_hmm_merge_chain",
@@ -137,7 +139,7 @@ def library_built() -> bool:
     return os.path.isfile(LIB_PATH)
 
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 def load():
@@ -181,6 +183,9 @@ def load():
     lib.smf_hmm_grouped_fit.restype = c_int
     lib.smf_hmm_grouped_fit.argtypes = [c_int, c_int, GP, c_int, c_void_p, c_int, c_double, c_double, c_int, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.smf_hmm_grouped_fit_step.restype = c_int
+    lib.smf_hmm_grouped_fit_step.argtypes = [c_int, c_int, c_int, GP, c_int, c_void_p, c_int, c_int, c_double, c_double,
+                                             c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.smf_hmm_call_features.restype = c_int
     lib.smf_hmm_call_features.argtypes = [c_void_p, c_void_p, c_int, c_double, c_int64, c_int64, c_void_p,
                                           c_void_p, c_void_p, c_int64, POINTER(c_double), POINTER(c_double),

@@ -1504,7 +1504,7 @@ int grouped_plan(int K, int obs_dtype, const smf_hmm_group* gh, int G, bool fit,
   long long n_items = 0;
   for (int g = 0; g < G; ++g) {
     const smf_hmm_group& q = gh[g];
-    if (q.n_reads < 1 || q.n_pos < 1 || q.n_pos > (1 << 24) || q.obs == nullptr) return SMF_ERR_BAD_ARG;
+    if (q.n_reads < 0 || q.n_pos < 1 || q.n_pos > (1 << 24) || (q.n_reads > 0 && q.obs == nullptr)) return SMF_ERR_BAD_ARG;
     if (q.row_stride < q.n_pos || (q.row_stride % (obs_dtype == SMF_OBS_U8 ? 16 : 4)) != 0) return SMF_ERR_ALIGN;
     if (reinterpret_cast<uintptr_t>(q.obs) & 15u) return SMF_ERR_ALIGN;
     if (!fit && (q.gamma != nullptr || q.states != nullptr)) {
@@ -1650,33 +1650,36 @@ int smf_hmm_grouped_posterior(int obs_dtype, const smf_hmm_group* groups_host, i
                 : (K == 3 ? launch_seq_grouped_k3(obs_dtype, mode, a, di, st) : launch_seq_grouped_k4(obs_dtype, mode, a, di, st));
 }
 
-int smf_hmm_grouped_fit(int n_states, int obs_dtype, const smf_hmm_group* groups_host, int n_groups,
-                        double* params, int max_iter, double tol, double eps, int update_mask, double* hist,
-                        int32_t* n_iter, int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
-  const int K = n_states;
+// phases of a grouped fit: SMF_FIT_PHASE_ALL runs begin + max_iter x (E-step, M-step) in one call
+static int grouped_fit_run(int phase, int K, int obs_dtype, const smf_hmm_group* groups_host, int n_groups, double* params,
+                           int iter, int max_iter, double tol, double eps, int update_mask, double* hist, int32_t* n_iter,
+                           int32_t* status, double* stats, void* workspace, size_t workspace_bytes, void* stream) {
   if (params == nullptr || hist == nullptr || n_iter == nullptr || status == nullptr || workspace == nullptr)
     return SMF_ERR_BAD_ARG;
   if (max_iter < 0 || !(eps > 0.0)) return SMF_ERR_BAD_ARG;
+  if (phase != SMF_FIT_PHASE_ALL && (iter < 0 || iter >= (max_iter > 0 ? max_iter : 1))) return SMF_ERR_BAD_ARG;
   GroupedPlan pl;
   int rc = grouped_plan(K, obs_dtype, groups_host, n_groups, true, &pl, nullptr, nullptr, nullptr);
   if (rc != SMF_OK) return rc;
   if (workspace_bytes < pl.total) return SMF_ERR_WORKSPACE;
   if (reinterpret_cast<uintptr_t>(workspace) & 255u) return SMF_ERR_ALIGN;
-  std::vector<SeqGroup> groups(n_groups);
-  std::vector<int> item_group((size_t)pl.n_items);
   char* ws = reinterpret_cast<char*>(workspace);
-  rc = grouped_plan(K, obs_dtype, groups_host, n_groups, true, &pl, ws, groups.data(), item_group.data());
-  if (rc != SMF_OK) return rc;
   DeviceInfo di;
   rc = get_device_info(&di);
   if (rc != SMF_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  rc = grouped_upload(pl, n_groups, groups, item_group, ws, st);
-  if (rc != SMF_OK) return rc;
+  if (phase == SMF_FIT_PHASE_ALL || phase == SMF_FIT_PHASE_BEGIN) {
+    std::vector<SeqGroup> groups(n_groups);
+    std::vector<int> item_group((size_t)pl.n_items);
+    rc = grouped_plan(K, obs_dtype, groups_host, n_groups, true, &pl, ws, groups.data(), item_group.data());
+    if (rc != SMF_OK) return rc;
+    rc = grouped_upload(pl, n_groups, groups, item_group, ws, st);
+    if (rc != SMF_OK) return rc;
+  }
   SeqFitState f;
   memset(&f, 0, sizeof(f));
   f.params = params;
-  f.stats = reinterpret_cast<double*>(ws + pl.off_stats);
+  f.stats = stats != nullptr ? stats : reinterpret_cast<double*>(ws + pl.off_stats);
   f.hist = hist;
   f.active = reinterpret_cast<int*>(ws + pl.off_active);
   f.n_iter = n_iter;
@@ -1692,12 +1695,11 @@ int smf_hmm_grouped_fit(int n_states, int obs_dtype, const smf_hmm_group* groups
   f.update_start = (update_mask & 1) != 0;
   f.update_trans = (update_mask & 2) != 0;
   f.update_emission = (update_mask & 4) != 0;
-  auto mstep = [&](int iter) {
-    f.iter = iter;
+  auto mstep = [&](int it, int what) {
+    f.iter = it;
+    f.what = what;
     return K == 2 ? launch_seq_mstep_k2(f, st) : (K == 3 ? launch_seq_mstep_k3(f, st) : launch_seq_mstep_k4(f, st));
   };
-  rc = mstep(-1);  // tables of the initial parameters; every group active
-  if (rc != SMF_OK) return rc;
   SeqArgs a;
   memset(&a, 0, sizeof(a));
   a.groups = reinterpret_cast<const SeqGroup*>(ws + pl.off_groups);
@@ -1708,15 +1710,50 @@ int smf_hmm_grouped_fit(int n_states, int obs_dtype, const smf_hmm_group* groups
   a.partials = reinterpret_cast<double*>(ws + pl.off_partials);
   a.S = pl.S;
   a.flush_chunks = 8;
-  for (int it = 0; it < max_iter; ++it) {
-    rc = K == 2 ? launch_seq_grouped_k2(obs_dtype, MODE_STATS, a, di, st)
-                : (K == 3 ? launch_seq_grouped_k3(obs_dtype, MODE_STATS, a, di, st)
-                          : launch_seq_grouped_k4(obs_dtype, MODE_STATS, a, di, st));
-    if (rc != SMF_OK) return rc;
-    rc = mstep(it);
-    if (rc != SMF_OK) return rc;
+  auto estep = [&]() {
+    if (pl.n_items == 0) return (int)SMF_OK;  // this rank holds no reads of any group
+    return K == 2 ? launch_seq_grouped_k2(obs_dtype, MODE_STATS, a, di, st)
+                  : (K == 3 ? launch_seq_grouped_k3(obs_dtype, MODE_STATS, a, di, st)
+                            : launch_seq_grouped_k4(obs_dtype, MODE_STATS, a, di, st));
+  };
+  switch (phase) {
+    case SMF_FIT_PHASE_BEGIN:
+      return mstep(-1, SEQ_MSTEP_ALL);  // tables of the initial parameters; every group active
+    case SMF_FIT_PHASE_ESTEP:
+      rc = estep();
+      if (rc != SMF_OK) return rc;
+      return mstep(iter, SEQ_MSTEP_REDUCE_ONLY);  // per-item partials -> stats[G][S]
+    case SMF_FIT_PHASE_MSTEP:
+      return mstep(iter, SEQ_MSTEP_UPDATE_ONLY);
+    case SMF_FIT_PHASE_ALL:
+      rc = mstep(-1, SEQ_MSTEP_ALL);
+      if (rc != SMF_OK) return rc;
+      for (int it = 0; it < max_iter; ++it) {
+        rc = estep();
+        if (rc != SMF_OK) return rc;
+        rc = mstep(it, SEQ_MSTEP_ALL);
+        if (rc != SMF_OK) return rc;
+      }
+      return SMF_OK;
   }
-  return SMF_OK;
+  return SMF_ERR_BAD_ARG;
+}
+
+int smf_hmm_grouped_fit(int n_states, int obs_dtype, const smf_hmm_group* groups_host, int n_groups,
+                        double* params, int max_iter, double tol, double eps, int update_mask, double* hist,
+                        int32_t* n_iter, int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+  return grouped_fit_run(SMF_FIT_PHASE_ALL, n_states, obs_dtype, groups_host, n_groups, params, 0, max_iter, tol, eps,
+                         update_mask, hist, n_iter, status, nullptr, workspace, workspace_bytes, stream);
+}
+
+int smf_hmm_grouped_fit_step(int phase, int n_states, int obs_dtype, const smf_hmm_group* groups_host, int n_groups,
+                             double* params, int iter, int max_iter, double tol, double eps, int update_mask,
+                             double* hist, int32_t* n_iter, int32_t* status, double* stats, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  if (phase != SMF_FIT_PHASE_BEGIN && phase != SMF_FIT_PHASE_ESTEP && phase != SMF_FIT_PHASE_MSTEP) return SMF_ERR_BAD_ARG;
+  if (stats == nullptr) return SMF_ERR_BAD_ARG;
+  return grouped_fit_run(phase, n_states, obs_dtype, groups_host, n_groups, params, iter, max_iter, tol, eps, update_mask,
+                         hist, n_iter, status, stats, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

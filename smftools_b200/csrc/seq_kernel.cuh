@@ -848,6 +848,10 @@ __host__ __device__ inline bool seq_cadence4_ok(const double* lt, const double* 
   return 2.0 * logg + 5.0 * logf >= -64.0;
 }
 
+constexpr int SEQ_MSTEP_ALL = 0;
+constexpr int SEQ_MSTEP_REDUCE_ONLY = 1;
+constexpr int SEQ_MSTEP_UPDATE_ONLY = 2;
+
 // Per-group EM bookkeeping of a grouped fit, all in device memory.
 struct SeqFitState {
   double* params;   // [G][K + K*K + K]: start | trans | emission (fp64, the reference's parameter layout)
@@ -860,6 +864,8 @@ struct SeqFitState {
   const SeqGroup* groups;   // [G] device group table
   const double* partials;   // [n_items][S] per-item statistics of the E-step
   int n_groups, S, max_iter, iter;  // iter < 0: build the tables of the initial parameters only
+  int what;                         // SEQ_MSTEP_*: reduce + update (one process), or the two halves separately so
+                                    // that the caller can all-reduce stats[G][S] over ranks in between
   double eps, tol;
   int update_start, update_trans, update_emission;
 };
@@ -872,8 +878,13 @@ template <int K>
 __global__ void __launch_bounds__(256) seq_mstep_kernel(const __grid_constant__ SeqFitState f) {
   const int g = blockIdx.x;
   constexpr int KK = K * K;
-  if (f.iter >= 0) {
-    if (f.active[g] == 0) return;  // uniform across the CTA
+  if (f.iter >= 0 && f.what != SEQ_MSTEP_UPDATE_ONLY) {
+    if (f.active[g] == 0) {
+      // a stopped group contributes nothing any more (its slot of an all-reduced statistics matrix must be defined)
+      if (f.what == SEQ_MSTEP_REDUCE_ONLY)
+        for (int sidx = threadIdx.x; sidx < f.S; sidx += blockDim.x) f.stats[(size_t)g * f.S + sidx] = 0.0;
+      return;  // uniform across the CTA
+    }
     __shared__ double red[256];
     const SeqGroup grp = f.groups[g];
     const long long n_items = (grp.N + kSeqThreads - 1) / kSeqThreads;
@@ -890,7 +901,7 @@ __global__ void __launch_bounds__(256) seq_mstep_kernel(const __grid_constant__ 
       __syncthreads();
     }
   }
-  if (threadIdx.x != 0) return;
+  if (threadIdx.x != 0 || f.what == SEQ_MSTEP_REDUCE_ONLY) return;
   double* p = f.params + (size_t)g * (K + KK + K);
   double* start = p;
   double* trans = p + K;

@@ -42,6 +42,36 @@ def deal_groups(costs: Sequence[float], world_size: int) -> List[List[int]]:
     return [sorted(o) for o in owned]
 
 
+def partition_reads(n_reads: Sequence[int], n_pos: Sequence[int], world_size: int) -> List[List[Tuple[int, int, int]]]:
+    """Balanced alternative to ``deal_groups`` for groups that are large next to a rank's share: lay the groups end to
+    end on a cost axis (cost of a read = its length), cut the axis into ``world_size`` equal pieces and give rank r the
+    reads inside piece r.  Returns, per rank, ``(group, lo, hi)`` read ranges in group order; a group that crosses a
+    cut is read-sharded over the ranks on either side (its statistics are then all-reduced: ``fit_groups(...,
+    process_group=...)``).  Every read is owned by exactly one rank; loads differ by at most one read per cut."""
+    world_size = int(world_size)
+    costs = [int(n) * int(l) for n, l in zip(n_reads, n_pos)]
+    total = sum(costs)
+    out: List[List[Tuple[int, int, int]]] = [[] for _ in range(world_size)]
+    if total == 0:
+        return out
+    cuts = [(total * r) // world_size for r in range(world_size + 1)]
+    c0 = 0
+    for g, (n, l) in enumerate(zip(n_reads, n_pos)):
+        n, l = int(n), int(l)
+        c1 = c0 + n * l
+        for r in range(world_size):
+            lo_c, hi_c = max(cuts[r], c0), min(cuts[r + 1], c1)
+            if lo_c >= hi_c:
+                continue
+            # read i of the group covers [c0 + i*l, c0 + (i+1)*l): it belongs to the piece that holds its first position
+            lo = -(-(lo_c - c0) // l)
+            hi = -(-(hi_c - c0) // l)
+            if hi > lo:
+                out[r].append((g, lo, hi))
+        c0 = c1
+    return out
+
+
 def pack_parameters(models) -> np.ndarray:
     """[G, K + K*K + K] fp64: start | trans | emission of every model (the layout of the C-ABI)."""
     rows = []
@@ -167,14 +197,20 @@ class _GroupTable:
 
 def fit_groups(models, obs_list, *, max_iter: int = 50, tol: float = 1e-5, update_start: bool = True,
                update_trans: bool = True, update_emission: bool = True, device=None,
-               return_status: bool = False):
+               return_status: bool = False, process_group=None, sharded: bool = False):
     """Baum-Welch fit of every ``models[g]`` on ``obs_list[g]`` (``BaseHMM.fit`` semantics per group:
     HMM.py:724-781, 1518-1630) in one device-resident loop.  The models are updated in place; returns the
     per-group log-likelihood histories (and, with ``return_status``, the per-group SMF_FIT_* codes).
 
     ``obs_list[g]``: (N_g, L_g) ``CodedU8`` / coded uint8 device tensor, or float matrix with NaN = missing.
     A group whose parameters leave the dynamic range of the scaled fp32 kernels is finished through the
-    model's own ``fit`` (same result as fitting it alone)."""
+    model's own ``fit`` (same result as fitting it alone).
+
+    ``sharded=True`` (or an explicit ``process_group``): the reads of the groups are sharded over the ranks of the
+    process group (``partition_reads``).  Every rank passes ALL groups in the same order, each with its own shard of
+    that group's reads (possibly zero rows); per iteration the ``[G, S]`` statistics matrix is sum-all-reduced (NCCL,
+    stream-ordered: still no host round trip) between the device E-step and the device M-step, so every rank ends
+    with bit-identical parameters for every group."""
     K, eps = _check_models(models)
     if len(models) != len(obs_list):
         raise ValueError("models and obs_list differ in length")
@@ -198,9 +234,28 @@ def fit_groups(models, obs_list, *, max_iter: int = 50, tol: float = 1e-5, updat
             raise ValueError("smf_hmm_grouped_workspace_bytes rejected the group table")
         ws = torch.empty((need,), dtype=torch.uint8, device=device)
         mask = (1 if update_start else 0) | (2 if update_trans else 0) | (4 if update_emission else 0)
-        rc = lib.smf_hmm_grouped_fit(K, tab.obs_dtype, tab.arr, G, _ptr(params), max_iter, float(tol), eps, mask,
-                                     _ptr(hist), _ptr(n_iter), _ptr(status), _ptr(ws), need, _stream_ptr(device))
-        _lib.check(rc, "smf_hmm_grouped_fit")
+        if sharded or process_group is not None:
+            import torch.distributed as dist
+
+            S_len = K + K * K + 2 * K + 1
+            stats = torch.zeros((G, S_len), dtype=torch.float64, device=device)
+
+            def step(phase, it):
+                rc = lib.smf_hmm_grouped_fit_step(phase, K, tab.obs_dtype, tab.arr, G, _ptr(params), it, max_iter,
+                                                  float(tol), eps, mask, _ptr(hist), _ptr(n_iter), _ptr(status),
+                                                  _ptr(stats), _ptr(ws), need, _stream_ptr(device))
+                _lib.check(rc, "smf_hmm_grouped_fit_step")
+
+            step(_lib.FIT_PHASE_BEGIN, 0)
+            for it in range(max_iter):
+                step(_lib.FIT_PHASE_ESTEP, it)
+                if dist.is_available() and dist.is_initialized():
+                    dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=process_group)
+                step(_lib.FIT_PHASE_MSTEP, it)
+        else:
+            rc = lib.smf_hmm_grouped_fit(K, tab.obs_dtype, tab.arr, G, _ptr(params), max_iter, float(tol), eps, mask,
+                                         _ptr(hist), _ptr(n_iter), _ptr(status), _ptr(ws), need, _stream_ptr(device))
+            _lib.check(rc, "smf_hmm_grouped_fit")
         # one read-back for the whole fit
         params_h = params.cpu().numpy()
         hist_h = hist.cpu().numpy()
@@ -216,11 +271,17 @@ def fit_groups(models, obs_list, *, max_iter: int = 50, tol: float = 1e-5, updat
 
             X = CodedU8(t) if t.dtype == torch.uint8 else t
             m._host_loop_only = True  # the general path: host M-step, kernels with a finer rescale cadence
+            was = (m.distributed, m.process_group)
+            if sharded or process_group is not None:
+                # every rank reaches this point for the same groups (the M-step is replicated): the host loop
+                # all-reduces the statistics of the shards like the device loop did
+                m.distributed, m.process_group = True, process_group
             try:
                 out.append(m.fit(X, max_iter=max_iter, tol=tol, device=device, update_start=update_start,
                                  update_trans=update_trans, update_emission=update_emission))
             finally:
                 m._host_loop_only = False
+                m.distributed, m.process_group = was
         else:
             out.append([float(v) for v in hist_h[g, :int(n_h[g])]])
     if return_status:

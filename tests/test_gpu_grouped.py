@@ -199,3 +199,75 @@ def test_many_small_groups_one_launch():
         q, h_ref = O.fit(X.astype(np.float64), p, max_iter=4, tol=0.0)
         np.testing.assert_allclose(hists[g], h_ref, rtol=1e-6)
         assert np.abs(params_of_model(models[g]).emission.reshape(-1) - q.emission.reshape(-1)).max() <= 1e-4
+
+
+@pytest.mark.parametrize("K", [2, 4])
+def test_stepwise_fit_of_read_sharded_groups_equals_the_whole_fit(K):
+    """smf_hmm_grouped_fit_step: two 'ranks' (two workspaces in this process) each hold a shard of every group's reads
+    -- one of them an empty shard of one group -- and the caller sums the two statistics matrices between the E-step
+    and the M-step, which is what the NCCL all-reduce does across GPUs.  Both ranks must end with the parameters,
+    histories and stop decisions of the unsharded grouped fit (and of the oracle)."""
+    from smftools_b200 import _lib
+    from smftools_b200.engine import _ptr, _stream_ptr
+
+    dev = torch.device("cuda")
+    gs = _groups(K, False, 4000 + K)
+    G = len(gs)
+    cuts = [max(0, min(X.shape[0], (X.shape[0] * (3 + g)) // 7)) for g, (X, _) in enumerate(gs)]
+    cuts[3] = 0  # the one-read group lives entirely on rank 1: rank 0 holds an empty shard
+    tol, max_iter = 1e-4, 9
+    whole = [model_from_params(p) for _, p in gs]
+    h_whole, st_whole = grouped.fit_groups(whole, [S.CodedU8(_code(X)) for X, _ in gs], max_iter=max_iter, tol=tol,
+                                           return_status=True)
+    lib = _lib.load()
+    S_len = K + K * K + 2 * K + 1
+    ranks = []
+    for r in range(2):
+        shards = [S.CodedU8(torch.from_numpy(_code(X[:c] if r == 0 else X[c:])).to(dev)) for (X, _), c in zip(gs, cuts)]
+        tab = grouped._GroupTable(shards, dev)
+        need = int(lib.smf_hmm_grouped_workspace_bytes(K, tab.arr, G, 1))
+        assert need > 0
+        st = dict(tab=tab, need=need, ws=torch.empty((need,), dtype=torch.uint8, device=dev),
+                  params=torch.from_numpy(grouped.pack_parameters([model_from_params(p) for _, p in gs])).to(dev),
+                  hist=torch.zeros((G, max_iter), dtype=torch.float64, device=dev),
+                  n_iter=torch.zeros((G,), dtype=torch.int32, device=dev),
+                  status=torch.zeros((G,), dtype=torch.int32, device=dev),
+                  stats=torch.zeros((G, S_len), dtype=torch.float64, device=dev))
+        ranks.append(st)
+
+    def step(st, phase, it):
+        rc = lib.smf_hmm_grouped_fit_step(phase, K, st["tab"].obs_dtype, st["tab"].arr, G, _ptr(st["params"]), it, max_iter, tol,
+                                          1e-8, 7, _ptr(st["hist"]), _ptr(st["n_iter"]), _ptr(st["status"]), _ptr(st["stats"]),
+                                          _ptr(st["ws"]), st["need"], _stream_ptr(dev))
+        _lib.check(rc, "smf_hmm_grouped_fit_step")
+
+    for st in ranks:
+        step(st, _lib.FIT_PHASE_BEGIN, 0)
+    for it in range(max_iter):
+        for st in ranks:
+            step(st, _lib.FIT_PHASE_ESTEP, it)
+        total = ranks[0]["stats"] + ranks[1]["stats"]  # the all-reduce
+        for st in ranks:
+            st["stats"].copy_(total)
+            step(st, _lib.FIT_PHASE_MSTEP, it)
+    torch.cuda.synchronize()
+    for k in ("params", "hist", "n_iter", "status"):
+        assert torch.equal(ranks[0][k], ranks[1][k]), f"ranks disagree on {k}"  # deterministic replicated M-step
+    n_it = ranks[0]["n_iter"].cpu().numpy()
+    hist = ranks[0]["hist"].cpu().numpy()
+    params = ranks[0]["params"].cpu().numpy()
+    assert [int(v) for v in ranks[0]["status"].cpu().numpy()] == st_whole
+    for g, ((X, p), m, h) in enumerate(zip(gs, whole, h_whole)):
+        if st_whole[g] == grouped.FIT_HANDED_BACK:
+            # fit_groups finished this group through model.fit; the raw entry point reports where it stopped
+            n = int(n_it[g])
+            assert 0 < n <= len(h)
+            np.testing.assert_allclose(hist[g, :n], h[:n], rtol=1e-6, atol=1e-5)
+            continue
+        assert int(n_it[g]) == len(h)
+        # the shards put different reads into a CTA, so the fp32 partial sums (flushed into fp64 every 8 chunks) differ
+        np.testing.assert_allclose(hist[g, :len(h)], h, rtol=1e-6, atol=1e-5)
+        np.testing.assert_allclose(params[g], grouped.pack_parameters([m])[0], rtol=0, atol=1e-5)
+        q, h_ref = O.fit(X.astype(np.float64), p, max_iter=max_iter, tol=tol)
+        assert len(h_ref) == len(h)
+        np.testing.assert_allclose(h, h_ref, rtol=1e-6, atol=1e-5)

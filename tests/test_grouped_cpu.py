@@ -30,6 +30,35 @@ def test_deal_groups_is_lpt_and_covers_every_group_once():
     assert deal_groups([2, 2, 2, 2], 2) == [[0, 2], [1, 3]]
 
 
+def test_partition_reads_covers_every_read_once_and_balances():
+    from smftools_b200.grouped import partition_reads
+
+    rng = np.random.default_rng(3)
+    for world in (1, 2, 3, 8):
+        n_reads = [int(x) for x in rng.integers(1, 5000, size=16)]
+        n_pos = [int(x) for x in rng.integers(2000, 20000, size=16)]
+        parts = partition_reads(n_reads, n_pos, world)
+        assert len(parts) == world
+        seen = {g: [] for g in range(16)}
+        loads = []
+        for r in parts:
+            loads.append(sum((hi - lo) * n_pos[g] for g, lo, hi in r))
+            assert [g for g, _, _ in r] == sorted(g for g, _, _ in r)  # group order, contiguous on the cost axis
+            for g, lo, hi in r:
+                assert 0 <= lo < hi <= n_reads[g]
+                seen[g].append((lo, hi))
+        for g, ranges in seen.items():
+            ranges.sort()
+            assert ranges[0][0] == 0 and ranges[-1][1] == n_reads[g]
+            assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))  # disjoint, no gaps
+        total = sum(n * l for n, l in zip(n_reads, n_pos))
+        assert sum(loads) == total
+        assert max(loads) - min(loads) <= 2 * max(n_pos)  # within one read per cut
+    assert partition_reads([10, 4, 7, 1], [100, 50, 200, 1000], 3) == [[(0, 0, 10), (1, 0, 4)], [(2, 0, 6)],
+                                                                       [(2, 6, 7), (3, 0, 1)]]
+    assert partition_reads([3], [7], 4) == [[(0, 0, 1)], [(0, 1, 2)], [(0, 2, 3)], []]
+
+
 def test_pack_unpack_round_trip_keeps_dtype():
     import smftools_b200 as S
     from smftools_b200.grouped import pack_parameters, unpack_parameters
@@ -67,8 +96,10 @@ def test_grouped_workspace_bytes_validates_the_group_table():
     arr[1].row_stride = 1999  # shorter than the read
     assert lib.smf_hmm_grouped_workspace_bytes(4, arr, 2, 1) == 0
     arr[1].row_stride = 2000
-    arr[0].n_reads = 0
+    arr[0].n_reads = -1
     assert lib.smf_hmm_grouped_workspace_bytes(4, arr, 2, 1) == 0
+    arr[0].n_reads = 0  # an empty shard of a read-sharded group is legal
+    assert 0 < lib.smf_hmm_grouped_workspace_bytes(4, arr, 2, 1) < fit
     assert lib.smf_hmm_grouped_workspace_bytes(5, arr, 2, 1) == 0
     assert lib.smf_hmm_grouped_workspace_bytes(4, None, 0, 1) == 0
     # null outputs / workspace are rejected before anything touches the device
