@@ -330,7 +330,9 @@ static int plan_fb2(int K, int64_t L64, bool stats, int S, int es, bool want_gam
       return SMF_OK;
     return plan_fb2_chunk(K, second, L64, stats, S, es, want_gamma_one, want_states, max_smem, a, plan, true);
   }
-  const bool can33 = (K != 3);
+  // K = 3 with chunk 33 spills heavily; so does the K = 4 E-step (3 KB of stack: 12-16e9 read-positions/s at 9-12 kb
+  // against 22-41e9 for the generic kernel and 44-65e9 for the two-kernel path, profiles/r02_k4_long_estep.txt)
+  const bool can33 = (K != 3) && !(K == 4 && stats);
   // lane utilisation of the two chunk lengths (threads are allocated in whole warps)
   auto lane_eff = [&](int ch) {
     const long long tact = (L64 + ch - 1) / ch;
@@ -431,8 +433,11 @@ static bool walk_eligible(const smf_hmm_tables* t, int64_t N, int64_t L, bool st
   const bool off_chip = L > (int64_t)33 * fb2w_max_threads_c(K, false);
   if (K < 3) return !stats && off_chip && N >= kWalkMinReads;
   if (env_walk == 1) return true;
-  if (N < kWalkMinReads) return false;
-  if (stats) return K == 4 || L > (int64_t)17 * fb2_max_threads_c(K, true);
+  // E-step beyond the single kernel's chunk-17 reach (only the generic kernel is left there): the walk already pays
+  // off from ~3,000 reads (K = 4, 9-16 kb, 4,000 reads: 44-46e9 read-positions/s vs 22-41e9; 1,000 reads: 17e9 vs 22-41e9)
+  const bool beyond17 = L > (int64_t)17 * fb2_max_threads_c(K, true);
+  if (N < ((stats && beyond17) ? 3000 : kWalkMinReads)) return false;
+  if (stats) return K == 4 || beyond17;
   // posterior: K = 4 up to ~6 kb and beyond the single kernel's chunk-17 range (8.7 kb; 0.31 vs 0.22 of
   // HBM peak at 9 kb); K = 3 beyond the single kernel's reach (13.4 kb with chunk 21): 0.27 vs 0.10
   // (generic kernel) at 16 kb
