@@ -99,6 +99,8 @@ const char* smf_hmm_strerror(int code);
  *            rows of a multiple of 4 (uint8: 16) positions runs on the direct kernel (no shared-memory staging) where
  *            it measured faster: uint8 code, K = 2, K = 4, and K = 3 up to 2,048 positions; 0 never / 1 wherever it
  *            applies.  Both kernels make bit-identical decisions.
+ *   "generic" 0 (default) / 1: route every forward-backward call to the generic kernel (testing and A/B timing; env
+ *            SMF_HMM_FORCE_GENERIC=1 sets the initial value).
  * Returns SMF_ERR_BAD_ARG for an unknown key or value.
  */
 int smf_hmm_set_option(const char* key, int value);

@@ -103,10 +103,11 @@ int cached_occupancy(const void* kern, int block, int smem_bytes, int* occ_out) 
 }
 
 // SMF_HMM_FORCE_GENERIC=1 routes everything through the generic kernel (testing / A-B timing).
-static const bool g_force_generic = [] {
+// smf_hmm_set_option("generic", 0 / 1) does the same at run time.
+static std::atomic<bool> g_force_generic{[] {
   const char* e = getenv("SMF_HMM_FORCE_GENERIC");
   return e != nullptr && e[0] == '1';
-}();
+}()};
 
 static int check_tables(const smf_hmm_tables* t) {
   if (t == nullptr) return SMF_ERR_BAD_ARG;
@@ -431,7 +432,11 @@ static bool walk_eligible(const smf_hmm_tables* t, int64_t N, int64_t L, bool st
   if (env_walk == 2) return !stats || K >= 3;  // any-length sweep kernels wherever they exist
   // reads that do not fit on chip: boundary walk + warp-independent sweeps (post_sweep_kernel), any K
   const bool off_chip = L > (int64_t)33 * fb2w_max_threads_c(K, false);
-  if (K < 3) return !stats && off_chip && N >= kWalkMinReads;
+  // reads that do not fit on chip have only the segmented generic kernel as the alternative: the walk pays off from
+  // ~3,000 reads (8,000 x 20 kb: 2.1 vs 3.2 ms for K = 3, 2.4 vs 5.8 ms for K = 4; 1,000 reads: 1.1 vs 0.4 ms)
+  const int64_t post_reach = (int64_t)(K == 3 ? 21 : 33) * fb2_max_threads_c(K, false);  // longest single-kernel read
+  if (!stats && (off_chip || L > post_reach) && N >= 3000) return true;
+  if (K < 3) return false;
   if (env_walk == 1) return true;
   // E-step beyond the single kernel's chunk-17 reach (only the generic kernel is left there): the walk already pays
   // off from ~3,000 reads (K = 4, 9-16 kb, 4,000 reads: 44-46e9 read-positions/s vs 22-41e9; 1,000 reads: 17e9 vs 22-41e9)
@@ -485,10 +490,14 @@ static std::atomic<int> g_vit_mode{[] { const char* e = getenv("SMF_VIT"); retur
 static std::atomic<int> g_seq_mode{[] { const char* e = getenv("SMF_SEQ"); return e ? atoi(e) : -1; }()};
 // Reads per launch from which the reads alone fill the machine (148 SMs x 4-5 CTAs x 128 threads); measured
 // break-even against the chunk-parallel kernels in profiles/r02_seq_estep.txt.
-static int64_t seq_min_reads(int K) {
+// (profiles/r02_seq_estep.txt, r02_policy_audit.txt: the chunk-parallel kernels lose ground with the read length, so
+// long reads switch earlier -- 30,000 x 12 kb: 1.3-1.6x faster for every K)
+static int64_t seq_min_reads(int K, int64_t L) {
   static const int env = [] { const char* e = getenv("SMF_SEQ_MIN_READS"); return e ? atoi(e) : 0; }();
   if (env > 0) return env;
-  return K == 2 ? 98304 : 49152;
+  if (L >= 8192) return 24576;
+  if (K == 2) return L >= 2000 ? 65536 : 98304;
+  return 49152;
 }
 // shape-only test (used for workspace sizing); the launch additionally needs an eligible dtype / alignment
 static bool seq_shape_eligible(const smf_hmm_tables* t, int64_t N, int64_t L) {
@@ -498,7 +507,7 @@ static bool seq_shape_eligible(const smf_hmm_tables* t, int64_t N, int64_t L) {
   if (L < 2 || L > (1 << 24)) return false;
   if (rescale_cadence(t) != 4) return false;
   if (mode == 1) return true;
-  return N >= seq_min_reads(t->n_states);
+  return N >= seq_min_reads(t->n_states, L);
 }
 // rows on 16-byte boundaries whose 16-element loads stay inside the buffer: vector loads
 static bool seq_rows_aligned(int64_t L, int obs_dtype, const void* obs) {
@@ -774,6 +783,11 @@ int smf_hmm_set_option(const char* key, int value) {
     g_short_mode = value;
     return SMF_OK;
   }
+  if (strcmp(key, "generic") == 0) {
+    if (value < 0 || value > 1) return SMF_ERR_BAD_ARG;
+    g_force_generic = value != 0;
+    return SMF_OK;
+  }
   if (strcmp(key, "vit") == 0) {
     if (value < -1 || value > 1) return SMF_ERR_BAD_ARG;
     g_vit_mode = value;
@@ -857,8 +871,13 @@ int smf_hmm_posterior(const smf_hmm_tables* tab, const void* obs, int obs_dtype,
   const int cadence = rescale_cadence(tab);
   if (tab->n_channels == 1 && tab->n_bins == 1 && !g_force_generic && cadence == 4 &&
       fb2_aligned(obs, obs_dtype, gamma, tab->n_states, gamma_state)) {
+    // large K = 4 batches: the sequential kernels also beat the bundled short-read kernel (10^6 x 100: 0.90 vs 1.20 ms)
+    const bool seq_first = tab->n_states == 4 && g_short_mode != 1 && workspace != nullptr &&
+                           seq_post_shape_eligible(tab, n_reads, n_pos) &&
+                           seq_launch_eligible(tab, n_reads, n_pos, obs_dtype, obs, true) &&
+                           workspace_bytes >= seq_ws_bytes(tab->n_states, n_reads, n_pos);
     // short reads: several reads per warp
-    if (g_short_mode != 0 && (g_short_mode == 1 || n_pos <= short_max_len(tab->n_states))) {
+    if (!seq_first && g_short_mode != 0 && (g_short_mode == 1 || n_pos <= short_max_len(tab->n_states))) {
       ShortArgs sa;
       memset(&sa, 0, sizeof(sa));
       if (plan_short(tab->n_states, n_pos, obs_dtype, gamma != nullptr && gamma_state < 0,
