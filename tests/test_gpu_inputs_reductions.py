@@ -217,3 +217,31 @@ def test_interval_records_feed_the_interval_consumer():
         row[:first[i]] = np.nan
         row[last[i] + 1:] = np.nan
         assert sizes_c[i] == IO.extract_intervals_from_row(row, full.astype(float))[0]
+
+
+def test_fit_recodes_binary_float_observations_once():
+    """fit() of 0 / 1 / NaN floats (the reference's dtype) re-codes them as the uint8 code for all iterations;
+    probabilistic calls stay floats; the fitted model equals the oracle's either way."""
+    import smftools_b200 as S
+    from helpers import params_of_model
+    from oracle import hmm_oracle as O
+
+    dev = torch.device("cuda")
+    for C, arch in ((1, "single"), (2, "multi")):
+        Xb = O.synth_reads(120, 1500, 3, 41, prob=False, nan_rate=0.3, n_channels=C)
+        Xp = O.synth_reads(120, 1500, 3, 42, prob=True, nan_rate=0.3, n_channels=C)
+        res_b = S.BaseHMM._code_binary_resident([torch.from_numpy(Xb.astype(np.float64)).to(dev)])
+        res_p = S.BaseHMM._code_binary_resident([torch.from_numpy(Xp.astype(np.float32)).to(dev)])
+        assert res_b[0].dtype == torch.uint8 and tuple(res_b[0].shape) == Xb.shape
+        assert np.array_equal(res_b[0].cpu().numpy(), np.where(np.isnan(Xb), 255, Xb).astype(np.uint8))
+        assert res_p[0].dtype == torch.float32
+        cfg = {"hmm_n_states": 3}
+        if C > 1:
+            cfg["hmm_n_channels"] = C
+        for X in (Xb, Xp):
+            m = S.create_hmm(cfg, arch=arch)
+            p0 = params_of_model(m)
+            hist = m.fit(X.astype(np.float64), max_iter=4, tol=0.0)
+            q, h_ref = O.fit(X.astype(np.float64), p0, max_iter=4, tol=0.0)
+            np.testing.assert_allclose(hist, h_ref, rtol=1e-6)
+            assert np.abs(params_of_model(m).emission - q.emission).max() <= 1e-4
