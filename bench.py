@@ -467,6 +467,8 @@ def stream_workload(name, ctx, steps_cap=None):
                "value": positions / (ms * 1e-3), "unit": "read-positions/s", "ms_total": ms,
                "gpu_launches_rank0": launches,
                "roofline": roofline_of(op, K, es, per_rank_positions, total_ms)}
+        rec["roofline"]["traffic"] = ncu_traffic(name)  # DRAM bytes per chunk launch from the committed ncu pass, or None
+        rec["roofline"]["algorithmic_bytes_per_launch"] = ALGO_BYTES[op](K, 1, es) * float(chunk) * L
         if op == "viterbi":
             rec["intervals_rank0"] = n_intervals
         rec["parity"] = parity_record(op, K, first, tables, feat)
