@@ -1519,18 +1519,21 @@ inline size_t seq_tables_bytes(int K) {
 //   SeqGroup[G] | item_group[n_items] | FbTables<K>[G] | active[G] | stats[G][S] | partials[n_items][S] (fit)
 //   | per group: log-likelihood [N] (when the caller gave none) and alpha checkpoints [Tact][N][KP]
 // With `out` != nullptr the device group table and the item table are also written (host copies).
+// obs_dtype < 0: sizing only (the workspace size does not depend on the element type; strides are not checked).
 int grouped_plan(int K, int obs_dtype, const smf_hmm_group* gh, int G, bool fit, GroupedPlan* pl, char* ws_base,
                  SeqGroup* out_groups, int* out_item_group) {
   if (K < 2 || K > SMF_MAX_STATES || gh == nullptr || G < 1) return SMF_ERR_BAD_ARG;
-  if (obs_dtype != SMF_OBS_U8 && obs_dtype != SMF_OBS_F32) return SMF_ERR_BAD_ARG;
+  const bool sizing_only = obs_dtype < 0;
+  if (!sizing_only && obs_dtype != SMF_OBS_U8 && obs_dtype != SMF_OBS_F32) return SMF_ERR_BAD_ARG;
   const int KP = (K == 2) ? 2 : 4;
   const int S = K + K * K + 2 * K + 1;
   long long n_items = 0;
   for (int g = 0; g < G; ++g) {
     const smf_hmm_group& q = gh[g];
     if (q.n_reads < 0 || q.n_pos < 1 || q.n_pos > (1 << 24) || (q.n_reads > 0 && q.obs == nullptr)) return SMF_ERR_BAD_ARG;
-    if (q.row_stride < q.n_pos || (q.row_stride % (obs_dtype == SMF_OBS_U8 ? 16 : 4)) != 0) return SMF_ERR_ALIGN;
-    if (reinterpret_cast<uintptr_t>(q.obs) & 15u) return SMF_ERR_ALIGN;
+    if (q.row_stride < q.n_pos) return SMF_ERR_BAD_ARG;
+    if (!sizing_only && (q.row_stride % (obs_dtype == SMF_OBS_U8 ? 16 : 4)) != 0) return SMF_ERR_ALIGN;
+    if (!sizing_only && (reinterpret_cast<uintptr_t>(q.obs) & 15u)) return SMF_ERR_ALIGN;
     if (!fit && (q.gamma != nullptr || q.states != nullptr)) {
       if (q.out_stride < q.n_pos || (q.out_stride & 3)) return SMF_ERR_ALIGN;
       if ((reinterpret_cast<uintptr_t>(q.gamma) & 15u) || (reinterpret_cast<uintptr_t>(q.states) & 3u)) return SMF_ERR_ALIGN;
@@ -1614,9 +1617,7 @@ extern "C" {
 
 size_t smf_hmm_grouped_workspace_bytes(int n_states, const smf_hmm_group* groups_host, int n_groups, int fit) {
   GroupedPlan pl;
-  // the dtype only decides the row-stride rule; sizes do not depend on it
-  int rc = grouped_plan(n_states, SMF_OBS_F32, groups_host, n_groups, fit != 0, &pl, nullptr, nullptr, nullptr);
-  if (rc == SMF_ERR_ALIGN) rc = grouped_plan(n_states, SMF_OBS_U8, groups_host, n_groups, fit != 0, &pl, nullptr, nullptr, nullptr);
+  const int rc = grouped_plan(n_states, -1, groups_host, n_groups, fit != 0, &pl, nullptr, nullptr, nullptr);
   return rc == SMF_OK ? pl.total : 0;
 }
 
