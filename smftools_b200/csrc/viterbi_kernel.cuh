@@ -394,23 +394,24 @@ __global__ void __launch_bounds__(128) viterbi_direct_kernel(const __grid_consta
           double nd[K];
 #pragma unroll
           for (int jn = 0; jn < K; ++jn) {
+            // first-index maximum; the back-pointer is selected as an already shifted constant (j and jn are
+            // compile-time here), so a decision costs one fp64 compare, two 32-bit selects of the value and one of the code
             double best = __dadd_rn(delta[0], lA[0][jn]);
-            unsigned arg = 0;
+            unsigned code = 0u;
 #pragma unroll
             for (int i = 1; i < K; ++i) {
               const double cnd = __dadd_rn(delta[i], lA[i][jn]);
-              if (cnd > best) {
-                best = cnd;
-                arg = i;
-              }
+              const bool p = cnd > best;
+              best = p ? cnd : best;
+              code = p ? ((unsigned)i << (2 * jn + 8 * (j & 3))) : code;
             }
             nd[jn] = __dadd_rn(best, logB[jn]);
-            packed |= arg << (2 * jn);
+            packed |= code;
           }
 #pragma unroll
           for (int k = 0; k < K; ++k) delta[k] = nd[k];
         }
-        bpw[j >> 2] |= packed << (8 * (j & 3));
+        bpw[j >> 2] |= packed;
       };
       if (c > 0 && len == kVitCH) {
 #pragma unroll
