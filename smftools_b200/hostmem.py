@@ -203,19 +203,7 @@ class HostPool:
         return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
     def empty_many(self, specs: Dict[str, Tuple[Sequence[int], object]]) -> Dict[str, np.ndarray]:
-        """Several arrays at once.  Blocks that have to be created (cold pool) are created concurrently: page-locking
-        one block (a single driver call) overlaps the first-touch of the next."""
-        items = list(specs.items())
-        big = [i for i, (_, (shape, dt)) in enumerate(items)
-               if int(np.prod(tuple(int(x) for x in shape), dtype=np.int64)) * np.dtype(dt).itemsize >= (64 << 20)]
-        if len(big) < 2:
-            return {nm: self.empty(shape, dt) for nm, (shape, dt) in items}
-        out: Dict[str, np.ndarray] = {}
-        with ThreadPoolExecutor(max_workers=min(4, len(big)), thread_name_prefix="smf-pin") as ex:
-            futs = {i: ex.submit(self.empty, items[i][1][0], items[i][1][1]) for i in big}
-            for i, (nm, (shape, dt)) in enumerate(items):
-                out[nm] = futs[i].result() if i in futs else self.empty(shape, dt)
-        return out
+        return {nm: self.empty(shape, dt) for nm, (shape, dt) in specs.items()}
 
 
 _pool: Optional[HostPool] = None
