@@ -72,6 +72,16 @@ def _bins_arg(bins: Optional[torch.Tensor], tables: _lib.HostTables, L: int) -> 
     return int(bins.data_ptr())
 
 
+def _narrow_f64(obs: torch.Tensor, tables: _lib.HostTables) -> torch.Tensor:
+    """Multi-channel / distance-binned models: float64 observations are narrowed to float32 on the device first.
+    Every forward-backward kernel converts an observation to float32 when it reads it (the posterior tolerance is an
+    fp32 one), so the results are the same -- but only the float32 / uint8 rows have the fast-path instantiations of
+    these two model families (a float64 row would run on the generic kernel, 3-4x slower)."""
+    if obs.dtype == torch.float64 and (tables.C > 1 or tables.n_bins > 1):
+        return obs.to(torch.float32)
+    return obs
+
+
 def set_option(key: str, value: int) -> None:
     """Process-wide tuning knob of the library (``smf_hmm_set_option``), e.g. ``set_option("walk", 1)``."""
     _lib.check(_lib.load().smf_hmm_set_option(key.encode(), int(value)), "smf_hmm_set_option")
@@ -102,6 +112,7 @@ def posterior(
     (``use_workspace=False`` withholds it, which selects the single-kernel path).
     """
     lib = _lib.load()
+    obs = _narrow_f64(obs, tables)
     N, L, dt = _obs_args(obs, tables)
     dev = obs.device
     K = tables.K
@@ -154,6 +165,7 @@ def estep(tables: _lib.HostTables, obs: torch.Tensor, bins: Optional[torch.Tenso
           *, out_stats: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Baum-Welch E-step (``smf_hmm_estep``): fp64 statistics vector on the device."""
     lib = _lib.load()
+    obs = _narrow_f64(obs, tables)
     N, L, dt = _obs_args(obs, tables)
     dev = obs.device
     S = stats_len(tables)

@@ -56,7 +56,7 @@ def test_multi_channel_posterior_and_estep_match_oracle(K, C, L, N, prob):
 
 
 @pytest.mark.parametrize("K,C,L,dt", [(4, 2, 300, np.float32), (2, 4, 300, np.float32), (2, 2, 300, np.float64),
-                                      (2, 2, 12000, np.float32)])
+                                      (2, 2, 12000, np.float32), (3, 3, 777, np.float64)])
 def test_shapes_outside_the_multi_fast_path_use_the_generic_kernel(K, C, L, dt):
     from smftools_b200 import engine
 
