@@ -119,11 +119,17 @@ int64_t smf_hmm_max_positions(const smf_hmm_tables* tab, int want_all_states);
  *   gamma       device float [N, L, K] (gamma_state < 0) or [N, L] holding state `gamma_state`; may be NULL
  *   states      device int8 [N, L] = argmax_k gamma (first maximum), may be NULL
  *   loglik      device double [N] = log P(read), may be NULL
- *   workspace   optional device scratch of smf_hmm_workspace_bytes(SMF_OP_POSTERIOR, ...) bytes.
- *               That size is non-zero for large batches of K >= 3 single-channel models: with it
- *               the library runs the two-kernel path (per-read boundary walk + local sweeps,
- *               DESIGN.md section 4) which is faster there.  NULL always works (single-kernel path);
- *               a non-NULL workspace smaller than required is SMF_ERR_WORKSPACE.
+ *   workspace   optional device scratch of smf_hmm_workspace_bytes(SMF_OP_POSTERIOR, ...) bytes (16-byte aligned).
+ *               That size is non-zero where a path that needs scratch is the faster one for the batch: the
+ *               two-kernel path (per-read boundary walk + local sweeps: boundary vectors) for large batches of
+ *               K >= 3 models and for reads beyond the single kernel's reach, the sequential kernels (one thread
+ *               per read: alpha checkpoints, about 1 byte per read-position) for large K = 4 batches, short / very
+ *               long K = 3 reads and K = 2 reads beyond 21 kb (DESIGN.md sections 4.2, 4.7).  NULL always works
+ *               (single-kernel or generic path); a non-NULL workspace smaller than required is SMF_ERR_WORKSPACE.
+ *   Models:     single-channel homogeneous (all K), multi-channel (C = 2, 3; K <= 3) and distance-binned (K <= 3)
+ *               models with float / uint8-coded rows run on the fast-path kernels; everything else (K = 4 or C = 4
+ *               multi-channel, float64 multi-channel rows, models whose emissions / transitions sit at the eps
+ *               clamp) on the generic kernel.  Results do not depend on the path beyond fp32 rounding.
  */
 int smf_hmm_posterior(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int64_t n_reads,
                       int64_t n_pos, const int8_t* bins, float* gamma, int gamma_state,
