@@ -271,3 +271,30 @@ def test_stepwise_fit_of_read_sharded_groups_equals_the_whole_fit(K):
         q, h_ref = O.fit(X.astype(np.float64), p, max_iter=max_iter, tol=tol)
         assert len(h_ref) == len(h)
         np.testing.assert_allclose(h, h_ref, rtol=1e-6, atol=1e-5)
+
+
+@pytest.mark.parametrize("K,prob,seed", [(2, False, 1), (3, True, 2), (4, False, 3), (4, True, 4)])
+def test_random_ragged_groups_including_degenerate_lengths(K, prob, seed):
+    """Seeded random group tables: 24 groups of 1-400 reads x 1-1500 positions (lengths 1, 2, 3, 15-17 and 31-33 forced
+    in), fitted for 3 iterations and decoded in one launch sequence each; a sample is checked against the oracle."""
+    rng = np.random.default_rng(seed)
+    lengths = [1, 2, 3, 15, 16, 17, 31, 32, 33] + [int(x) for x in rng.integers(4, 1500, size=15)]
+    reads = [int(x) for x in rng.integers(1, 400, size=len(lengths))]
+    gs = []
+    for g, (N, L) in enumerate(zip(reads, lengths)):
+        gs.append((O.synth_reads(N, L, K, 9100 + 31 * seed + g, prob=prob, nan_rate=0.3), _perturbed(K, g)))
+    models = [model_from_params(p) for _, p in gs]
+    obs = [S.CodedU8(_code(X)) if not prob else X.astype(np.float32) for X, _ in gs]
+    res = grouped.decode_groups(models, obs, want_loglik=True)
+    hists = grouped.fit_groups(models, obs, max_iter=3, tol=0.0)
+    torch.cuda.synchronize()
+    for g in list(range(9)) + [int(x) for x in rng.choice(np.arange(9, len(gs)), size=4, replace=False)]:
+        X, p = gs[g]
+        g_ref, ll_ref = O.posterior(X.astype(np.float64), p)
+        gam, st, ll = res[g]
+        assert tuple(gam.shape) == g_ref.shape and tuple(st.shape) == g_ref.shape[:2]
+        assert np.abs(gam.cpu().numpy() - g_ref).max() <= 1e-5, (g, X.shape)
+        np.testing.assert_allclose(ll.cpu().numpy(), ll_ref, rtol=1e-6, atol=1e-4)
+        q, h_ref = O.fit(X.astype(np.float64), p, max_iter=3, tol=0.0)
+        np.testing.assert_allclose(hists[g], h_ref, rtol=1e-6, atol=1e-5)
+        assert np.abs(params_of_model(models[g]).emission.reshape(-1) - q.emission.reshape(-1)).max() <= 1e-4
