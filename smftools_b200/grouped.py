@@ -13,8 +13,7 @@ once at the end (``exchange_group_parameters``).
 """
 from __future__ import annotations
 
-import ctypes
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -134,16 +133,15 @@ def _group_obs(X, device) -> Tuple[torch.Tensor, int, int]:
     """Device observation matrix of one group in a layout the kernels accept: uint8 0 / 1 / other = missing code
     (``CodedU8`` or an already-coded device tensor) or float32 with NaN = missing; rows padded to whole 16-byte
     groups.  Returns (tensor [N, stride], L, obs_dtype)."""
-    from .hmm import BaseHMM, CodedU8
+    from .hmm import BaseHMM
 
-    coded = isinstance(X, CodedU8)
     src, numeric_u8 = BaseHMM._as_obs_source(X)
     if src.ndim != 2:
         raise ValueError(f"grouped launches expect X of shape (N, L); got {tuple(src.shape)}")
     if isinstance(src, np.ndarray):
         src = torch.from_numpy(np.ascontiguousarray(src))
     t = src.to(device)
-    if t.dtype == torch.uint8 and numeric_u8 and not coded:
+    if t.dtype == torch.uint8 and numeric_u8:  # plain uint8: the byte value is the observation (HMM.py:694)
         t = t.to(torch.float32)
     elif t.dtype == torch.float64:
         t = t.to(torch.float32)
