@@ -27,6 +27,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, engine, hostmem
+from . import stream as _stream_mod
 
 COVERED_BASE_MASK = "covered_base_mask"  # reference constants.py:141
 
@@ -773,7 +774,8 @@ class BaseHMM(nn.Module):
         (K = 4, 262,144 x 8 kb: 13.4 -> 10.3 ms per iteration).  Probabilistic calls are left as they are."""
         if not isinstance(resident, list) or not resident:
             return resident
-        if any((not t.is_cuda) or t.dtype not in (torch.float32, torch.float64) or t.numel() == 0 for t in resident):
+        if any((not isinstance(t, torch.Tensor)) or (not t.is_cuda) or t.dtype not in (torch.float32, torch.float64)
+               or t.numel() == 0 for t in resident):
             return resident
         dev = resident[0].device
         L = int(resident[0].shape[1])
@@ -1181,7 +1183,7 @@ class BaseHMM(nn.Module):
         ev_cmp = [None, None]
         ev_out = [None, None]
         if fast_final:
-            s_out = torch.cuda.Stream(device)
+            s_out = _stream_mod.side_stream(device, "d2h")
             s_out.wait_event(entry)
             stage64 = [torch.empty((n_f64, rows, n_vars), dtype=torch.float64, device=device) for _ in range(2)]
             stage32 = [torch.empty((max(n_f32, 1), rows, n_vars), dtype=torch.float32, device=device) for _ in range(2)]

@@ -23,6 +23,7 @@ import numpy as np
 import torch
 
 from . import _lib, engine, hostmem
+from . import stream as _stream_mod
 from .hmm import BaseHMM, _alloc_host_layers, _default_cuda_device, _safe_int_coords, _span_inputs
 
 CODE_CLASS_MASK = 0x0F
@@ -179,7 +180,7 @@ def expand_merge_chain_device(
         adata.layers[nm] = arr
     rows = rows_per_step or max(1, min(n_obs, int((256 << 20) // max(8 * len(plan) * n_vars, 1))))
     cur = torch.cuda.current_stream(dev)
-    s_out = torch.cuda.Stream(dev)
+    s_out = _stream_mod.side_stream(dev, "d2h")
     entry = torch.cuda.Event()
     entry.record(cur)
     s_out.wait_event(entry)
@@ -256,7 +257,7 @@ def apply_merges(adata, model, prefix: str, feature_sets: dict, cfg) -> None:
             continue
         rows = _chain_rows(n_obs, n_vars, len(plan), min(BaseHMM.device_chunk_bytes, 1 << 30))
         cur = torch.cuda.current_stream(dev)
-        s_out = torch.cuda.Stream(dev)
+        s_out = _stream_mod.side_stream(dev, "d2h")
         entry = torch.cuda.Event()
         entry.record(cur)
         s_out.wait_event(entry)

@@ -12,12 +12,30 @@ All copies are explicit ``cudaMemcpyAsync`` calls through the C-ABI (``smf_hmm_c
 """
 from __future__ import annotations
 
+import threading
 from typing import List, Optional
 
 import numpy as np
 import torch
 
 from . import engine, hostmem
+
+
+_side_streams: dict = {}
+_side_lock = threading.Lock()
+
+
+def side_stream(device: torch.device, role: str) -> torch.cuda.Stream:
+    """Per-(device, role) copy stream, created once per process: a decode call of a small subset (the reference's
+    regime: ~1000 reads x ~170 sites) should not pay two cudaStreamCreate per call.  Ordering between calls is kept by
+    the entry / completion events every call records anyway."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device(), role)
+    with _side_lock:
+        st = _side_streams.get(key)
+        if st is None:
+            st = torch.cuda.Stream(device)
+            _side_streams[key] = st
+        return st
 
 
 class ChunkUploader:
@@ -38,7 +56,7 @@ class ChunkUploader:
             self.dev_src = None
             self.host = src.detach().numpy() if isinstance(src, torch.Tensor) else np.asarray(src)
         self.tail = tuple(int(s) for s in (src.shape[1:]))
-        self.stream = torch.cuda.Stream(device)
+        self.stream = side_stream(device, "h2d")
         self.ev_in: List[Optional[torch.cuda.Event]] = [None] * nbuf
         self.d_buf: List[Optional[torch.Tensor]] = [None] * nbuf
         self.stage: List[Optional[np.ndarray]] = [None] * nbuf
@@ -96,7 +114,7 @@ def decode_stream(model, src, numeric_u8: bool, tables, bins, use_viterbi: bool,
     rows = max(1, int(chunk_out_bytes // max(per_read_out, 1)))
     rows = min(rows, N)
     cur = torch.cuda.current_stream(device)
-    s_out = torch.cuda.Stream(device)
+    s_out = side_stream(device, "d2h")
     entry = torch.cuda.Event()
     entry.record(cur)
     s_out.wait_event(entry)
