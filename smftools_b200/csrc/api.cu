@@ -1212,6 +1212,46 @@ int smf_hmm_estep(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int
       return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
     }
   }
+  if (fb2_binned_eligible(tab, obs_dtype) && tab->n_states == 2 && !g_force_generic && cadence == 4 && n_pos > 1 &&
+      fb2_aligned(obs, obs_dtype, nullptr, tab->n_states, -1)) {
+    // distance-binned K = 2: per-thread, per-bin transition statistics in shared memory (fb2_kernel<..., BINNED, STATS>)
+    Fb2Args b;
+    Fb2Plan p2;
+    const int lpad = (int)((n_pos + 16) / 17 * 17);
+    const int bins_b = align_up(lpad, 16);
+    const int btab_b = align_up(tab->n_bins * 4 * 4, 16);
+    const int ls0_b = align_up(tab->n_bins * 8, 16);
+    const int xi_stride = tab->n_bins | 1;
+    int block = 0, prc = SMF_ERR_TOO_LONG;
+    for (int round = 0; round < 3; ++round) {  // the accumulator area depends on the CTA size the planner picks
+      memset(&b, 0, sizeof(b));
+      const int sxi_b = block * xi_stride * 16;
+      prc = plan_fb2_chunk(2, 17, n_pos, true, S, obs_elem_size(obs_dtype), false, false, di.max_smem_optin, &b, &p2, false,
+                           false, bins_b + btab_b + ls0_b + sxi_b);
+      if (prc != SMF_OK || p2.block == block) break;
+      block = p2.block;
+      prc = SMF_ERR_TOO_LONG;
+    }
+    if (prc == SMF_OK && block > 0) {
+      b.off_btab = b.off_bins + bins_b;
+      b.off_ls0 = b.off_btab + btab_b;
+      b.off_sxi = b.off_ls0 + ls0_b;
+      b.bins = bins;
+      b.n_bins = tab->n_bins;
+      b.obs = obs;
+      b.N = n_reads;
+      b.L = (int)n_pos;
+      b.gamma_state = -1;
+      b.partials = reinterpret_cast<double*>(workspace);
+      b.S = S;
+      b.flush_every = 8;
+      int nb2 = kMaxEstepBlocks;
+      rc = launch_fb2b_stats_k2(obs_dtype, tab, b, p2, di, &nb2, st);
+      if (rc != SMF_OK) return rc;
+      reduce_partials_kernel<<<(S + 127) / 128, 128, 0, st>>>(b.partials, nb2, S, stats);
+      return cudaGetLastError() == cudaSuccess ? SMF_OK : SMF_ERR_CUDA;
+    }
+  }
   if (fb2_multi_eligible(tab, obs_dtype) && !g_force_generic && cadence == 4 &&
       fb2_aligned(obs, obs_dtype, nullptr, tab->n_states, -1)) {
     Fb2Args b;

@@ -52,6 +52,7 @@ struct Fb2Args {
   int off_bins;     // BINNED, CTA-wide: int8 [Lpad] bin of the transition INTO position t at index t (0 for t = 0 / pads)
   int off_btab;     // BINNED, CTA-wide: float [n_bins][kBinRow] column-normalised transitions + log2 scale ratios
   int off_ls0;      // BINNED, CTA-wide: double [n_bins] log A_b[0][0]
+  int off_sxi;      // BINNED E-step (K = 2), CTA-wide: float4 [blockDim.x][n_bins | 1] per-thread, per-bin xi accumulators
   int late_load;  // 1: the next read is requested at the end of the iteration (multi-channel E-step: the backward
                   //    sweep re-reads the observations from shared memory for the per-channel emission statistics)
 };
@@ -166,7 +167,8 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
   // recompute the ratios (3 ex2 per position and phase; the kernel is FMA-bound there anyway)
   constexpr bool RECOMP = (K >= 4);
   static_assert(C == 1 || (!WALK && OUT == 2 && K <= 3), "multi-channel variant: K <= 3, run-time output set, single kernel");
-  static_assert(!BINNED || (C == 1 && !WALK && !STATS && OUT == 2 && K <= 3), "distance-binned variant: posterior decode, K <= 3");
+  static_assert(!BINNED || (C == 1 && !WALK && OUT == 2 && K <= 3 && (!STATS || K == 2)),
+                "distance-binned variant: posterior decode for K <= 3, E-step for K = 2");
   constexpr int kBinRow = (K == 2) ? 4 : 8;  // floats per bin: K (K - 1) off-diagonal entries + K - 1 scale ratios (+ pad)
 
   const int tid = threadIdx.x;
@@ -215,6 +217,13 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
     const int nw = blockDim.x >> 5;
     for (int i = tid; i < nw * a.S; i += blockDim.x) wacc[i] = 0.0;
   }
+  // BINNED E-step: the bin of a position is the same for every read, and a thread owns the same positions of every
+  // read it processes -- so the transition statistics are kept per thread and per bin in shared memory (one float4 =
+  // the K x K = 4 sums of one bin; an odd number of float4 per thread keeps the 128-bit accesses conflict free)
+  const int xi_stride = a.n_bins | 1;
+  float4* s_xi = reinterpret_cast<float4*>(smem + a.off_sxi) + (size_t)tid * xi_stride;
+  if (BINNED && STATS)
+    for (int b = 0; b < a.n_bins; ++b) s_xi[b] = make_float4(0.f, 0.f, 0.f, 0.f);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
 
@@ -233,6 +242,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
     acc_den[i] = 0.0f;
   }
 
+  const int off_em = K + (BINNED ? a.n_bins : 1) * KK;  // emission statistics follow the transition block(s)
   auto flush_stats = [&]() {
     if (!STATS) return;
     double* my = wacc + (size_t)wcta * a.S;
@@ -247,17 +257,34 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
       const float r1 = warp_sum_f32(acc_num[i]);
       const float r2 = warp_sum_f32(acc_den[i]);
       if (lane == 0) {
-        my[K + KK + i] += (double)r1;
-        my[K + KK + K * C + i] += (double)r2;
+        my[off_em + i] += (double)r1;
+        my[off_em + K * C + i] += (double)r2;
       }
       acc_num[i] = 0.0f;
       acc_den[i] = 0.0f;
     }
+    if (BINNED) {
+      // per-bin sums: the constant factor A'_b[i][j] (unit diagonal) is applied here, once per flush
+      for (int b = 0; b < a.n_bins; ++b) {
+        const float4 q = s_xi[b];
+        s_xi[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float r00 = warp_sum_f32(q.x), r01 = warp_sum_f32(q.y), r10 = warp_sum_f32(q.z), r11 = warp_sum_f32(q.w);
+        if (lane == 0) {
+          const float* row = s_btab + b * kBinRow;  // [A'_01, A'_10, ...]
+          double* dst = my + K + b * KK;
+          dst[0] += (double)r00;
+          dst[1 % KK] += (double)r01 * (double)row[0];
+          dst[2 % KK] += (double)r10 * (double)row[1];
+          dst[3 % KK] += (double)r11;
+        }
+      }
+    } else {
 #pragma unroll
-    for (int i = 0; i < NXI; ++i) {
-      const float r = warp_sum_f32(acc_xi[i]);
-      if (lane == 0) my[K + i] += (double)r * (double)tab.Ap[(i / K) % K][i % K];
-      acc_xi[i] = 0.0f;
+      for (int i = 0; i < NXI; ++i) {
+        const float r = warp_sum_f32(acc_xi[i]);
+        if (lane == 0) my[K + i] += (double)r * (double)tab.Ap[(i / K) % K][i % K];
+        acc_xi[i] = 0.0f;
+      }
     }
   };
 
@@ -931,11 +958,23 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
             for (int i = 0; i < K; ++i) s2 = fmaf(alp[i], nb[i], s2);
             const float r2 = valid ? rcp_approx(s2) : 0.0f;
             // the constant factor Ap[i][jj] is applied once per flush (flush_stats)
+            if (BINNED) {
+              // K = 2: one 128-bit read-modify-write of this thread's slot of the transition's bin
+              float4* slot = s_xi + (int)s_bins[t0 + j];
+              float4 q = *slot;
+              const float a0 = alp[0] * r2, a1 = alp[1 % K] * r2;
+              q.x = fmaf(a0, cb[0], q.x);
+              q.y = fmaf(a0, cb[1 % K], q.y);
+              q.z = fmaf(a1, cb[0], q.z);
+              q.w = fmaf(a1, cb[1 % K], q.w);
+              *slot = q;
+            } else {
 #pragma unroll
-            for (int i = 0; i < K; ++i) {
-              const float ai = alp[i] * r2;
+              for (int i = 0; i < K; ++i) {
+                const float ai = alp[i] * r2;
 #pragma unroll
-              for (int jj = 0; jj < K; ++jj) acc_xi[i * K + jj] = fmaf(ai, cb[jj], acc_xi[i * K + jj]);
+                for (int jj = 0; jj < K; ++jj) acc_xi[i * K + jj] = fmaf(ai, cb[jj], acc_xi[i * K + jj]);
+              }
             }
           }
           if ((((CH - 1) - j) & 3) == 3) {

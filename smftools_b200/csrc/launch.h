@@ -143,6 +143,8 @@ int launch_fb2b_k2(int obs_dtype, const smf_hmm_tables* t, Fb2Args& a, const Fb2
                    cudaStream_t s);
 int launch_fb2b_k3(int obs_dtype, const smf_hmm_tables* t, Fb2Args& a, const Fb2Plan& plan, const DeviceInfo& di,
                    cudaStream_t s);
+int launch_fb2b_stats_k2(int obs_dtype, const smf_hmm_tables* t, Fb2Args& a, const Fb2Plan& plan, const DeviceInfo& di,
+                         int* nblocks, cudaStream_t s);
 struct WalkArgs;
 struct SeqArgs;
 struct SweepArgs;

@@ -80,3 +80,35 @@ def test_binned_decode_and_fit_through_the_host_mirror():
     st, g = m.decode(X, coords)
     g_ref, _ = O.posterior(X.astype(np.float64), params_of_model(m), coords)
     assert np.abs(g - g_ref).max() <= 1e-5
+
+
+@pytest.mark.parametrize("L,N,prob", [(64, 40, False), (1000, 33, True), (5000, 12, False), (35, 300, False), (2, 5, True),
+                                      (10000, 6, True), (517, 700, True)])
+def test_binned_k2_estep_matches_oracle(L, N, prob):
+    """fb2_kernel<2, ..., BINNED, STATS>: per-bin transition statistics kept per thread in shared memory."""
+    from smftools_b200 import engine
+
+    dev = torch.device("cuda")
+    K = 2
+    p = O.synth_params(K, arch="single_distance_binned", distance_bins=BINS)
+    m = model_from_params(p, arch="single_distance_binned")
+    tables = m._host_tables()
+    coords = _coords(L, 11 + L)
+    bins = m._bins_for(coords, L, dev)
+    X = O.synth_reads(N, L, K, 8300 + L % 61, prob=prob, nan_rate=0.3)
+    ref = O.stats_vector(O.estep(X.astype(np.float64), p, coords))
+    scale = np.maximum(np.abs(ref), 1.0)
+    variants = [torch.from_numpy(X.astype(np.float32)).to(dev)]
+    if not prob:
+        variants.append(torch.from_numpy(np.where(np.isnan(X), 255, X).astype(np.uint8)).to(dev))
+    for obs in variants:
+        st = engine.estep(tables, obs, bins).cpu().numpy()
+        assert st.shape == ref.shape
+        assert np.all(np.abs(st - ref) / scale <= 3e-6), (np.abs(st - ref) / scale).max()
+        assert np.array_equal(st, engine.estep(tables, obs, bins).cpu().numpy()), "not deterministic"
+        engine.set_option("generic", 1)
+        try:
+            st_g = engine.estep(tables, obs, bins).cpu().numpy()
+        finally:
+            engine.set_option("generic", 0)
+        assert np.all(np.abs(st - st_g) / scale <= 5e-6)
