@@ -470,9 +470,9 @@ def stream_workload(name, ctx, steps_cap=None):
         rec["roofline"]["traffic"] = ncu_traffic(name)  # DRAM bytes per chunk launch from the committed ncu pass, or None
         if name == "c4_u8":
             # the E-step moves 1 algorithmic byte per read-position: it is bound by instruction issue, not HBM.  Thread
-            # instructions per read-position from the committed ncu captures (profiles/r02_walk_ncu.txt: 36.8 forward +
-            # 112.3 backward) against the chip's issue rate (SMs x 4 schedulers x 32 lanes x SM clock)
-            instr = 149.1
+            # instructions per read-position from the committed ncu captures (profiles/r02_walk_ncu.txt: 30.5 forward +
+            # 106.0 backward) against the chip's issue rate (SMs x 4 schedulers x 32 lanes x SM clock)
+            instr = 136.5
             peak_issue = 148 * 4 * 32 * 1.965e9
             rec["roofline"]["issue"] = {"thread_instr_per_read_position": instr, "source": "profiles/r02_walk_ncu.txt",
                                         "achieved_thread_instr_per_s": instr * per_rank_positions / (total_ms * 1e-3),
