@@ -316,6 +316,10 @@ class CodedU8:
     def __len__(self):
         return int(self.data.shape[0])
 
+    def __getitem__(self, idx):
+        """Row / column selection keeps the marker (``CodedU8(x)[lo:hi]`` is the coded rows ``lo:hi``)."""
+        return CodedU8(self.data[idx])
+
 
 def _run_lengths_np(bin_mat: np.ndarray) -> np.ndarray:
     """Per-cell length of the True-run it belongs to (int32); vectorised HMM.py:947-959."""
