@@ -99,6 +99,10 @@ const char* smf_hmm_strerror(int code);
  *            rows of a multiple of 4 (uint8: 16) positions runs on the direct kernel (no shared-memory staging) where
  *            it measured faster: uint8 code, K = 2, K = 4, and K = 3 up to 2,048 positions; 0 never / 1 wherever it
  *            applies.  Both kernels make bit-identical decisions.
+ *   "fitloop" 1 (default) smf_hmm_grouped_fit runs the whole Baum-Welch loop of a small fit (every 128-read work item
+ *            resident at once, i.e. up to a few hundred items) in ONE cooperative launch with grid barriers between
+ *            the E-step and the M-step; 0 always enqueues the forward / backward / M-step kernels per iteration.
+ *            Identical results (env SMF_FIT_LOOP sets the initial value).
  *   "generic" 0 (default) / 1: route every forward-backward call to the generic kernel (testing and A/B timing; env
  *            SMF_HMM_FORCE_GENERIC=1 sets the initial value).
  * Returns SMF_ERR_BAD_ARG for an unknown key or value.

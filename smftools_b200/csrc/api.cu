@@ -487,6 +487,8 @@ static int launch_walk_path(bool stats, const smf_hmm_tables* t, int obs_dtype, 
 // -1 = measured policy, 0 = never, 1 = whenever the batch is eligible.  SMF_SEQ / smf_hmm_set_option("seq", v).
 // Viterbi: -1 = measured policy, 1 = direct kernel wherever it applies, 0 = staged kernel only.  SMF_VIT / smf_hmm_set_option("vit", v).
 static std::atomic<int> g_vit_mode{[] { const char* e = getenv("SMF_VIT"); return e ? atoi(e) : -1; }()};
+// one-launch Baum-Welch loop of small grouped fits: 1 = whenever every work item is resident at once (default), 0 = never
+static std::atomic<int> g_fit_loop_mode{[] { const char* e = getenv("SMF_FIT_LOOP"); return e ? atoi(e) : 1; }()};
 static std::atomic<int> g_seq_mode{[] { const char* e = getenv("SMF_SEQ"); return e ? atoi(e) : -1; }()};
 // Reads per launch from which the reads alone fill the machine (148 SMs x 4-5 CTAs x 128 threads); measured
 // break-even against the chunk-parallel kernels in profiles/r02_seq_estep.txt.
@@ -796,6 +798,11 @@ int smf_hmm_set_option(const char* key, int value) {
   if (strcmp(key, "seq") == 0) {
     if (value < -1 || value > 1) return SMF_ERR_BAD_ARG;
     g_seq_mode = value;
+    return SMF_OK;
+  }
+  if (strcmp(key, "fitloop") == 0) {
+    if (value < 0 || value > 1) return SMF_ERR_BAD_ARG;
+    g_fit_loop_mode = value;
     return SMF_OK;
   }
   return SMF_ERR_BAD_ARG;
@@ -1592,7 +1599,7 @@ int grouped_plan(int K, int obs_dtype, const smf_hmm_group* gh, int G, bool fit,
   pl->off_tabs = off;
   off = up256(off + (size_t)G * seq_tables_bytes(K));
   pl->off_active = off;
-  off = up256(off + (size_t)G * sizeof(int));
+  off = up256(off + (size_t)(G + 1) * sizeof(int));  // + the grid-barrier counter of the one-launch fit loop
   pl->off_stats = off;
   off = up256(off + (fit ? (size_t)G * S * sizeof(double) : 0));
   pl->off_partials = off;
@@ -1793,6 +1800,16 @@ static int grouped_fit_run(int phase, int K, int obs_dtype, const smf_hmm_group*
     case SMF_FIT_PHASE_ALL:
       rc = mstep(-1, SEQ_MSTEP_ALL);
       if (rc != SMF_OK) return rc;
+      // small fits (every work item resident at once): the whole loop in one cooperative launch
+      if (max_iter > 1 && pl.n_items > 0 && g_fit_loop_mode.load() != 0) {
+        f.iter = 0;
+        f.what = SEQ_MSTEP_ALL;
+        unsigned* counter = reinterpret_cast<unsigned*>(ws + pl.off_active) + n_groups;
+        rc = K == 2 ? launch_seq_fit_loop_k2(obs_dtype, a, f, counter, di, st)
+                    : (K == 3 ? launch_seq_fit_loop_k3(obs_dtype, a, f, counter, di, st)
+                              : launch_seq_fit_loop_k4(obs_dtype, a, f, counter, di, st));
+        if (rc != SMF_ERR_TOO_LONG) return rc;
+      }
       for (int it = 0; it < max_iter; ++it) {
         rc = estep();
         if (rc != SMF_OK) return rc;

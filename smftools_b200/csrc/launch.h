@@ -155,7 +155,9 @@ struct SeqFitState;
   int launch_seq_k##KV(int obs_dtype, int mode, const smf_hmm_tables* t, const SeqArgs& a, const DeviceInfo& di,     \
                        int* nblocks, cudaStream_t s);                                                                \
   int launch_seq_grouped_k##KV(int obs_dtype, int mode, const SeqArgs& a, const DeviceInfo& di, cudaStream_t s);     \
-  int launch_seq_mstep_k##KV(const SeqFitState& f, cudaStream_t s);
+  int launch_seq_mstep_k##KV(const SeqFitState& f, cudaStream_t s);                                                 \
+  int launch_seq_fit_loop_k##KV(int obs_dtype, const SeqArgs& a, const SeqFitState& f, unsigned* counter,           \
+                                const DeviceInfo& di, cudaStream_t s);
 SMF_DECLARE_SEQ(2)
 SMF_DECLARE_SEQ(3)
 SMF_DECLARE_SEQ(4)

@@ -275,15 +275,18 @@ struct SeqItem {
 // -----------------------------------------------------------------------------------------------------
 // forward: checkpoints + log-likelihood
 // -----------------------------------------------------------------------------------------------------
+// (a device function so that the fused fit loop below runs it too; tab0 is read only when !GROUPED)
 template <int K, typename ObsT, bool GROUPED>
-__global__ void __launch_bounds__(kSeqThreads) seq_forward_kernel(const __grid_constant__ FbTables<K> tab0,
-                                                                  const __grid_constant__ SeqArgs a) {
+__device__ __forceinline__ void seq_forward_body(const FbTables<K>& tab0, const SeqArgs& a, float4* s_tab) {
   constexpr int KP = SeqVec<K>::KP;
-  __shared__ float4 s_tab[3];
   SeqEmit<K, ObsT> em;
   SeqTab<K> T;
-  double log_pi2_sum = tab0.log_pi2_sum, l00 = tab0.l00[0], dl0 = tab0.dl0[0], log_s0 = tab0.log_s0;
+  double log_pi2_sum = 0.0, l00 = 0.0, dl0 = 0.0, log_s0 = 0.0;
   if (!GROUPED) {
+    log_pi2_sum = tab0.log_pi2_sum;
+    l00 = tab0.l00[0];
+    dl0 = tab0.dl0[0];
+    log_s0 = tab0.log_s0;
     seq_emit_init<K, ObsT>(tab0, em, s_tab);
     seq_tab_load<K>(tab0, T);
   }
@@ -365,6 +368,13 @@ __global__ void __launch_bounds__(kSeqThreads) seq_forward_kernel(const __grid_c
   }
 }
 
+template <int K, typename ObsT, bool GROUPED>
+__global__ void __launch_bounds__(kSeqThreads) seq_forward_kernel(const __grid_constant__ FbTables<K> tab0,
+                                                                  const __grid_constant__ SeqArgs a) {
+  __shared__ float4 s_tab[3];
+  seq_forward_body<K, ObsT, GROUPED>(tab0, a, s_tab);
+}
+
 // MODE_POST copy-out plan of a lane.  A read's chunk of posteriors is ONE contiguous run of 16 * KO floats in the
 // output (KO = K, or 1 for a single state column) and one dense run in the read's stack row; the warp's 32 runs
 // are cut into 16-byte pieces, P = 4 * KO per read, piece p = it * 32 + lane of iteration `it`.  The (read, piece)
@@ -427,12 +437,10 @@ constexpr int seq_bwd_min_blocks(int K, size_t obs_size, int mode) {
 // backward: alpha recomputed per chunk, one beta recursion; statistics (MODE_STATS) or posteriors (MODE_POST)
 // -----------------------------------------------------------------------------------------------------
 template <int K, typename ObsT, bool GROUPED, int MODE>
-__global__ void __launch_bounds__(kSeqThreads, seq_bwd_min_blocks(K, sizeof(ObsT), MODE)) seq_backward_kernel(const __grid_constant__ FbTables<K> tab0,
-                                                                                      const __grid_constant__ SeqArgs a) {
+__device__ __forceinline__ void seq_backward_body(const FbTables<K>& tab0, const SeqArgs& a, unsigned char* smem) {
   constexpr int KP = SeqVec<K>::KP;
   constexpr int KK = K * K;
   constexpr bool STATS = (MODE == MODE_STATS);
-  extern __shared__ __align__(16) unsigned char smem[];
   // [warps][S] fp64 accumulators | [16][128][KP] alpha stack | emission table
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kWarps = kSeqThreads / 32;
@@ -780,6 +788,13 @@ __global__ void __launch_bounds__(kSeqThreads, seq_bwd_min_blocks(K, sizeof(ObsT
   if (STATS && !GROUPED) emit_partials(blockIdx.x);
 }
 
+template <int K, typename ObsT, bool GROUPED, int MODE>
+__global__ void __launch_bounds__(kSeqThreads, seq_bwd_min_blocks(K, sizeof(ObsT), MODE)) seq_backward_kernel(const __grid_constant__ FbTables<K> tab0,
+                                                                                      const __grid_constant__ SeqArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  seq_backward_body<K, ObsT, GROUPED, MODE>(tab0, a, smem);
+}
+
 // Single-channel, homogeneous-transition tables from the fp64 log tables (the same arithmetic as the host's
 // build_fb_tables in launch.h, usable on the device by the grouped M-step).
 template <int K>
@@ -870,44 +885,32 @@ struct SeqFitState {
   int update_start, update_trans, update_emission;
 };
 
-// M-step + convergence test + table rebuild of every active group (one thread per group): the closed forms
-// and the unconditional re-normalisation of HMM.py:1598-1614, the stop rule of :1616-1628.
-// Launched with one CTA of 256 threads per group: the CTA first reduces the group's per-item partial statistics
-// in a fixed order (threads sum strided subsets, then a fixed-shape tree: deterministic), then thread 0 updates.
-template <int K>
-__global__ void __launch_bounds__(256) seq_mstep_kernel(const __grid_constant__ SeqFitState f) {
-  const int g = blockIdx.x;
-  constexpr int KK = K * K;
-  if (f.iter >= 0 && f.what != SEQ_MSTEP_UPDATE_ONLY) {
-    if (f.active[g] == 0) {
-      // a stopped group contributes nothing any more (its slot of an all-reduced statistics matrix must be defined)
-      if (f.what == SEQ_MSTEP_REDUCE_ONLY)
-        for (int sidx = threadIdx.x; sidx < f.S; sidx += blockDim.x) f.stats[(size_t)g * f.S + sidx] = 0.0;
-      return;  // uniform across the CTA
-    }
-    __shared__ double red[256];
-    const SeqGroup grp = f.groups[g];
-    const long long n_items = (grp.N + kSeqThreads - 1) / kSeqThreads;
-    for (int sidx = 0; sidx < f.S; ++sidx) {
-      double tot = 0.0;
-      for (long long i = threadIdx.x; i < n_items; i += 256) tot += f.partials[(size_t)(grp.item0 + i) * f.S + sidx];
-      red[threadIdx.x] = tot;
-      __syncthreads();
-      for (int d = 128; d > 0; d >>= 1) {
-        if (threadIdx.x < d) red[threadIdx.x] += red[threadIdx.x + d];
-        __syncthreads();
-      }
-      if (threadIdx.x == 0) f.stats[(size_t)g * f.S + sidx] = red[0];
-      __syncthreads();
-    }
+// Statistics of group g from the per-item partials of the E-step, in a fixed order that does not depend on the
+// CTA size: warp w takes statistics w, w + warps, ...; lane l sums items l, l + 32, ...; one xor-shuffle tree.
+__device__ __forceinline__ void seq_reduce_group(const SeqFitState& f, int g) {
+  const SeqGroup grp = f.groups[g];
+  const long long n_items = (grp.N + kSeqThreads - 1) / kSeqThreads;
+  const int nw = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int sidx = w; sidx < f.S; sidx += nw) {
+    double tot = 0.0;
+    for (long long i = lane; i < n_items; i += 32) tot += f.partials[(size_t)(grp.item0 + i) * f.S + sidx];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, d);
+    if (lane == 0) f.stats[(size_t)g * f.S + sidx] = tot;
   }
-  if (threadIdx.x != 0 || f.what == SEQ_MSTEP_REDUCE_ONLY) return;
+}
+
+// M-step + convergence test + table rebuild of group g by ONE thread: the closed forms and the unconditional
+// re-normalisation of HMM.py:1598-1614, the stop rule of :1616-1628.  iter < 0: tables of the initial parameters.
+template <int K>
+__device__ inline void seq_mstep_update(const SeqFitState& f, int g, int iter) {
+  constexpr int KK = K * K;
   double* p = f.params + (size_t)g * (K + KK + K);
   double* start = p;
   double* trans = p + K;
   double* em = p + K + KK;
   const double eps = f.eps;
-  if (f.iter < 0) {
+  if (iter < 0) {
     f.active[g] = 1;
     f.n_iter[g] = 0;
     f.status[g] = 0;
@@ -915,8 +918,8 @@ __global__ void __launch_bounds__(256) seq_mstep_kernel(const __grid_constant__ 
     if (f.active[g] == 0) return;
     const double* st = f.stats + (size_t)g * f.S;
     const double ll = st[f.S - 1];
-    f.hist[(size_t)g * f.max_iter + f.iter] = ll;
-    f.n_iter[g] = f.iter + 1;
+    f.hist[(size_t)g * f.max_iter + iter] = ll;
+    f.n_iter[g] = iter + 1;
     if (f.update_start) {
       double s[K], tot = 0.0;
       for (int k = 0; k < K; ++k) {
@@ -962,8 +965,8 @@ __global__ void __launch_bounds__(256) seq_mstep_kernel(const __grid_constant__ 
       }
       for (int k = 0; k < K; ++k) em[k] = em[k] < eps ? eps : (em[k] > 1.0 - eps ? 1.0 - eps : em[k]);
     }
-    if (f.iter > 0) {
-      const double prev = f.hist[(size_t)g * f.max_iter + f.iter - 1];
+    if (iter > 0) {
+      const double prev = f.hist[(size_t)g * f.max_iter + iter - 1];
       const double scale = fabs(ll) > 1.0 ? fabs(ll) : 1.0;
       if (fabs(ll - prev) < f.tol * scale) {
         f.active[g] = 0;
@@ -985,10 +988,80 @@ __global__ void __launch_bounds__(256) seq_mstep_kernel(const __grid_constant__ 
     f.active[g] = 0;
     return;
   }
-  FbTables<K> tab;
-  memset(&tab, 0, sizeof(tab));
-  seq_tables_from_logs<K>(ls, lt, l1, l0, &tab);
-  reinterpret_cast<FbTables<K>*>(f.tabs)[g] = tab;
+  FbTables<K>* out = reinterpret_cast<FbTables<K>*>(f.tabs) + g;
+  if (iter < 0) {
+    FbTables<K> tab;
+    memset(&tab, 0, sizeof(tab));
+    seq_tables_from_logs<K>(ls, lt, l1, l0, &tab);
+    *out = tab;
+  } else {
+    seq_tables_from_logs<K>(ls, lt, l1, l0, out);  // the same fields every time: the rest stays as first written
+  }
+}
+
+// One CTA per group: the group's statistics from the per-item partials, then thread 0 updates (see above).
+template <int K>
+__global__ void __launch_bounds__(256) seq_mstep_kernel(const __grid_constant__ SeqFitState f) {
+  const int g = blockIdx.x;
+  if (f.iter >= 0 && f.what != SEQ_MSTEP_UPDATE_ONLY) {
+    if (f.active[g] == 0) {
+      // a stopped group contributes nothing any more (its slot of an all-reduced statistics matrix must be defined)
+      if (f.what == SEQ_MSTEP_REDUCE_ONLY)
+        for (int sidx = threadIdx.x; sidx < f.S; sidx += blockDim.x) f.stats[(size_t)g * f.S + sidx] = 0.0;
+      return;  // uniform across the CTA
+    }
+    seq_reduce_group(f, g);
+    __syncthreads();
+  }
+  if (threadIdx.x != 0 || f.what == SEQ_MSTEP_REDUCE_ONLY) return;
+  seq_mstep_update<K>(f, g, f.iter);
+}
+
+// -----------------------------------------------------------------------------------------------------
+// The whole Baum-Welch loop of a SMALL grouped fit in one cooperative launch (every work item has its own resident
+// CTA): forward + backward of an item run back to back in the same threads, two grid barriers per iteration
+// separate the E-step from the M-step (groups dealt round-robin to the CTAs), and the loop ends as soon as no
+// group is active.  Same arithmetic and summation orders as the three-kernel sequence: identical results.
+// -----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void seq_grid_barrier(unsigned* counter, unsigned& target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    } while ((int)(seen - target) < 0);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <int K, typename ObsT>
+__global__ void __launch_bounds__(kSeqThreads, 1) seq_fit_loop_kernel(const __grid_constant__ SeqArgs a,
+                                                                      const __grid_constant__ SeqFitState f,
+                                                                      unsigned* barrier_counter) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ float4 s_tab[3];
+  const FbTables<K>& unused = *reinterpret_cast<const FbTables<K>*>(a.tabs);
+  unsigned target = 0;
+  for (int iter = 0; iter < f.max_iter; ++iter) {
+    seq_forward_body<K, ObsT, true>(unused, a, s_tab);
+    seq_backward_body<K, ObsT, true, MODE_STATS>(unused, a, smem);
+    seq_grid_barrier(barrier_counter, target);
+    for (int g = blockIdx.x; g < f.n_groups; g += gridDim.x) {
+      if (f.active[g] == 0) continue;  // uniform across the CTA
+      seq_reduce_group(f, g);
+      __syncthreads();
+      if (threadIdx.x == 0) seq_mstep_update<K>(f, g, iter);
+      __syncthreads();
+    }
+    seq_grid_barrier(barrier_counter, target);
+    int any = 0;
+    for (int g = threadIdx.x; g < f.n_groups; g += kSeqThreads) any |= f.active[g];
+    if (__syncthreads_or(any) == 0) break;
+  }
 }
 
 }  // namespace smf

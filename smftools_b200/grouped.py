@@ -223,10 +223,15 @@ def fit_groups(models, obs_list, *, max_iter: int = 50, tol: float = 1e-5, updat
     tab = _GroupTable(obs_list, device)
     init = pack_parameters(models)
     with torch.cuda.device(device):
-        params = torch.from_numpy(init).to(device)
-        hist = torch.zeros((G, max_iter), dtype=torch.float64, device=device)
-        n_iter = torch.zeros((G,), dtype=torch.int32, device=device)
-        status = torch.zeros((G,), dtype=torch.int32, device=device)
+        # parameters | log-likelihood histories | iteration counts | stop reasons share one buffer: one fill, one read-back
+        P = init.shape[1]
+        o_hist, o_n, o_st, o_end = 8 * G * P, 8 * G * (P + max_iter), 8 * G * (P + max_iter) + 4 * G, 8 * G * (P + max_iter + 1)
+        buf = torch.zeros((o_end,), dtype=torch.uint8, device=device)
+        params = buf[:o_hist].view(torch.float64).view(G, P)
+        params.copy_(torch.from_numpy(init))
+        hist = buf[o_hist:o_n].view(torch.float64).view(G, max_iter)
+        n_iter = buf[o_n:o_st].view(torch.int32)
+        status = buf[o_st:o_end].view(torch.int32)
         need = int(lib.smf_hmm_grouped_workspace_bytes(K, tab.arr, G, 1))
         if need == 0:
             raise ValueError("smf_hmm_grouped_workspace_bytes rejected the group table")
@@ -255,10 +260,11 @@ def fit_groups(models, obs_list, *, max_iter: int = 50, tol: float = 1e-5, updat
                                          _ptr(hist), _ptr(n_iter), _ptr(status), _ptr(ws), need, _stream_ptr(device))
             _lib.check(rc, "smf_hmm_grouped_fit")
         # one read-back for the whole fit
-        params_h = params.cpu().numpy()
-        hist_h = hist.cpu().numpy()
-        n_h = n_iter.cpu().numpy()
-        st_h = status.cpu().numpy()
+        host = buf.cpu().numpy()
+        params_h = host[:o_hist].view(np.float64).reshape(G, P)
+        hist_h = host[o_hist:o_n].view(np.float64).reshape(G, max_iter)
+        n_h = host[o_n:o_st].view(np.int32)
+        st_h = host[o_st:o_end].view(np.int32)
     out: List[List[float]] = []
     unpack_parameters(models, params_h)
     for g, m in enumerate(models):

@@ -298,3 +298,47 @@ def test_random_ragged_groups_including_degenerate_lengths(K, prob, seed):
         q, h_ref = O.fit(X.astype(np.float64), p, max_iter=3, tol=0.0)
         np.testing.assert_allclose(hists[g], h_ref, rtol=1e-6, atol=1e-5)
         assert np.abs(params_of_model(models[g]).emission.reshape(-1) - q.emission.reshape(-1)).max() <= 1e-4
+
+
+@pytest.mark.parametrize("K,prob,tol", [(2, False, 0.0), (2, False, 1e-4), (3, True, 1e-4), (4, False, 1e-5), (3, False, 0.0)])
+def test_one_launch_fit_loop_is_bit_identical_to_the_kernel_sequence(K, prob, tol):
+    """Small fits run the whole Baum-Welch loop in one cooperative launch (grid barriers between E-step and M-step);
+    option "fitloop" = 0 enqueues forward / backward / M-step kernels per iteration instead.  Same arithmetic, same
+    summation orders: parameters, log-likelihood histories, iteration counts and stop reasons are identical."""
+    from smftools_b200 import engine
+
+    gs = _groups(K, prob, 4100 + K)
+    obs = [S.CodedU8(_code(X)) if not prob else X.astype(np.float32) for X, _ in gs]
+    out = []
+    try:
+        for mode in (1, 0):
+            engine.set_option("fitloop", mode)
+            models = [model_from_params(p) for _, p in gs]
+            hists, status = grouped.fit_groups(models, obs, max_iter=12, tol=tol, return_status=True)
+            torch.cuda.synchronize()
+            out.append((models, hists, status))
+    finally:
+        engine.set_option("fitloop", 1)
+    (m1, h1, s1), (m0, h0, s0) = out
+    assert list(s1) == list(s0)
+    if tol > 0.0:
+        assert len({len(h) for h in h1}) > 1  # groups stop at different iterations
+    for a, b, ha, hb in zip(m1, m0, h1, h0):
+        assert len(ha) == len(hb)
+        np.testing.assert_array_equal(np.asarray(ha), np.asarray(hb))
+        for name in ("start", "trans", "emission"):
+            assert torch.equal(getattr(a, name), getattr(b, name)), name
+
+
+def test_one_launch_fit_loop_single_small_group_matches_oracle():
+    K, N, L, iters = 2, 1000, 170, 25
+    X = O.synth_reads(N, L, K, 5, prob=False, nan_rate=0.3)
+    p = O.synth_params(K)
+    m = model_from_params(p)
+    hist = grouped.fit_groups([m], [S.CodedU8(_code(X))], max_iter=iters, tol=0.0)[0]
+    ref, ref_hist = O.fit(X.astype(np.float64), p, max_iter=iters, tol=0.0)
+    assert len(hist) == iters
+    np.testing.assert_allclose(np.asarray(hist), np.asarray(ref_hist), rtol=1e-6)
+    q = params_of_model(m)
+    assert np.abs(q.emission - ref.emission).max() <= 1e-4
+    assert np.abs(q.trans - ref.trans).max() <= 1e-4
