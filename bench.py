@@ -843,7 +843,8 @@ def run_ours(args, wl):
     # E-step launches per call: two-kernel path (walk + sweeps + reduce) for K = 4 and long K = 3 batches
     # (api.cu walk_eligible), otherwise one forward-backward kernel + reduce
     two_kernel = N >= 8192 and (K == 4 or (K == 3 and L > 8704))
-    estep_launches = 3 if two_kernel else 2
+    seq_estep = N >= (24576 if L >= 8192 else (49152 if K > 2 else (65536 if L >= 2000 else 98304))) and L % 4 == 0  # seq_min_reads()
+    estep_launches = 3 if (two_kernel or seq_estep) else 2
 
     def step():
         if op == "posterior":
@@ -929,7 +930,9 @@ def run_ours(args, wl):
         roof = roofline_of(op, K, 4, float(N) * L, k_ms, args.workload)
         roof["kernel"] = {"posterior": "smf::fb2_kernel<K, CH, STATS=false, ...> (one launch per step)",
                           "viterbi": "smf::viterbi_kernel (+ smf::call_intervals_kernel)",
-                          "estep": ("smf::walk_kernel + smf::estep_sweep_kernel (+ reduce_partials_kernel)"
+                          "estep": ("smf::seq_forward_kernel + smf::seq_backward_kernel<MODE_STATS> (+ reduce_partials_kernel)"
+                                    if seq_estep else
+                                    "smf::walk_kernel + smf::estep_sweep_kernel (+ reduce_partials_kernel)"
                                     if two_kernel else
                                     "smf::fb2_kernel<K, CH, STATS=true, ...> (+ reduce_partials_kernel)")}[op]
         line = {
