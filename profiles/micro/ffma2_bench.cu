@@ -64,6 +64,48 @@ __global__ void __launch_bounds__(256) bench(float* out, int iters, float m, flo
   out[blockIdx.x * blockDim.x + threadIdx.x] = s + (float)hs;
 }
 
+// dependent chains: one warp, 1 or 2 independent chains, cycles per dependent instruction (latency)
+template <int MODE>
+__global__ void latency(float* out, long long* cycles, int iters, float m, float c) {
+  float a = threadIdx.x * 0.001f, b = a + 1.0f;
+  u64 p = pack(a, b);
+  const u64 mm = pack(m, m), cc = pack(c, c);
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    if (MODE == 0) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a = fmaf(a, m, c);
+    } else if (MODE == 1) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) p = fma2(p, mm, cc);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {  // two scalar chains = the work of one packed chain
+        a = fmaf(a, m, c);
+        b = fmaf(b, m, c);
+      }
+    }
+  }
+  long long t1 = clock64();
+  float x, y;
+  unpack(p, x, y);
+  out[threadIdx.x] = a + b + x + y;
+  if (threadIdx.x == 0) cycles[0] = t1 - t0;
+}
+
+template <int MODE>
+void run_latency(const char* name, float* out) {
+  long long* cyc;
+  cudaMalloc(&cyc, 8);
+  const int iters = 4096;
+  latency<MODE><<<1, 32>>>(out, cyc, iters, 0.999f, 0.001f);
+  latency<MODE><<<1, 32>>>(out, cyc, iters, 0.999f, 0.001f);
+  long long h = 0;
+  cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+  printf("%-40s %6.2f cycles per step of the chain\n", name, (double)h / (16.0 * iters));
+  cudaFree(cyc);
+}
+
 template <int MODE>
 void run(const char* name, float* out, int blocks) {
   const int iters = 20000;
@@ -96,6 +138,9 @@ int main() {
   run<1>("B  8 x FFMA2", out, blocks);
   run<2>("C 16 x FFMA  + 8 LOP3", out, blocks);
   run<3>("D  8 x FFMA2 + 8 LOP3", out, blocks);
+  run_latency<0>("latency: FFMA chain", out);
+  run_latency<1>("latency: FFMA2 chain", out);
+  run_latency<2>("latency: two interleaved FFMA chains", out);
   cudaError_t err = cudaDeviceSynchronize();
   printf("status: %s\n", cudaGetErrorString(err));
   return err != cudaSuccess;

@@ -497,6 +497,7 @@ static std::atomic<int> g_seq_mode{[] { const char* e = getenv("SMF_SEQ"); retur
 static int64_t seq_min_reads(int K, int64_t L) {
   static const int env = [] { const char* e = getenv("SMF_SEQ_MIN_READS"); return e ? atoi(e) : 0; }();
   if (env > 0) return env;
+  if (L >= 16384 && K >= 3) return 16384;  // 20,000 x 20 kb: K = 3 3.7-4.1 vs 4.5-4.9 ms, K = 4 4.3-4.4 vs 5.0 (r02_policy_audit3.txt)
   if (L >= 8192) return 24576;
   if (K == 2) return L >= 2000 ? 65536 : 98304;
   return 49152;
@@ -530,6 +531,9 @@ static bool seq_launch_eligible(const smf_hmm_tables* t, int64_t N, int64_t L, i
 static bool seq_post_shape_eligible(const smf_hmm_tables* t, int64_t N, int64_t L) {
   if (!seq_shape_eligible(t, N, L) || (L & 3)) return false;
   if (g_seq_mode == 1) return true;
+  // (the E-step switches earlier for the longest reads; posterior decode of 20,000 x 20 kb measured slower here:
+  // K = 4 6.6 vs 5.2 ms, profiles/r02_policy_audit4.txt)
+  if (L >= 8192 && N < 24576) return false;
   // measured (profiles/r02_seq_post.txt, r02_final_sweep.txt; ~2.4 ms per 4e8 positions for K = 3 at any length):
   // K = 4 wins at every length (0.31-0.44 of HBM peak vs 0.26-0.40); K = 3 where the chunk-parallel kernels are
   // weak -- short reads (<= 400: 0.31-0.41) and reads beyond the single kernel's reach (> 13.4 kb: 0.27); K = 2 only
@@ -1107,7 +1111,8 @@ int smf_hmm_estep(const smf_hmm_tables* tab, const void* obs, int obs_dtype, int
       fb2_aligned(obs, obs_dtype, nullptr, tab->n_states, -1)) {
     // large batches of K >= 3: the sequential kernels also beat the bundled short-read kernel (K = 4, 10^6 x 304:
     // 1.8e11 vs 7e10 read-positions/s; K = 3: 2.0e11 vs 1.4e11); K = 2 short reads stay bundled (3.0e11 either way)
-    const bool seq_first = tab->n_states >= 3 && g_short_mode != 1 &&
+    // (uint8-coded K = 2 too since the packed fp32x2 rewrite: 10^6 x 100: 0.39 vs 0.52 ms, profiles/r02_policy_audit3.txt)
+    const bool seq_first = (tab->n_states >= 3 || obs_dtype == SMF_OBS_U8) && g_short_mode != 1 &&
                            seq_launch_eligible(tab, n_reads, n_pos, obs_dtype, obs, false);
     // short reads: several reads per warp (E-step variant of short_kernel)
     if (!seq_first && g_short_mode != 0 && obs_dtype != SMF_OBS_F64 &&

@@ -340,26 +340,12 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
     rc1[k] = CODE_TAB ? ex2_approx(fmaf(1.0f, tab.rdl[k][0], tab.rl0p[k])) : 0.0f;
     rcm[k] = CODE_TAB ? ex2_approx(tab.rmiss[k]) : 0.0f;
   }
-  auto vecA = [&](const float (&Am)[K][K], const float (&x)[K], float (&y)[K]) {
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
-      float s = x[j];
-#pragma unroll
-      for (int i = 0; i < K; ++i)
-        if (i != j) s = fmaf(x[i], Am[i][j], s);
-      y[j] = s;
-    }
-  };
-  auto Avec = [&](const float (&Am)[K][K], const float (&x)[K], float (&y)[K]) {
-#pragma unroll
-    for (int i = 0; i < K; ++i) {
-      float s = x[i];
-#pragma unroll
-      for (int j = 0; j < K; ++j)
-        if (j != i) s = fmaf(Am[i][j], x[j], s);
-      y[i] = s;
-    }
-  };
+  // Packed fp32x2 (f32x2.cuh) for K = 3 only: measured 3-6 % faster there (21 % at 544 positions), while K = 2
+  // (1-7 % slower: the pair moves cost what the packing saves) and K = 4 (6-20 % slower) keep the scalar code
+  // (profiles/r02_policy_audit4.txt against r02_policy_audit.txt).
+  constexpr bool PK = (K == 3);
+  auto vecA = [&](const float (&Am)[K][K], const float (&x)[K], float (&y)[K]) { vec_mat_unit<K, PK>(x, Am, y); };
+  auto Avec = [&](const float (&Am)[K][K], const float (&x)[K], float (&y)[K]) { mat_vec_unit<K, PK>(Am, x, y); };
   // BINNED: the table row of the transition into position t (off-diagonal entries of A'_b, then log2 scale ratios)
   auto bin_row = [&](int t, float (&Ab)[K][K], float (&rs)[K]) {
     const float* row = s_btab + (int)s_bins[t] * kBinRow;
@@ -547,11 +533,10 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
           for (int i = 0; i < K; ++i) {
             float q[K];
             vecA(Am, P[i], q);
-#pragma unroll
-            for (int jj = 0; jj < K; ++jj) P[i][jj] = (jj == 0) ? q[jj] : q[jj] * c[jj];
+            vec_mul_tail<K, PK>(P[i], q, c);
           }
         }
-        if ((j & 3) == 3 || j == CH - 1) mat_scale<K>(P, pow2_rescale_noexp(mat_max<K>(P)));
+        if ((j & 3) == 3 || j == CH - 1) mat_scale<K, PK>(P, pow2_rescale_noexp(mat_max<K>(P)));
       }
     }
 
@@ -588,7 +573,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
       for (int i = 0; i < K; ++i)
 #pragma unroll
         for (int j = 0; j < K; ++j) q[i][j] = __shfl_up_sync(kFull, pre[i][j], d);
-      mat_mul<K>(q, pre, r);
+      mat_mul<K, PK>(q, pre, r);
       const bool up_ok = lane >= d;
 #pragma unroll
       for (int i = 0; i < K; ++i)
@@ -598,15 +583,15 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
       for (int i = 0; i < K; ++i)
 #pragma unroll
         for (int j = 0; j < K; ++j) q[i][j] = __shfl_down_sync(kFull, suf[i][j], d);
-      mat_mul<K>(suf, q, r);
+      mat_mul<K, PK>(suf, q, r);
       const bool dn_ok = lane + d < 32;
 #pragma unroll
       for (int i = 0; i < K; ++i)
 #pragma unroll
         for (int j = 0; j < K; ++j) suf[i][j] = dn_ok ? r[i][j] : suf[i][j];
       if (d == 2 || d == 8) {
-        mat_scale<K>(pre, pow2_rescale_noexp(mat_max<K>(pre)));
-        mat_scale<K>(suf, pow2_rescale_noexp(mat_max<K>(suf)));
+        mat_scale<K, PK>(pre, pow2_rescale_noexp(mat_max<K>(pre)));
+        mat_scale<K, PK>(suf, pow2_rescale_noexp(mat_max<K>(suf)));
       }
     }
 
@@ -791,13 +776,11 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
         } else {
           float y[K];
           vecA(Am, al, y);
-#pragma unroll
-          for (int jj = 0; jj < K; ++jj) nx[jj] = (jj == 0) ? y[jj] : y[jj] * cf[jj];
+          vec_mul_tail<K, PK>(nx, y, cf);
         }
         if ((j & 3) == 3) {
           const float sc = want_ll ? pow2_rescale(vec_max<K>(nx), e) : pow2_rescale_noexp(vec_max<K>(nx));
-#pragma unroll
-          for (int k = 0; k < K; ++k) nx[k] *= sc;
+          vec_scale<K, PK>(nx, sc);
         }
 #pragma unroll
         for (int k = 0; k < K; ++k) al[k] = nx[k];
@@ -840,15 +823,12 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
 #pragma unroll
       for (int j = CH - 1; j >= 0; --j) {
         float gk[K];
+        vec_mul<K, PK>(gk, alc, bv);
         float s = 0.0f;
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-          gk[k] = alc[k] * bv[k];
-          s += gk[k];
-        }
+        for (int k = 0; k < K; ++k) s += gk[k];
         const float r = rcp_approx(s);
-#pragma unroll
-        for (int k = 0; k < K; ++k) gk[k] *= r;
+        vec_scale<K, PK>(gk, r);
         // alpha of the previous position (this thread's chunk, or the incoming prefix vector)
         float alp[K];
         if (j > 0) {
@@ -914,10 +894,9 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
           }
           if (C == 1) {
             if ((obsmask >> j) & (mask_t)1) {
-#pragma unroll
-              for (int k = 0; k < K; ++k) {
-                acc_num[k] = fmaf(gk[k], ov[(STATS && C == 1) ? j : 0], acc_num[k]);
-                acc_den[k] += gk[k];
+              if constexpr (STATS && C == 1) {
+                vec_fma_vs<K, PK>(acc_num, gk, ov[(STATS && C == 1) ? j : 0]);
+                vec_add<K, PK>(acc_den, gk);
               }
             }
           } else {
@@ -941,9 +920,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
         if (need_step) {
           float cb[K], nb[K], cr[K];
           ratios(j, cr);
-          cb[0] = bv[0];
-#pragma unroll
-          for (int k = 1; k < K; ++k) cb[k] = cr[k] * bv[k];
+          vec_mul_tail<K, PK>(cb, bv, cr);
           float Ab[K][K], rsb[K];
           if (BINNED) bin_row(t0 + j, Ab, rsb);
           const float(&Am)[K][K] = BINNED ? Ab : A;
@@ -969,18 +946,24 @@ __global__ void __launch_bounds__(MAXT, MINB) fb2_kernel(const __grid_constant__
               q.w = fmaf(a1, cb[1 % K], q.w);
               *slot = q;
             } else {
+              float ai[K];
+#pragma unroll
+              for (int i = 0; i < K; ++i) ai[i] = alp[i];
+              vec_scale<K, PK>(ai, r2);
 #pragma unroll
               for (int i = 0; i < K; ++i) {
-                const float ai = alp[i] * r2;
+                float row[K];
 #pragma unroll
-                for (int jj = 0; jj < K; ++jj) acc_xi[i * K + jj] = fmaf(ai, cb[jj], acc_xi[i * K + jj]);
+                for (int jj = 0; jj < K; ++jj) row[jj] = acc_xi[i * K + jj];
+                vec_fma_s<K, PK>(row, ai[i], cb);
+#pragma unroll
+                for (int jj = 0; jj < K; ++jj) acc_xi[i * K + jj] = row[jj];
               }
             }
           }
           if ((((CH - 1) - j) & 3) == 3) {
             const float sc = pow2_rescale_noexp(vec_max<K>(nb));
-#pragma unroll
-            for (int k = 0; k < K; ++k) nb[k] *= sc;
+            vec_scale<K, PK>(nb, sc);
           }
 #pragma unroll
           for (int k = 0; k < K; ++k) bv[k] = nb[k];

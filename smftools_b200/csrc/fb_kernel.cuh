@@ -73,27 +73,27 @@ __device__ __forceinline__ float mat_max(const float (&P)[K][K]) {
   return m;
 }
 
-template <int K>
+template <int K, bool PK = true>
 __device__ __forceinline__ void mat_scale(float (&P)[K][K], float s) {
 #pragma unroll
-  for (int i = 0; i < K; ++i)
-#pragma unroll
-    for (int j = 0; j < K; ++j) P[i][j] *= s;
+  for (int i = 0; i < K; ++i) vec_scale<K, PK>(P[i], s);  // packed fp32x2 rows (f32x2.cuh)
 }
 
-// C = A * B
-template <int K>
+// C = A * B: row i of C = sum_l A[i][l] * (row l of B), l ascending -- packed rows, the scalar code's order per entry
+template <int K, bool PK = true>
 __device__ __forceinline__ void mat_mul(const float (&A)[K][K], const float (&B)[K][K],
                                         float (&C)[K][K]) {
 #pragma unroll
-  for (int i = 0; i < K; ++i)
+  for (int i = 0; i < K; ++i) {
+    float r[K];
 #pragma unroll
-    for (int j = 0; j < K; ++j) {
-      float s = A[i][0] * B[0][j];
+    for (int j = 0; j < K; ++j) r[j] = B[0][j];
+    vec_scale<K, PK>(r, A[i][0]);
 #pragma unroll
-      for (int l = 1; l < K; ++l) s = fmaf(A[i][l], B[l][j], s);
-      C[i][j] = s;
-    }
+    for (int l = 1; l < K; ++l) vec_fma_s<K, PK>(r, A[i][l], B[l]);
+#pragma unroll
+    for (int j = 0; j < K; ++j) C[i][j] = r[j];
+  }
 }
 
 template <int K>

@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include "smf_hmm.h"
+#include "f32x2.cuh"
 
 namespace smf {
 

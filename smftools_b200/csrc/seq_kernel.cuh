@@ -234,92 +234,21 @@ __device__ __forceinline__ void seq_load_vec(const float* p, float (&y)[K]) {
 }
 
 // one forward step: al <- (al A') .* c   (no transition into the very first position of the read)
-// K = 2, 4: packed fp32x2 (f32x2.cuh), every lane in the scalar code's operation order -- bit-identical results.
-//   y_j = x_j + sum_{i != j} x_i A_ij, i ascending: the pair (j, j + 1) starts from (x_j, x_j+1), takes the partner
-//   term through the lane swap and every other i as a broadcast.
-template <int K>
-__device__ __forceinline__ void seq_vec_mat(const float (&x)[K], const float (&A)[K][K], float (&y)[K]) {
-  if constexpr (K == 2) {
-    fma2f(y[0], y[1], x[1], x[0], A[1][0], A[0][1], x[0], x[1]);
-  } else if constexpr (K == 4) {
-    fma2f(y[0], y[1], x[1], x[0], A[1][0], A[0][1], x[0], x[1]);
-    fma2f(y[0], y[1], x[2], x[2], A[2][0], A[2][1], y[0], y[1]);
-    fma2f(y[0], y[1], x[3], x[3], A[3][0], A[3][1], y[0], y[1]);
-    fma2f(y[2], y[3], x[0], x[0], A[0][2], A[0][3], x[2], x[3]);
-    fma2f(y[2], y[3], x[1], x[1], A[1][2], A[1][3], y[2], y[3]);
-    fma2f(y[2], y[3], x[3], x[2], A[3][2], A[2][3], y[2], y[3]);
-  } else {
-#pragma unroll
-    for (int jj = 0; jj < K; ++jj) {
-      float s = x[jj];
-#pragma unroll
-      for (int i = 0; i < K; ++i)
-        if (i != jj) s = fmaf(x[i], A[i][jj], s);
-      y[jj] = s;
-    }
-  }
-}
-//   y_i = x_i + sum_{j != i} A_ij x_j, j ascending (the backward recursion)
-template <int K>
-__device__ __forceinline__ void seq_mat_vec(const float (&A)[K][K], const float (&x)[K], float (&y)[K]) {
-  if constexpr (K == 2) {
-    fma2f(y[0], y[1], x[1], x[0], A[0][1], A[1][0], x[0], x[1]);
-  } else if constexpr (K == 4) {
-    fma2f(y[0], y[1], x[1], x[0], A[0][1], A[1][0], x[0], x[1]);
-    fma2f(y[0], y[1], x[2], x[2], A[0][2], A[1][2], y[0], y[1]);
-    fma2f(y[0], y[1], x[3], x[3], A[0][3], A[1][3], y[0], y[1]);
-    fma2f(y[2], y[3], x[0], x[0], A[2][0], A[3][0], x[2], x[3]);
-    fma2f(y[2], y[3], x[1], x[1], A[2][1], A[3][1], y[2], y[3]);
-    fma2f(y[2], y[3], x[3], x[2], A[2][3], A[3][2], y[2], y[3]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < K; ++i) {
-      float acc = x[i];
-#pragma unroll
-      for (int jj = 0; jj < K; ++jj)
-        if (jj != i) acc = fmaf(A[i][jj], x[jj], acc);
-      y[i] = acc;
-    }
-  }
-}
-// v <- v * s (all states)
-template <int K>
-__device__ __forceinline__ void seq_vec_scale(float (&v)[K], float s) {
-  if constexpr (K == 2 || K == 4) {
-#pragma unroll
-    for (int k = 0; k < K; k += 2) mul2f(v[k], v[k + 1], v[k], v[k + 1], s, s);
-  } else {
-#pragma unroll
-    for (int k = 0; k < K; ++k) v[k] *= s;
-  }
-}
-// d = a .* b
-template <int K>
-__device__ __forceinline__ void seq_vec_mul(float (&d)[K], const float (&a)[K], const float (&b)[K]) {
-  if constexpr (K == 2 || K == 4) {
-#pragma unroll
-    for (int k = 0; k < K; k += 2) mul2f(d[k], d[k + 1], a[k], a[k + 1], b[k], b[k + 1]);
-  } else {
-#pragma unroll
-    for (int k = 0; k < K; ++k) d[k] = a[k] * b[k];
-  }
-}
-
-template <int K>
+// (vector helpers: f32x2.cuh -- packed fp32x2 for K = 2, 3, 4 in the scalar code's per-lane operation order)
+template <int K, bool PK = true>
 __device__ __forceinline__ void seq_fwd_step(float (&al)[K], const float (&A)[K][K], const float (&c)[K], bool no_trans) {
   float y[K];
-  seq_vec_mat<K>(al, A, y);
+  vec_mat_unit<K, PK>(al, A, y);
 #pragma unroll
   for (int k = 0; k < K; ++k) y[k] = no_trans ? al[k] : y[k];
-  if constexpr (K == 4) {
+  if constexpr (PK && K == 4) {
     mul2f(y[0], y[1], y[0], y[1], c[0], c[1]);  // c[0] == 1: exact
     mul2f(y[2], y[3], y[2], y[3], c[2], c[3]);
+#pragma unroll
+    for (int k = 0; k < K; ++k) al[k] = y[k];
   } else {
-#pragma unroll
-    for (int k = 1; k < K; ++k) y[k] *= c[k];
+    vec_mul_tail<K, PK>(al, y, c);
   }
-#pragma unroll
-  for (int k = 0; k < K; ++k) al[k] = y[k];
 }
 
 // work-item bookkeeping shared by the kernels: which group / tables / read this thread works on
@@ -417,7 +346,7 @@ __device__ __forceinline__ void seq_forward_body(const FbTables<K>& tab0, const 
         seq_fwd_step<K>(al, T.A, cf, c == 0 && j == 0);
         if ((j & 3) == 3) {
           const float sc = pow2_rescale(vec_max<K>(al), e);
-          seq_vec_scale<K>(al, sc);
+          vec_scale<K>(al, sc);
         }
       };
       if (len == kSeqCH) {
@@ -512,6 +441,10 @@ __device__ __forceinline__ void seq_backward_body(const FbTables<K>& tab0, const
   constexpr int KP = SeqVec<K>::KP;
   constexpr int KK = K * K;
   constexpr bool STATS = (MODE == MODE_STATS);
+  // Packed fp32x2 arithmetic in the E-step only: issue-bound at four resident CTAs per SM (configs[3]: 14.0 -> 10.8 ms).
+  // Posterior decode measured mixed (float rows of large batches 6-13 % faster, uint8 rows and batches of ~25,000
+  // reads 11-13 % slower: the pair moves sit on the dependency chain) and keeps the scalar code.
+  constexpr bool PK = STATS;
   // [warps][S] fp64 accumulators | [16][128][KP] alpha stack | emission table
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kWarps = kSeqThreads / 32;
@@ -677,10 +610,10 @@ __device__ __forceinline__ void seq_backward_body(const FbTables<K>& tab0, const
         bool m;
         float om;
         em.get(cur, j, cf, m, om);
-        seq_fwd_step<K>(al, T.A, cf, first && j == 0);
+        seq_fwd_step<K, PK>(al, T.A, cf, first && j == 0);
         if ((j & 3) == 3) {
           const float sc = pow2_rescale_noexp(vec_max<K>(al));
-          seq_vec_scale<K>(al, sc);
+          vec_scale<K, PK>(al, sc);
         }
         seq_store_vec<K>(my + j * jstride, al);
       };
@@ -704,31 +637,23 @@ __device__ __forceinline__ void seq_backward_body(const FbTables<K>& tab0, const
         float om;
         em.get(cur, j, cr, m, om);
         float gk[K];
-        seq_vec_mul<K>(gk, alc, bv);
+        vec_mul<K, PK>(gk, alc, bv);
         float gs = 0.0f;
 #pragma unroll
         for (int k = 0; k < K; ++k) gs += gk[k];
         const float g0 = rcp_approx(gs);
         if (STATS) {
           const float gr = m ? g0 : 0.0f;
-          if constexpr (STATS && (K == 2 || K == 4)) {
+          if constexpr (STATS) {
+            float gg[K];
 #pragma unroll
-            for (int k = 0; k < K; k += 2) {
-              float gg0, gg1;
-              mul2f(gg0, gg1, gk[k], gk[k + 1], gr, gr);
-              fma2f(acc_num[k], acc_num[k + 1], gg0, gg1, om, om, acc_num[k], acc_num[k + 1]);
-              add2f(acc_den[k], acc_den[k + 1], acc_den[k], acc_den[k + 1], gg0, gg1);
-            }
-          } else {
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-              const float gg = gk[k] * gr;
-              acc_num[STATS ? k : 0] = fmaf(gg, om, acc_num[STATS ? k : 0]);
-              acc_den[STATS ? k : 0] += gg;
-            }
+            for (int k = 0; k < K; ++k) gg[k] = gk[k];
+            vec_scale<K, PK>(gg, gr);
+            vec_fma_vs<K, PK>(acc_num, gg, om);
+            vec_add<K, PK>(acc_den, gg);
           }
         } else {
-          seq_vec_scale<K>(gk, g0);
+          vec_scale<K, PK>(gk, g0);
           if (srow != nullptr) {
             unsigned best = 0;
             float gbest = gk[0];
@@ -781,14 +706,12 @@ __device__ __forceinline__ void seq_backward_body(const FbTables<K>& tab0, const
           for (int k = 0; k < K; ++k) acc_start[STATS ? k : 0] += gk[k] * g0;
         }
         float cb[K], nb[K];
-        if constexpr (K == 4) {
-          seq_vec_mul<K>(cb, cr, bv);  // cr[0] == 1: exact
+        if constexpr (PK && K == 4) {
+          vec_mul<K, PK>(cb, cr, bv);  // cr[0] == 1: exact
         } else {
-          cb[0] = bv[0];
-#pragma unroll
-          for (int k = 1; k < K; ++k) cb[k] = cr[k] * bv[k];
+          vec_mul_tail<K, PK>(cb, bv, cr);
         }
-        seq_mat_vec<K>(T.A, cb, nb);
+        mat_vec_unit<K, PK>(T.A, cb, nb);
         if (STATS) {
           const bool prev_obs = (j > 0) ? cur.observed(j > 0 ? j - 1 : 0) : prev_obs0;
           const bool valid = m && prev_obs && !at_start;
@@ -796,30 +719,25 @@ __device__ __forceinline__ void seq_backward_body(const FbTables<K>& tab0, const
 #pragma unroll
           for (int i = 0; i < K; ++i) s2 = fmaf(alp[i], nb[i], s2);
           const float r2 = valid ? rcp_approx(s2) : 0.0f;
-          if constexpr (STATS && (K == 2 || K == 4)) {
+          if constexpr (STATS) {
             float ai[K];
 #pragma unroll
             for (int i = 0; i < K; ++i) ai[i] = alp[i];
-            seq_vec_scale<K>(ai, r2);
-#pragma unroll
-            for (int i = 0; i < K; ++i)
-#pragma unroll
-              for (int jj = 0; jj < K; jj += 2)
-                fma2f(acc_xi[i * K + jj], acc_xi[i * K + jj + 1], ai[i], ai[i], cb[jj], cb[jj + 1], acc_xi[i * K + jj],
-                      acc_xi[i * K + jj + 1]);
-          } else {
+            vec_scale<K, PK>(ai, r2);
 #pragma unroll
             for (int i = 0; i < K; ++i) {
-              const float ai = alp[i] * r2;
+              float row[K];
 #pragma unroll
-              for (int jj = 0; jj < K; ++jj)
-                acc_xi[STATS ? i * K + jj : 0] = fmaf(ai, cb[jj], acc_xi[STATS ? i * K + jj : 0]);
+              for (int jj = 0; jj < K; ++jj) row[jj] = acc_xi[i * K + jj];
+              vec_fma_s<K, PK>(row, ai[i], cb);
+#pragma unroll
+              for (int jj = 0; jj < K; ++jj) acc_xi[i * K + jj] = row[jj];
             }
           }
         }
         if ((j & 3) == 0) {
           const float sc = pow2_rescale_noexp(vec_max<K>(nb));
-          seq_vec_scale<K>(nb, sc);
+          vec_scale<K, PK>(nb, sc);
         }
 #pragma unroll
         for (int k = 0; k < K; ++k) {

@@ -127,14 +127,37 @@ __global__ void __launch_bounds__(kShortWarps * 32, 4) short_kernel(const __grid
   for (int i = 0; i < K; ++i)
 #pragma unroll
     for (int j = 0; j < K; ++j) A[i][j] = tab.Ap[i][j];
+  // packed fp32x2 (f32x2.cuh) for K >= 3; K = 2 measured 2-5 % slower with it here (profiles/r02_policy_audit4.txt)
   auto vecA = [&](const float (&x)[K], float (&y)[K]) {
+    if constexpr (K >= 3) {
+      vec_mat_unit<K>(x, A, y);
+    } else {
 #pragma unroll
-    for (int j = 0; j < K; ++j) {
-      float s = x[j];
+      for (int j = 0; j < K; ++j) {
+        float s = x[j];
 #pragma unroll
-      for (int i = 0; i < K; ++i)
-        if (i != j) s = fmaf(x[i], A[i][j], s);
-      y[j] = s;
+        for (int i = 0; i < K; ++i)
+          if (i != j) s = fmaf(x[i], A[i][j], s);
+        y[j] = s;
+      }
+    }
+  };
+  auto tailAvec = [&](const float (&bvv)[K], const float (&c)[K], float (&cb)[K], float (&nb)[K]) {
+    if constexpr (K >= 3) {
+      vec_mul_tail<K>(cb, bvv, c);
+      mat_vec_unit<K>(A, cb, nb);
+    } else {
+      cb[0] = bvv[0];
+#pragma unroll
+      for (int k = 1; k < K; ++k) cb[k] = c[k] * bvv[k];
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        float s = cb[i];
+#pragma unroll
+        for (int jj = 0; jj < K; ++jj)
+          if (jj != i) s = fmaf(A[i][jj], cb[jj], s);
+        nb[i] = s;
+      }
     }
   };
   auto ratios = [&](float o, float (&c)[K]) {
@@ -448,17 +471,7 @@ __global__ void __launch_bounds__(kShortWarps * 32, 4) short_kernel(const __grid
         }
         if (j > 0 || STATS) {
           float cb[K], nb[K];
-          cb[0] = bv[0];
-#pragma unroll
-          for (int k = 1; k < K; ++k) cb[k] = rt[j][k] * bv[k];
-#pragma unroll
-          for (int i = 0; i < K; ++i) {
-            float s = cb[i];
-#pragma unroll
-            for (int jj = 0; jj < K; ++jj)
-              if (jj != i) s = fmaf(A[i][jj], cb[jj], s);
-            nb[i] = s;
-          }
+          tailAvec(bv, rt[j], cb, nb);
           if (STATS) {
             // xi_{t-1}(i,jj) ~ alpha_{t-1}(i) Ap[i][jj] cb[jj], t = t0 + j > 0, both ends observed
             float alp[K];
@@ -608,17 +621,7 @@ __global__ void __launch_bounds__(kShortWarps * 32, 4) short_kernel(const __grid
         }
         if (j > 0) {
           float cb[K], nb[K];
-          cb[0] = bv[0];
-#pragma unroll
-          for (int k = 1; k < K; ++k) cb[k] = cr[k] * bv[k];
-#pragma unroll
-          for (int i = 0; i < K; ++i) {
-            float s = cb[i];
-#pragma unroll
-            for (int jj = 0; jj < K; ++jj)
-              if (jj != i) s = fmaf(A[i][jj], cb[jj], s);
-            nb[i] = s;
-          }
+          tailAvec(bv, cr, cb, nb);
           if (((mylen - 1 - j) & 3) == 3) {
             const float sc = pow2_rescale_noexp(vec_max<K>(nb));
 #pragma unroll
