@@ -430,7 +430,12 @@ constexpr int seq_bwd_min_blocks(int K, size_t obs_size, int mode) {
   // posterior decode of float rows, K <= 3: one CTA fewer (128 registers), so that the chunk-ahead observation
   // loads stay in registers (K = 3, 100,000 x 5 kb: 4.27 -> 3.37 ms); K = 4 measured mixed with 3 CTAs and keeps 4
   if (mode == 1 && obs_size > 1 && K < 4) return 4;
-  return K == 4 ? 4 : 5;
+  // K = 4 E-step on uint8-coded rows: the packed fp32x2 code fits 96 registers without spilling, so a fifth CTA
+  // is resident (the kernel is latency-bound at 16 warps per SM: 61 % issue, 54 % of the FMA pipe); float rows
+  // would spill 24-184 bytes and keep four
+  if (K == 4) return (mode == 0 && obs_size == 1) ? 5 : 4;
+  if (K == 2 && mode == 0 && obs_size == 1) return 6;  // 80 registers without spilling (float rows: 24-32 bytes)
+  return 5;
 }
 
 // -----------------------------------------------------------------------------------------------------
