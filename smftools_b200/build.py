@@ -19,7 +19,7 @@ OBJ = os.path.join(HERE, "build")
 OUT = os.path.join(HERE, "libsmfhmm.so")
 SOURCES = (["api.cu", "host_io.cu", "reduce_kernels.cu"] + [f"{fam}_k{k}.cu" for fam in ("fb2", "fb", "vit") for k in (2, 3, 4)]
            + [f"fb2w_k{k}.cu" for k in (2, 3, 4)] + [f"short_k{k}.cu" for k in (2, 3, 4)] + [f"seq_k{k}.cu" for k in (2, 3, 4)] + ["fb2x_k2.cu", "fb2x_k3.cu", "fb2y_k2.cu", "fb2m_k2.cu", "fb2m_k3.cu", "fb2b_k2.cu", "fb2b_k3.cu"])
-HEADERS = ["seq_kernel.cuh", "seq_launch.inc", "post_sweep_kernel.cuh", "short_kernel.cuh", "short_launch.inc", "sweep_kernel.cuh", "hmm_common.cuh", "fb_kernel.cuh", "fb2_kernel.cuh", "viterbi_kernel.cuh", "features_kernel.cuh",
+HEADERS = ["f32x2.cuh", "seq_kernel.cuh", "seq_launch.inc", "post_sweep_kernel.cuh", "short_kernel.cuh", "short_launch.inc", "sweep_kernel.cuh", "hmm_common.cuh", "fb_kernel.cuh", "fb2_kernel.cuh", "viterbi_kernel.cuh", "features_kernel.cuh",
            "walk_kernel.cuh", "launch.h", "fb2_launch.inc", "fb2m_launch.inc", "fb2b_launch.inc", "fb2w_launch.inc", "fb_launch.inc", "vit_launch.inc"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
