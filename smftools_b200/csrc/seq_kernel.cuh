@@ -147,12 +147,13 @@ struct SeqEmit<K, unsigned char> {
   __device__ __forceinline__ void get(const SeqChunk<unsigned char>& ch, int j, float (&c)[K], bool& m, float& om) const {
     const unsigned code = ch.code(j);
     const float4 r = tab4[min(code, 2u)];
-    c[0] = 1.0f;
+    c[0] = r.x;  // == 1, taken from the row so that (c_0, c_1) arrives as a register pair (f32x2.cuh)
     c[1] = r.y;
     if (K > 2) c[2 % K] = r.z;
     if (K > 3) c[3 % K] = r.w;
     m = code < 2u;
-    om = code == 1u ? 1.0f : 0.0f;
+    // K <= 3: the row's last slot carries the observation value (0 / 1 / 0 for missing)
+    om = (K == 4) ? (code == 1u ? 1.0f : 0.0f) : r.w;
   }
 };
 
@@ -180,6 +181,7 @@ __device__ __forceinline__ void seq_emit_init(const FbTables<K>& tab, SeqEmit<K,
         const float x = threadIdx.x == 0 ? tab.rl0p[k] : (threadIdx.x == 1 ? tab.rl0p[k] + tab.rdl[k][0] : tab.rmiss[k]);
         r[k] = exp2f(x);
       }
+      if (K < 4) r[3] = (threadIdx.x == 1) ? 1.0f : 0.0f;  // observation value of the code (SeqEmit::get)
       s_tab[threadIdx.x] = make_float4(r[0], r[1], r[2], r[3]);
     }
     em.tab4 = s_tab;
@@ -241,11 +243,9 @@ __device__ __forceinline__ void seq_fwd_step(float (&al)[K], const float (&A)[K]
   vec_mat_unit<K, PK>(al, A, y);
 #pragma unroll
   for (int k = 0; k < K; ++k) y[k] = no_trans ? al[k] : y[k];
-  if constexpr (PK && K == 4) {
-    mul2f(y[0], y[1], y[0], y[1], c[0], c[1]);  // c[0] == 1: exact
-    mul2f(y[2], y[3], y[2], y[3], c[2], c[3]);
-#pragma unroll
-    for (int k = 0; k < K; ++k) al[k] = y[k];
+  if constexpr (PK && (K == 4 || K == 2)) {
+    // whole pairs, c[0] == 1 (exact): a multiply of ONE lane would make ptxas re-assemble the pair with moves
+    vec_mul<K, PK>(al, y, c);
   } else {
     vec_mul_tail<K, PK>(al, y, c);
   }
@@ -711,7 +711,7 @@ __device__ __forceinline__ void seq_backward_body(const FbTables<K>& tab0, const
           for (int k = 0; k < K; ++k) acc_start[STATS ? k : 0] += gk[k] * g0;
         }
         float cb[K], nb[K];
-        if constexpr (PK && K == 4) {
+        if constexpr (PK && (K == 4 || K == 2)) {
           vec_mul<K, PK>(cb, cr, bv);  // cr[0] == 1: exact
         } else {
           vec_mul_tail<K, PK>(cb, bv, cr);
