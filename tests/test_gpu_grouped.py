@@ -342,3 +342,32 @@ def test_one_launch_fit_loop_single_small_group_matches_oracle():
     q = params_of_model(m)
     assert np.abs(q.emission - ref.emission).max() <= 1e-4
     assert np.abs(q.trans - ref.trans).max() <= 1e-4
+
+
+def test_one_launch_fit_loop_with_several_resident_ctas_per_sm():
+    """~330 work items: more CTAs than SMs, so the grid barrier runs with several resident CTAs per SM."""
+    from smftools_b200 import engine
+
+    K = 2
+    shapes = [(30000, 64), (12000, 48), (257, 160)]
+    gs = [(O.synth_reads(N, L, K, 900 + g, prob=False, nan_rate=0.3), _perturbed(K, g)) for g, (N, L) in enumerate(shapes)]
+    obs = [S.CodedU8(_code(X)) for X, _ in gs]
+    out = []
+    try:
+        for mode in (1, 0):
+            engine.set_option("fitloop", mode)
+            models = [model_from_params(p) for _, p in gs]
+            hists = grouped.fit_groups(models, obs, max_iter=8, tol=0.0)
+            torch.cuda.synchronize()
+            out.append((models, hists))
+    finally:
+        engine.set_option("fitloop", 1)
+    (m1, h1), (m0, h0) = out
+    for a, b, ha, hb in zip(m1, m0, h1, h0):
+        np.testing.assert_array_equal(np.asarray(ha), np.asarray(hb))
+        for name in ("start", "trans", "emission"):
+            assert torch.equal(getattr(a, name), getattr(b, name)), name
+    # and against the oracle on the small group
+    X, p = gs[2]
+    ref, ref_hist = O.fit(X.astype(np.float64), p, max_iter=8, tol=0.0)
+    np.testing.assert_allclose(np.asarray(h1[2]), np.asarray(ref_hist), rtol=1e-6)
