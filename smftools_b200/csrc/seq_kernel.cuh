@@ -432,7 +432,7 @@ constexpr int seq_bwd_min_blocks(int K, size_t obs_size, int mode) {
   if (mode == 1 && obs_size > 1 && K < 4) return 4;
   // K = 4 E-step on uint8-coded rows: the packed fp32x2 code fits 96 registers without spilling, so a fifth CTA
   // is resident (the kernel is latency-bound at 16 warps per SM: 61 % issue, 54 % of the FMA pipe); float rows
-  // would spill 24-184 bytes and keep four
+  // spill 24-184 bytes at that cap and measured slower with it (262,144 x 8 kb: 11.7 vs 10.8 ms), so they keep four
   if (K == 4) return (mode == 0 && obs_size == 1) ? 5 : 4;
   if (K == 2 && mode == 0 && obs_size == 1) return 6;  // 80 registers without spilling (float rows: 24-32 bytes)
   return 5;
