@@ -111,13 +111,15 @@ def test_seq_posterior_matches_oracle(K, L, N, prob, force_seq):
         assert (gam0 - gam).abs().max().item() <= 4e-6
 
 
-def test_seq_posterior_is_the_policy_for_large_k4_batches():
-    """49,152 replicated reads x 512 positions, K = 4: the default policy decodes on the sequential kernels (the
-    library asks for the checkpoint workspace); every replica must get the oracle's posterior of its base read."""
+@pytest.mark.parametrize("reps", [1024, 1400])
+def test_seq_posterior_is_the_policy_for_large_k4_batches(reps):
+    """49,152 / 67,200 replicated reads x 512 positions, K = 4: the default policy decodes on the sequential kernels
+    (the library asks for the checkpoint workspace); every replica must get the oracle's posterior of its base read.
+    (two batch sizes: 384 and 525 work items)"""
     from helpers import assert_states_match_up_to_ties
     from smftools_b200 import _lib, engine
 
-    K, L, base_n, reps = 4, 512, 48, 1024
+    K, L, base_n = 4, 512, 48
     dev = torch.device("cuda")
     p = O.synth_params(K)
     tables = model_from_params(p)._host_tables()
