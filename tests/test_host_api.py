@@ -228,6 +228,26 @@ def test_tuning_options_and_workspace_policy():
         assert lib.smf_hmm_set_option(b"seq", -1) == _lib.SMF_OK
 
 
+def test_every_option_key_is_documented_in_the_header():
+    """Each key smf_hmm_set_option accepts (csrc/api.cu) is described in include/smf_hmm.h, and bad values are refused."""
+    import os
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    api = open(os.path.join(root, "smftools_b200", "csrc", "api.cu")).read()
+    body = api[api.index("int smf_hmm_set_option("):]
+    body = body[:body.index("\n}\n")]
+    keys = re.findall(r'strcmp\(key, "([a-z_]+)"\)', body)
+    assert {"walk", "short", "seq", "vit", "generic", "fitloop"} <= set(keys)
+    header = open(os.path.join(root, "include", "smf_hmm.h")).read()
+    for k in keys:
+        assert f'"{k}"' in header, f"option {k} is not documented in include/smf_hmm.h"
+    lib = _lib.load()
+    assert lib.smf_hmm_set_option(b"fitloop", 2) == _lib.SMF_ERR_BAD_ARG
+    assert lib.smf_hmm_set_option(b"fitloop", 0) == _lib.SMF_OK
+    assert lib.smf_hmm_set_option(b"fitloop", 1) == _lib.SMF_OK
+
+
 def test_log_tables_are_the_reference_expressions():
     m = S.create_hmm({"hmm_n_states": 2, "hmm_init_emission_probs": [0.9, 0.07]}, arch="single")
     t = m._host_tables()
